@@ -1,0 +1,169 @@
+"""ctypes binding of libfofb200.so (include/fofb.h).  There is no CPU fallback: if the CUDA library
+is missing or no B200 is visible, every compute entry point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfofb200.so")
+
+
+class FofbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libfofb200 error {code}: {message}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """fofb_params (include/fofb.h) == params.py:16-27 + inlined magic numbers."""
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("H0", C.c_double), ("Om0", C.c_double), ("Ode0", C.c_double),
+        ("max_velocity", C.c_double),
+        ("linking_length_factor", C.c_double),
+        ("virial_radius", C.c_double),
+        ("overdensity", C.c_double),
+        ("count_radius", C.c_double),
+        ("bcg_fraction", C.c_double),
+        ("survey_area", C.c_double),
+        ("richness", C.c_int32),
+        ("min_window", C.c_int32),
+        ("min_count", C.c_int32),
+        ("min_virial", C.c_int32),
+        ("n_random", C.c_int32),
+        ("n_bins", C.c_int32),
+        ("grid_cells", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class Matrix(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int32), ("mem", C.c_int32),
+                ("row_stride", C.c_int64), ("col_stride", C.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is ``python -m fof_b200.build`` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m fof_b200.build` (nvcc, sm_100a). "
+                          "fof_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    sigs = {
+        "fofb_abi_version": (C.c_int, []),
+        "fofb_build_info": (C.c_char_p, []),
+        "fofb_params_default": (C.c_int, [P(Params)]),
+        "fofb_create": (C.c_int, [C.c_int, P(vp)]),
+        "fofb_destroy": (None, [vp]),
+        "fofb_last_error": (C.c_char_p, [vp]),
+        "fofb_synchronize": (C.c_int, [vp]),
+        "fofb_last_timing": (C.c_int, [vp, P(dbl), P(i64)]),
+        "fofb_comoving_distance": (C.c_int, [P(Params), i64, vp, vp]),
+        "fofb_angular_diameter_distance": (C.c_int, [P(Params), i64, vp, vp]),
+        "fofb_linear_to_angular_dist": (C.c_int, [P(Params), dbl, i64, vp, vp]),
+        "fofb_mean_separation": (C.c_int, [P(Params), dbl, dbl, P(dbl)]),
+        "fofb_redshift_to_velocity": (C.c_int, [i64, vp, dbl, vp]),
+        "fofb_number_counts": (C.c_int, [vp, P(Params), P(Matrix), vp, i32, P(i64)]),
+        "fofb_candidate_order": (C.c_int, [vp, vp, i32, i64]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.fofb_abi_version() != 1:
+        raise ImportError("libfofb200.so ABI version mismatch; rebuild with `python -m fof_b200.build -f`")
+    _lib = lib
+    return lib
+
+
+def default_params(**overrides):
+    p = Params()
+    load().fofb_params_default(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"fofb_params has no field {k!r}")
+        setattr(p, k, v)
+    return p
+
+
+def matrix_of(arr):
+    """Describe a 2-D float64 numpy array (any strides >= 0) or a torch CUDA tensor to the C ABI."""
+    if hasattr(arr, "data_ptr"):  # torch tensor
+        if arr.dtype.__str__() != "torch.float64" or arr.dim() != 2:
+            raise TypeError("device matrices must be 2-D float64 tensors")
+        mem = 1 if arr.is_cuda else 0
+        return Matrix(arr.data_ptr(), arr.shape[0], arr.shape[1], mem, arr.stride(0), arr.stride(1)), arr
+    a = np.asarray(arr)
+    if a.dtype != np.float64 or a.ndim != 2:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.ndim != 2:
+            raise TypeError("expected a 2-D array")
+    rs, cs = a.strides[0] // 8, a.strides[1] // 8
+    if a.strides[0] % 8 or a.strides[1] % 8 or rs < 0 or cs < 0:
+        a = np.ascontiguousarray(a)
+        rs, cs = a.strides[0] // 8, a.strides[1] // 8
+    return Matrix(a.ctypes.data, a.shape[0], a.shape[1], 0, rs, cs), a
+
+
+class Handle:
+    """One fofb_handle bound to one CUDA device."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.fofb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise FofbError(rc, self.lib.fofb_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != 0:
+            raise FofbError(rc, self.lib.fofb_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fofb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_timing(self):
+        ms, k = C.c_double(), C.c_int64()
+        self.lib.fofb_last_timing(self.h, C.byref(ms), C.byref(k))
+        return ms.value, k.value
+
+    # ---- stage 0 -----------------------------------------------------------------------------
+    def number_counts(self, galaxies, params):
+        """N(0.5) per row (int32, host) and the candidate rows sorted by (N desc, row desc)."""
+        m, keep = matrix_of(galaxies)
+        n = m.rows
+        N = np.empty(n, dtype=np.int32)
+        ncand = C.c_int64()
+        self.check(self.lib.fofb_number_counts(self.h, C.byref(params), C.byref(m), N.ctypes.data, 0, C.byref(ncand)))
+        rows = np.empty(ncand.value, dtype=np.int32)
+        self.check(self.lib.fofb_candidate_order(self.h, rows.ctypes.data, 0, rows.size))
+        del keep
+        return N, rows
+
+
+_default_handles = {}
+
+
+def get_handle(device=0):
+    h = _default_handles.get(device)
+    if h is None:
+        h = _default_handles[device] = Handle(device)
+    return h

@@ -1,0 +1,280 @@
+// extern "C" surface of libfofb200 (include/fofb.h).  Exceptions stop here.
+#include <cstring>
+#include <new>
+
+#include "catalog_host.cuh"
+#include "stage0.cuh"
+
+namespace fofb {
+
+struct Stage0Holder {
+  Catalog cat;
+  Stage0 s0;
+};
+
+Cosmo host_cosmo_with(const fofb_params& p, std::vector<double>& table) {
+  table.resize(kCosmoTableSize);
+  cosmo_build_table(p.Om0, p.Ode0, table.data());
+  Cosmo c{};
+  c.H0 = p.H0; c.Om0 = p.Om0; c.Ode0 = p.Ode0; c.Ok0 = 1.0 - p.Om0 - p.Ode0;
+  c.h = p.H0 / 100.0; c.DH = kCkms / p.H0;
+  c.zmax = (double)(kCosmoTableSize - 1) / kCosmoPanelsPerUnit;
+  c.table = table.data();
+  return c;
+}
+
+Cosmo device_cosmo(fofb_handle* h, const fofb_params& p) {
+  if (h->cosmo_key[0] != p.Om0 || h->cosmo_key[1] != p.Ode0 || !h->cosmo_table.p) {
+    std::vector<double> t;
+    host_cosmo_with(p, t);
+    double* d = h->cosmo_table.alloc(kCosmoTableSize);
+    FOFB_CUDA(cudaMemcpyAsync(d, t.data(), sizeof(double) * kCosmoTableSize, cudaMemcpyHostToDevice, h->stream));
+    FOFB_CUDA(cudaStreamSynchronize(h->stream));
+    h->cosmo_key[0] = p.Om0;
+    h->cosmo_key[1] = p.Ode0;
+  }
+  std::vector<double> unused;
+  Cosmo c{};
+  c.H0 = p.H0; c.Om0 = p.Om0; c.Ode0 = p.Ode0; c.Ok0 = 1.0 - p.Om0 - p.Ode0;
+  c.h = p.H0 / 100.0; c.DH = kCkms / p.H0;
+  c.zmax = (double)(kCosmoTableSize - 1) / kCosmoPanelsPerUnit;
+  c.table = h->cosmo_table.p;
+  return c;
+}
+
+View to_device(fofb_handle* h, const fofb_matrix& m, DBuf<double>& staging) {
+  FOFB_REQUIRE(m.data != nullptr && m.rows >= 0 && m.cols > 0, "matrix: null data or bad shape");
+  FOFB_REQUIRE(m.row_stride >= 0 && m.col_stride >= 0, "matrix: negative strides are not supported");
+  View v;
+  v.rows = m.rows; v.cols = m.cols; v.rs = m.row_stride; v.cs = m.col_stride;
+  if (m.mem == 1) {
+    v.data = m.data;
+    return v;
+  }
+  FOFB_REQUIRE(m.mem == 0, "matrix: mem must be 0 (host) or 1 (device)");
+  const size_t extent = m.rows > 0 ? (size_t)((m.rows - 1) * m.row_stride + (m.cols - 1) * m.col_stride + 1) : 0;
+  double* d = staging.alloc(extent ? extent : 1);
+  if (extent) FOFB_CUDA(cudaMemcpyAsync(d, m.data, extent * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  v.data = d;
+  return v;
+}
+
+static void check_params(const fofb_params* p) {
+  FOFB_REQUIRE(p != nullptr, "params is null");
+  FOFB_REQUIRE(p->struct_size == sizeof(fofb_params), "params.struct_size does not match this library (ABI mismatch)");
+  FOFB_REQUIRE(p->H0 > 0 && p->Om0 > 0 && p->max_velocity >= 0, "params: H0, Om0 must be positive, max_velocity >= 0");
+  FOFB_REQUIRE(p->grid_cells >= 1 && p->grid_cells <= 32768, "params: grid_cells out of range");
+  FOFB_REQUIRE(p->count_radius > 0 && p->virial_radius > 0, "params: radii must be positive");
+}
+
+struct Timed {  // CUDA-event bracket around one compute call
+  fofb_handle* h;
+  explicit Timed(fofb_handle* h_) : h(h_) {
+    h->launches = 0;
+    cudaEventRecord(h->ev0, h->stream);
+  }
+  void stop() {
+    cudaEventRecord(h->ev1, h->stream);
+    cudaEventSynchronize(h->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_ms = ms;
+  }
+};
+
+}  // namespace fofb
+
+using namespace fofb;
+
+#define FOFB_TRY(h) try {
+#define FOFB_CATCH(h)                                              \
+  }                                                                \
+  catch (const fofb::Error& e) {                                   \
+    if (h) (h)->last_error = e.what();                             \
+    return e.code;                                                 \
+  }                                                                \
+  catch (const std::bad_alloc&) {                                  \
+    if (h) (h)->last_error = "host allocation failed";             \
+    return FOFB_ERR_INTERNAL;                                      \
+  }                                                                \
+  catch (const std::exception& e) {                                \
+    if (h) (h)->last_error = std::string("internal: ") + e.what(); \
+    return FOFB_ERR_INTERNAL;                                      \
+  }
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+int fofb_abi_version(void) { return FOFB_ABI_VERSION; }
+
+const char* fofb_build_info(void) { return "libfofb200 sm_100a " __DATE__ " " __TIME__; }
+
+int fofb_params_default(fofb_params* p) {
+  if (!p) return FOFB_ERR_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->struct_size = sizeof(fofb_params);
+  p->H0 = 70.0; p->Om0 = 0.3; p->Ode0 = 0.7;
+  p->max_velocity = 2000.0;
+  p->linking_length_factor = 0.2;
+  p->virial_radius = 1.5;
+  p->overdensity = 2.0;
+  p->count_radius = 0.5;
+  p->bcg_fraction = 0.25;
+  p->survey_area = 1.7;
+  p->richness = 12;
+  p->min_window = 8; p->min_count = 8; p->min_virial = 12;
+  p->n_random = 300; p->n_bins = 10; p->grid_cells = 64;
+  return FOFB_OK;
+}
+
+int fofb_create(int device, fofb_handle** out) {
+  if (!out) return FOFB_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    g_create_error = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range") +
+                     "); libfofb200 has no CPU fallback";
+    return FOFB_ERR_NO_DEVICE;
+  }
+  fofb_handle* h = new (std::nothrow) fofb_handle();
+  if (!h) return FOFB_ERR_INTERNAL;
+  FOFB_TRY(h)
+  h->device = device;
+  FOFB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FOFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  FOFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  FOFB_CUDA(cudaEventCreate(&h->ev0));
+  FOFB_CUDA(cudaEventCreate(&h->ev1));
+  *out = h;
+  return FOFB_OK;
+  }
+  catch (const fofb::Error& err) {
+    g_create_error = err.what();
+    delete h;
+    return err.code;
+  }
+}
+
+void fofb_destroy(fofb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete reinterpret_cast<Stage0Holder*>(h->catalog);
+  h->catalog = nullptr;
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* fofb_last_error(const fofb_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int fofb_synchronize(fofb_handle* h) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  FOFB_CUDA(cudaSetDevice(h->device));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_last_timing(const fofb_handle* h, double* device_ms, int64_t* kernel_launches) {
+  if (!h) return FOFB_ERR_INVALID;
+  if (device_ms) *device_ms = h->last_ms;
+  if (kernel_launches) *kernel_launches = h->launches;
+  return FOFB_OK;
+}
+
+// ---- host scalar helpers ------------------------------------------------------------------------
+int fofb_comoving_distance(const fofb_params* p, int64_t n, const double* z, double* out) {
+  fofb_handle* h = nullptr;
+  FOFB_TRY(h)
+  check_params(p);
+  std::vector<double> t;
+  const Cosmo c = host_cosmo_with(*p, t);
+  for (int64_t i = 0; i < n; ++i) out[i] = cosmo_comoving_distance(c, z[i]);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_angular_diameter_distance(const fofb_params* p, int64_t n, const double* z, double* out) {
+  fofb_handle* h = nullptr;
+  FOFB_TRY(h)
+  check_params(p);
+  std::vector<double> t;
+  const Cosmo c = host_cosmo_with(*p, t);
+  for (int64_t i = 0; i < n; ++i) out[i] = cosmo_angular_diameter_distance(c, z[i]);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_linear_to_angular_dist(const fofb_params* p, double distance_mpc_h, int64_t n, const double* z, double* out) {
+  fofb_handle* h = nullptr;
+  FOFB_TRY(h)
+  check_params(p);
+  std::vector<double> t;
+  const Cosmo c = host_cosmo_with(*p, t);
+  for (int64_t i = 0; i < n; ++i) out[i] = cosmo_linear_to_angular_dist(c, distance_mpc_h, z[i]);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_mean_separation(const fofb_params* p, double n_objects, double z, double* out) {
+  fofb_handle* h = nullptr;
+  FOFB_TRY(h)
+  check_params(p);
+  std::vector<double> t;
+  const Cosmo c = host_cosmo_with(*p, t);
+  *out = cosmo_mean_separation(c, n_objects, z, p->max_velocity, p->survey_area);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_redshift_to_velocity(int64_t n, const double* z, double center_z, double* out) {
+  if (!z || !out) return FOFB_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i) out[i] = fofb::redshift_to_velocity(z[i], center_z);
+  return FOFB_OK;
+}
+
+// ---- stage 0 ------------------------------------------------------------------------------------------
+int fofb_number_counts(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, int32_t* N_out,
+                       int32_t N_mem, int64_t* n_candidates) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(galaxies && N_out, "galaxies / N_out is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->catalog) h->catalog = reinterpret_cast<Catalog*>(new Stage0Holder());
+  Stage0Holder* s = reinterpret_cast<Stage0Holder*>(h->catalog);
+  s->s0.valid = false;
+  Timed timer(h);
+  const View v = to_device(h, *galaxies, h->upload);
+  s->cat.build(h, v);
+  s->s0.run(h, *p, s->cat);
+  FOFB_CUDA(cudaMemcpyAsync(N_out, s->s0.N_row.p, sizeof(int32_t) * s->cat.n,
+                            N_mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  timer.stop();
+  if (n_candidates) *n_candidates = s->s0.n_candidates;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_candidate_order(fofb_handle* h, int32_t* rows_out, int32_t rows_mem, int64_t capacity) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Stage0Holder* s = reinterpret_cast<Stage0Holder*>(h->catalog);
+  if (!s || !s->s0.valid) throw fofb::Error(FOFB_ERR_STATE, "fofb_candidate_order called before fofb_number_counts");
+  FOFB_REQUIRE(rows_out && capacity >= s->s0.n_candidates, "rows_out too small");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (s->s0.n_candidates > 0)
+    FOFB_CUDA(cudaMemcpyAsync(rows_out, s->s0.cand_rows.p, sizeof(int32_t) * s->s0.n_candidates,
+                              rows_mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+}  // extern "C"

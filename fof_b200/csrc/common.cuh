@@ -1,0 +1,134 @@
+// Shared plumbing of libfofb200: error handling, grow-only device buffers, the handle.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fofb.h"
+#include "cosmo.cuh"
+
+namespace fofb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define FOFB_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw ::fofb::Error(FOFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +   \
+                                             " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+#define FOFB_REQUIRE(cond, msg)                                           \
+  do {                                                                    \
+    if (!(cond)) throw ::fofb::Error(FOFB_ERR_INVALID, std::string(msg)); \
+  } while (0)
+
+// Grow-only device buffer: benchmark steps and repeated API calls reuse the allocation.
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  T* alloc(size_t n) {
+    if (n > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = 0;
+      size_t want = n + n / 8 + 64;
+      FOFB_CUDA(cudaMalloc(&p, want * sizeof(T)));
+      cap = want;
+    }
+    return p;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  ~DBuf() { release(); }
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+};
+
+// Pinned host staging buffer (grow-only) for small device->host result reads.
+template <class T>
+struct HBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  T* alloc(size_t n) {
+    if (n > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      size_t want = n + n / 8 + 64;
+      FOFB_CUDA(cudaMallocHost(&p, want * sizeof(T)));
+      cap = want;
+    }
+    return p;
+  }
+  ~HBuf() {
+    if (p) cudaFreeHost(p);
+  }
+};
+
+struct View {  // strided float64 matrix resident on the device
+  const double* data = nullptr;
+  int64_t rows = 0;
+  int32_t cols = 0;
+  int64_t rs = 0, cs = 0;
+  __host__ __device__ __forceinline__ double at(int64_t i, int c) const { return data[i * rs + c * cs]; }
+};
+
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+struct Catalog;    // catalog.cu
+struct FofState;   // fof_stage.cu
+struct CleanState; // clean.cu
+
+}  // namespace fofb
+
+struct fofb_handle {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string last_error;
+  double last_ms = 0.0;
+  int64_t launches = 0;       // kernels launched by the current/last compute call
+  fofb::DBuf<double> cosmo_table;
+  double cosmo_key[2] = {-1.0, -1.0};
+  fofb::Catalog* catalog = nullptr;
+  fofb::FofState* fof = nullptr;
+  fofb::CleanState* clean = nullptr;
+  fofb::DBuf<unsigned char> cub_tmp;
+  fofb::DBuf<double> upload;      // staging for host matrices
+  fofb::DBuf<double> upload2;
+  fofb::HBuf<int64_t> pinned_i64;
+};
+
+namespace fofb {
+
+// Device cosmology for the given parameters (table uploaded once per (Om0, Ode0)).
+Cosmo device_cosmo(fofb_handle* h, const fofb_params& p);
+Cosmo host_cosmo(const fofb_params& p);
+
+// Bring a caller matrix onto the device (copying the underlying block if it lives on the host).
+View to_device(fofb_handle* h, const fofb_matrix& m, DBuf<double>& staging);
+
+inline void count_launch(fofb_handle* h, int k = 1) { h->launches += k; }
+
+#define FOFB_LAUNCH_CHECK(h)          \
+  do {                                \
+    ::fofb::count_launch(h);          \
+    FOFB_CUDA(cudaGetLastError());    \
+  } while (0)
+
+}  // namespace fofb

@@ -1,0 +1,149 @@
+// Spherical geometry and GriSPy grid predicates in fp64 (device side).
+//
+// Replaces GriSPy's haversine metric and cell-box candidate selection (call sites fof.py:177,203,
+// 209,280,337; helper.py:183,213; algorithm restated in SURVEY.md App. B.1) and astropy's
+// SkyCoord.separation (Vincenty; fof.py:429, analysis/mass_estimator.py:88).
+#pragma once
+#include "cosmo.cuh"
+
+namespace fofb {
+
+// ---- GriSPy haversine, literal association (degrees in, degrees out) ---------------------------
+// numpy evaluates  sdlat**2 + (clat1*clat2)*(sdlon**2)  with separate roundings; the explicit _rn
+// intrinsics keep nvcc from contracting them into FMAs.
+__device__ __forceinline__ double haversine_a_literal(double ra1, double dec1, double cosdec1, double ra2,
+                                                      double dec2, double cosdec2) {
+  const double lon1 = __dmul_rn(ra1, kDeg2Rad), lat1 = __dmul_rn(dec1, kDeg2Rad);
+  const double lon2 = __dmul_rn(ra2, kDeg2Rad), lat2 = __dmul_rn(dec2, kDeg2Rad);
+  const double sdlon = sin(__dmul_rn(__dsub_rn(lon2, lon1), 0.5));
+  const double sdlat = sin(__dmul_rn(__dsub_rn(lat2, lat1), 0.5));
+  return __dadd_rn(__dmul_rn(sdlat, sdlat), __dmul_rn(__dmul_rn(cosdec1, cosdec2), __dmul_rn(sdlon, sdlon)));
+}
+
+__device__ __forceinline__ double haversine_deg_literal(double ra1, double dec1, double cosdec1, double ra2,
+                                                        double dec2, double cosdec2) {
+  const double a = haversine_a_literal(ra1, dec1, cosdec1, ra2, dec2, cosdec2);
+  return __dmul_rn(__dmul_rn(2.0, asin(sqrt(a))), kRad2Deg);
+}
+
+// sin(x) for |x| << 1 by its Taylor series (rel. error < 1e-16 for |x| < 0.02), libm otherwise
+__device__ __forceinline__ double sin_small(double x) {
+  if (fabs(x) < 0.02) {
+    const double x2 = x * x;
+    return x * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0 + x2 * (-1.0 / 5040.0 + x2 * (1.0 / 362880.0)))));
+  }
+  return sin(x);
+}
+
+// hav(c, p) <= r  decided on  a = sin^2(d/2)  against  T = sin^2(r/2); pairs closer to the threshold
+// than the guard band are re-decided with the literal degrees formula (bit-for-bit GriSPy association).
+struct BubbleTest {
+  double ra, dec, cosdec, r_deg, T_lo, T_hi;
+  __device__ __forceinline__ void init(double ra_, double dec_, double cosdec_, double r) {
+    ra = ra_; dec = dec_; cosdec = cosdec_; r_deg = r;
+    const double s = sin(0.5 * r * kDeg2Rad);
+    const double T = s * s;
+    T_lo = T * (1.0 - 1e-9);
+    T_hi = T * (1.0 + 1e-9);
+  }
+  __device__ __forceinline__ bool inside(double pra, double pdec, double pcos) const {
+    const double sl = sin_small(0.5 * kDeg2Rad * (pra - ra));
+    const double sd = sin_small(0.5 * kDeg2Rad * (pdec - dec));
+    const double a = sd * sd + cosdec * pcos * sl * sl;
+    if (a < T_lo) return true;
+    if (a > T_hi) return false;
+    return haversine_deg_literal(ra, dec, cosdec, pra, pdec, pcos) <= r_deg;
+  }
+};
+
+// ---- astropy angular_separation (Vincenty), radians ---------------------------------------------
+// num2 must be exactly 0 for identical coordinates (three_sigma's "is this the centre" test,
+// fof.py:462), hence the explicit roundings.
+__device__ __forceinline__ double vincenty_rad(double lon1, double lat1, double lon2, double lat2) {
+  double sdlon, cdlon, slat1, clat1, slat2, clat2;
+  sincos(__dsub_rn(lon2, lon1), &sdlon, &cdlon);
+  sincos(lat1, &slat1, &clat1);
+  sincos(lat2, &slat2, &clat2);
+  const double num1 = __dmul_rn(clat2, sdlon);
+  const double num2 = __dsub_rn(__dmul_rn(clat1, slat2), __dmul_rn(__dmul_rn(slat1, clat2), cdlon));
+  const double den = __dadd_rn(__dmul_rn(slat1, slat2), __dmul_rn(__dmul_rn(clat1, clat2), cdlon));
+  return atan2(hypot(num1, num2), den);
+}
+
+// ---- GriSPy grid: bins = linspace(min - 1e-6, max + 1e-6, N + 1) ----------------------------------
+struct GridAxis {
+  double b0, bN;  // bins[0], bins[-1]
+  int ncell;
+  __host__ __device__ __forceinline__ void init(double vmin, double vmax, int n) {
+    b0 = vmin - 1.0e-6;
+    bN = vmax + 1.0e-6;
+    ncell = n;
+  }
+  // int(N * (x - b0) / (bN - b0)) with C truncation, as a double (no overflow for far-away x)
+  __device__ __forceinline__ double digit(double x) const {
+    return trunc(__ddiv_rn(__dmul_rn((double)ncell, __dsub_rn(x, b0)), __dsub_rn(bN, b0)));
+  }
+  __device__ __forceinline__ int digit_clamped(double x) const {
+    double t = digit(x);
+    t = t < 0.0 ? 0.0 : t;
+    t = t > (double)(ncell - 1) ? (double)(ncell - 1) : t;
+    return (int)t;
+  }
+};
+
+// Closed interval [lo, hi] of coordinate values whose cell index lies in [ilo, ihi]
+// (ilo = clamp(digit(c - r)), ihi = clamp(digit(c + r))).  digit() is monotone, so the cell-box
+// test on a point is equivalent to lo <= x <= hi; the bounds are found by stepping single ulps
+// around the analytic cell edge until the exact predicate flips.
+__device__ __forceinline__ void grid_axis_bounds(const GridAxis& g, double c, double r, double* lo, double* hi) {
+  const int ilo = g.digit_clamped(__dsub_rn(c, r));
+  const int ihi = g.digit_clamped(__dadd_rn(c, r));
+  const double w = (g.bN - g.b0) / g.ncell;
+  if (ilo <= 0) {
+    *lo = -INFINITY;  // every member of the grid's point set has digit >= 0
+  } else {
+    double x = g.b0 + ilo * w;
+    for (int it = 0; it < 64 && g.digit(x) >= (double)ilo; ++it) x = nextafter(x, -INFINITY);
+    for (int it = 0; it < 64 && g.digit(x) < (double)ilo; ++it) x = nextafter(x, INFINITY);
+    *lo = x;
+  }
+  if (ihi >= g.ncell - 1) {
+    *hi = INFINITY;
+  } else {
+    double x = g.b0 + (ihi + 1) * w;
+    for (int it = 0; it < 64 && g.digit(x) <= (double)ihi; ++it) x = nextafter(x, INFINITY);
+    for (int it = 0; it < 64 && g.digit(x) > (double)ihi; ++it) x = nextafter(x, -INFINITY);
+    *hi = x;
+  }
+}
+
+struct Box {  // cell-box bounds of one query in raw coordinates
+  double ra_lo, ra_hi, dec_lo, dec_hi;
+  __device__ __forceinline__ bool contains(double ra, double dec) const {
+    return ra >= ra_lo && ra <= ra_hi && dec >= dec_lo && dec <= dec_hi;
+  }
+};
+
+struct BBox {  // bounding box of a point set: (ra_min, ra_max, dec_min, dec_max)
+  double ra_min, ra_max, dec_min, dec_max;
+};
+
+__device__ __forceinline__ Box grid_box(const BBox& bb, int ncell, double c_ra, double c_dec, double r) {
+  GridAxis gx, gy;
+  gx.init(bb.ra_min, bb.ra_max, ncell);
+  gy.init(bb.dec_min, bb.dec_max, ncell);
+  Box b;
+  grid_axis_bounds(gx, c_ra, r, &b.ra_lo, &b.ra_hi);
+  grid_axis_bounds(gy, c_dec, r, &b.dec_lo, &b.dec_hi);
+  return b;
+}
+
+// GriSPy cell index of a point in a grid (for the cell-major return order)
+__device__ __forceinline__ int grid_cell_key(const BBox& bb, int ncell, double ra, double dec) {
+  GridAxis gx, gy;
+  gx.init(bb.ra_min, bb.ra_max, ncell);
+  gy.init(bb.dec_min, bb.dec_max, ncell);
+  return gy.digit_clamped(dec) * ncell + gx.digit_clamped(ra);
+}
+
+}  // namespace fofb

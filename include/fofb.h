@@ -1,0 +1,110 @@
+/* fofb.h -- C ABI of the B200-native FoF cluster-finding hot path (libfofb200.so).
+ *
+ * The reference (kencx/FoF) is pure Python and has no FFI: its boundary for this path is the set
+ * of Python call signatures used by /root/reference/FoF/pipeline.py.  Each entry point below names
+ * the reference interface it stands behind; the Python facade in fof_b200/ keeps those signatures
+ * and calls these functions through ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative fofb_status on failure; nothing throws across
+ *     the ABI; fofb_last_error(h) returns the message of the last failure on that handle;
+ *   - plain pointers and sizes only; buffers are caller-owned and borrowed for the call;
+ *   - a fofb_matrix describes a strided float64 matrix in HOST (mem = 0) or DEVICE (mem = 1) memory;
+ *     the whole underlying block [data, data + extent) must be readable;
+ *   - variable-size results stay in the handle after a *_run call; the caller reads the sizes,
+ *     allocates, and copies them out with the matching *_fetch call;
+ *   - a handle is bound to one CUDA device and is not thread-safe; calls are synchronous.
+ * Column layout of galaxy / centre rows (pipeline.py:51-53 + fof.py:61):
+ *   0 ra[deg] 1 dec[deg] 2 z 3 z_lower 4 z_upper 5 RMag 6 ID 7 N(0.5)
+ */
+#ifndef FOFB_H
+#define FOFB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOFB_ABI_VERSION 1
+
+typedef enum fofb_status {
+  FOFB_OK = 0,
+  FOFB_ERR_INVALID = -1,     /* bad argument / shape / struct_size                      */
+  FOFB_ERR_CUDA = -2,        /* CUDA runtime error (message holds cudaGetErrorString)    */
+  FOFB_ERR_NO_DEVICE = -3,   /* no usable CUDA device: there is NO CPU fallback          */
+  FOFB_ERR_STATE = -4,       /* call order violated (e.g. fetch before run)              */
+  FOFB_ERR_UNSUPPORTED = -5, /* degenerate input the device path refuses (documented)    */
+  FOFB_ERR_INTERNAL = -6
+} fofb_status;
+
+typedef struct fofb_handle fofb_handle;
+
+/* params.py:16-27 plus the magic numbers inlined in fof.py / helper.py.  */
+typedef struct fofb_params {
+  size_t struct_size;            /* = sizeof(fofb_params); versioning                           */
+  double H0, Om0, Ode0;          /* params.py:16   LambdaCDM(70, 0.3, 0.7), Tcmb0 = 0           */
+  double max_velocity;           /* params.py:23   km/s                                          */
+  double linking_length_factor;  /* params.py:24   b (FoF() default 0.1, fof.py:104)             */
+  double virial_radius;          /* params.py:25   Mpc/h                                         */
+  double overdensity;            /* params.py:27   D                                             */
+  double count_radius;           /* fof.py:73,378; helper.py:212   0.5 Mpc/h                     */
+  double bcg_fraction;           /* fof.py:334     0.25                                          */
+  double survey_area;            /* fof.py:192     1.7 (used as a radius in degrees)             */
+  int32_t richness;              /* params.py:26                                                 */
+  int32_t min_window;            /* fof.py:71      8                                             */
+  int32_t min_count;             /* fof.py:77,386  8                                             */
+  int32_t min_virial;            /* fof.py:185     12                                            */
+  int32_t n_random;              /* helper.py:196  300                                           */
+  int32_t n_bins;                /* fof.py:506     10                                            */
+  int32_t grid_cells;            /* GriSPy N_cells 64                                            */
+  int32_t reserved;
+} fofb_params;
+
+typedef struct fofb_matrix {
+  const double* data;  /* element (i, c) at data[i * row_stride + c * col_stride]               */
+  int64_t rows;
+  int32_t cols;
+  int32_t mem;         /* 0 = host, 1 = device                                                  */
+  int64_t row_stride;  /* in elements                                                           */
+  int64_t col_stride;  /* in elements                                                           */
+} fofb_matrix;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int fofb_abi_version(void);
+const char* fofb_build_info(void);
+int fofb_params_default(fofb_params* p);             /* params.py defaults                       */
+int fofb_create(int device, fofb_handle** out);      /* fails with FOFB_ERR_NO_DEVICE w/o a GPU  */
+void fofb_destroy(fofb_handle* h);
+const char* fofb_last_error(const fofb_handle* h);
+int fofb_synchronize(fofb_handle* h);
+/* CUDA-event time [ms] of the kernels launched by the last compute call, and their count.    */
+int fofb_last_timing(const fofb_handle* h, double* device_ms, int64_t* kernel_launches);
+
+/* ---- host scalar helpers: analysis/methods.py (no GPU needed) ----------------------------------
+ * fofb_linear_to_angular_dist : analysis/methods.py:12-32   h^-1 Mpc (proper) at z -> degrees
+ * fofb_mean_separation        : analysis/methods.py:35-65   Mpc
+ * fofb_redshift_to_velocity   : analysis/methods.py:68-87   km/s
+ * fofb_comoving_distance / fofb_angular_diameter_distance : astropy LambdaCDM (Mpc)
+ */
+int fofb_comoving_distance(const fofb_params* p, int64_t n, const double* z, double* out);
+int fofb_angular_diameter_distance(const fofb_params* p, int64_t n, const double* z, double* out);
+int fofb_linear_to_angular_dist(const fofb_params* p, double distance_mpc_h, int64_t n, const double* z, double* out);
+int fofb_mean_separation(const fofb_params* p, double n_objects, double z, double* out);
+int fofb_redshift_to_velocity(int64_t n, const double* z, double center_z, double* out);
+
+/* ---- stage 0: candidate_center_search (fof.py:24-95) ---------------------------------------------
+ * N(0.5) for every row of `galaxies` (>= 3 columns: ra, dec, z), written to N_out[rows] (host or
+ * device pointer per N_mem) in input row order; the number of rows with N >= min_count is returned
+ * in *n_candidates.  fofb_candidate_order then writes the row indices of the candidate centres
+ * sorted by N descending, ties by descending row index (oracle pin D1 for fof.py:79-81).
+ */
+int fofb_number_counts(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies,
+                       int32_t* N_out, int32_t N_mem, int64_t* n_candidates);
+int fofb_candidate_order(fofb_handle* h, int32_t* rows_out, int32_t rows_mem, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOFB_H */
