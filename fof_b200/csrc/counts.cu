@@ -36,67 +36,48 @@ __global__ void k_count_prep(CatalogView cat, Cosmo cosmo, double count_radius, 
   theta_out[r] = theta;
 }
 
-// ---- K5: the count.  One warp per home cell; the three cell rows around it are staged through
-// shared memory in chunks; every lane owns one home galaxy and scans the staged candidates
-// (shared-memory broadcast reads), testing z-rank window -> cell box -> fp64 haversine.
-constexpr int kCountWarps = 8;
-constexpr int kCountChunk = 128;
+// ---- K5: the count.  One thread per galaxy in cell order (a warp = 32 consecutive members of one
+// or two adjacent cells, so their probes and candidate loads share L1 lines).  Cells are z-rank
+// sorted, so the velocity window is one contiguous sub-range per neighbour cell, found by binary
+// search; only in-window candidates reach the cell-box and fp64 haversine tests.
+__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int lo, int hi, int key) {
+  while (lo < hi) {
+    const int m = (lo + hi) >> 1;
+    if (__ldg(a + m) < key) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
 
-__global__ void __launch_bounds__(32 * kCountWarps) k_count(CellListView cl, const QueryRec* __restrict__ rec,
-                                                            int* __restrict__ N_row) {
-  __shared__ int s_zr[kCountWarps][kCountChunk];
-  __shared__ double s_ra[kCountWarps][kCountChunk];
-  __shared__ double s_dec[kCountWarps][kCountChunk];
-  __shared__ double s_cos[kCountWarps][kCountChunk];
-  const int lane = threadIdx.x;
-  const int w = threadIdx.y;
-  const int ncell = cl.ncx * cl.ncy;
-  for (int cell = blockIdx.x * kCountWarps + w; cell < ncell; cell += gridDim.x * kCountWarps) {
-    const int h0 = cl.cell_start[cell], h1 = cl.cell_start[cell + 1];
-    if (h0 == h1) continue;
-    const int cy = cell / cl.ncx, cx = cell - cy * cl.ncx;
+__global__ void __launch_bounds__(256) k_count(CellListView cl, int n, const QueryRec* __restrict__ rec,
+                                               int* __restrict__ N_row) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const QueryRec qr = rec[cl.zrank[q]];
+  int count = 0;
+  if (qr.whi > qr.wlo) {
+    const double ra = cl.ra[q], dec = cl.dec[q];
+    BubbleTest bt;
+    bt.init(ra, dec, cl.cosdec[q], qr.r_deg);
+    const int cx = cl.cx_of(ra), cy = cl.cy_of(dec);
     const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < cl.ncx - 1 ? cx + 1 : cl.ncx - 1;
     const int y0 = cy > 0 ? cy - 1 : 0, y1 = cy < cl.ncy - 1 ? cy + 1 : cl.ncy - 1;
-    for (int hb = h0; hb < h1; hb += 32) {
-      const int q = hb + lane;
-      const bool valid = q < h1;
-      QueryRec qr;
-      BubbleTest bt;
-      unsigned wlo = 0, wlen = 0;
-      if (valid) {
-        qr = rec[cl.zrank[q]];
-        bt.init(cl.ra[q], cl.dec[q], cl.cosdec[q], qr.r_deg);
-        wlo = (unsigned)qr.wlo;
-        wlen = (unsigned)(qr.whi - qr.wlo);
-      }
-      int count = 0;
-      for (int yy = y0; yy <= y1; ++yy) {
-        const int g0 = cl.cell_start[yy * cl.ncx + x0], g1 = cl.cell_start[yy * cl.ncx + x1 + 1];
-        for (int c0 = g0; c0 < g1; c0 += kCountChunk) {
-          const int m = min(kCountChunk, g1 - c0);
-          __syncwarp();
-          for (int j = lane; j < m; j += 32) {
-            s_zr[w][j] = cl.zrank[c0 + j];
-            s_ra[w][j] = cl.ra[c0 + j];
-            s_dec[w][j] = cl.dec[c0 + j];
-            s_cos[w][j] = cl.cosdec[c0 + j];
-          }
-          __syncwarp();
-          if (wlen) {
-            for (int j = 0; j < m; ++j) {
-              if ((unsigned)s_zr[w][j] - wlo < wlen) {
-                const double pra = s_ra[w][j], pdec = s_dec[w][j];
-                if (pra >= qr.ra_lo && pra <= qr.ra_hi && pdec >= qr.dec_lo && pdec <= qr.dec_hi &&
-                    bt.inside(pra, pdec, s_cos[w][j]))
-                  ++count;
-              }
-            }
-          }
+    for (int yy = y0; yy <= y1; ++yy) {
+      int s = __ldg(cl.cell_start + yy * cl.ncx + x0);
+      for (int xx = x0; xx <= x1; ++xx) {
+        const int e = __ldg(cl.cell_start + yy * cl.ncx + xx + 1);
+        const int a = lower_bound_i32(cl.zrank, s, e, qr.wlo);
+        const int b = lower_bound_i32(cl.zrank, a, e, qr.whi);
+        for (int j = a; j < b; ++j) {
+          const double pra = __ldg(cl.ra + j), pdec = __ldg(cl.dec + j);
+          if (pra >= qr.ra_lo && pra <= qr.ra_hi && pdec >= qr.dec_lo && pdec <= qr.dec_hi &&
+              bt.inside(pra, pdec, __ldg(cl.cosdec + j)))
+            ++count;
         }
+        s = e;
       }
-      if (valid) N_row[cl.row[q]] = count;
     }
   }
+  N_row[cl.row[q]] = count;
 }
 
 // ---- K6: candidate keys: N descending, ties by descending row (oracle pin D1 of fof.py:79-81) ----
@@ -140,9 +121,7 @@ void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat) {
   cat.build_cells(h, r_max);
   cv = cat.view();
   int* N = N_row.alloc(n);
-  const int ncell = cat.ncx * cat.ncy;
-  const int blocks = std::min((ncell + kCountWarps - 1) / kCountWarps, h->sm_count * 32);
-  k_count<<<blocks, dim3(32, kCountWarps), 0, st>>>(cv.cells, recs, N);
+  k_count<<<grid_for(n, 256), 256, 0, st>>>(cv.cells, n, recs, N);
   FOFB_LAUNCH_CHECK(h);
 
   unsigned long long* k_all = key_all.alloc(n);

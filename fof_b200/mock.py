@@ -62,11 +62,13 @@ def make_catalog(n, seed=20260101, kind="cosmos", density=50000.0, zmin=0.5, zma
     else:
         target = int(cluster_fraction * n)
         mean_rich = 0.5 * (richness_range[0] + richness_range[1])
-        n_cl = max(1, int(round(target / mean_rich))) if target > 0 else 0
+        n_cl = int(target / mean_rich * 1.3) + 8 if target > 0 else 0  # over-draw, then trim
         rich = rng.integers(richness_range[0], richness_range[1] + 1, size=n_cl)
         if n_cl:
-            # trim / pad the last cluster so members sum to the target exactly
             csum = np.cumsum(rich)
+            while csum[-1] < target:
+                rich = np.concatenate([rich, rng.integers(richness_range[0], richness_range[1] + 1, size=n_cl)])
+                csum = np.cumsum(rich)
             keep = int(np.searchsorted(csum, target, side="left")) + 1
             rich = rich[:keep]
             rich[-1] -= int(rich.sum() - target)
