@@ -73,6 +73,11 @@ def load():
         "fofb_redshift_to_velocity": (C.c_int, [i64, vp, dbl, vp]),
         "fofb_number_counts": (C.c_int, [vp, P(Params), P(Matrix), vp, i32, P(i64)]),
         "fofb_candidate_order": (C.c_int, [vp, vp, i32, i64]),
+        "fofb_fof_run": (C.c_int, [vp, P(Params), P(Matrix), P(Matrix), P(i64), vp]),
+        "fofb_fof_finish": (C.c_int, [vp, vp, vp, i32, P(i64)]),
+        "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
+        "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+        "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -157,6 +162,46 @@ class Handle:
         self.check(self.lib.fofb_candidate_order(self.h, rows.ctypes.data, 0, rows.size))
         del keep
         return N, rows
+
+
+    # ---- stages 1-4 ----------------------------------------------------------------------------
+    def fof_run(self, galaxies, centres, params):
+        """Stages 1-3. Returns (number of clusters reaching stage 4, galaxy bbox (4,))."""
+        mg, kg = matrix_of(galaxies)
+        mc, kc = matrix_of(centres)
+        k = C.c_int64()
+        bbox = np.empty(4)
+        self.check(self.lib.fofb_fof_run(self.h, C.byref(params), C.byref(mg), C.byref(mc), C.byref(k),
+                                         bbox.ctypes.data))
+        del kg, kc
+        return k.value, bbox
+
+    def fof_finish(self, rand_ra, rand_dec):
+        """Stage 4 with caller-drawn uniform points (cluster-major, n_random per cluster)."""
+        ra = np.ascontiguousarray(rand_ra, dtype=np.float64)
+        dec = np.ascontiguousarray(rand_dec, dtype=np.float64)
+        k = C.c_int64()
+        self.check(self.lib.fofb_fof_finish(self.h, ra.ctypes.data, dec.ctypes.data, 0, C.byref(k)))
+        return k.value
+
+    def fof_fetch(self, which=3):
+        """(offsets int64[K+1], members int32[total], centre int32[K], N float64[K], D float64[K])."""
+        k, t = C.c_int64(), C.c_int64()
+        self.check(self.lib.fofb_fof_sizes(self.h, which, C.byref(k), C.byref(t)))
+        K, total = k.value, t.value
+        off = np.zeros(K + 1, dtype=np.int64)
+        mem = np.empty(total, dtype=np.int32)
+        cen = np.empty(K, dtype=np.int32)
+        N = np.empty(K)
+        D = np.empty(K)
+        self.check(self.lib.fofb_fof_fetch(self.h, which, off.ctypes.data, mem.ctypes.data, cen.ctypes.data,
+                                           N.ctypes.data, D.ctypes.data))
+        return off, mem, cen, N, D
+
+    def fof_stats(self):
+        r, e = C.c_int64(), C.c_int64()
+        self.lib.fofb_fof_stats(self.h, C.byref(r), C.byref(e))
+        return r.value, e.value
 
 
 _default_handles = {}

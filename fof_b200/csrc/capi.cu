@@ -4,11 +4,13 @@
 
 #include "catalog_host.cuh"
 #include "stage0.cuh"
+#include "fof_stage.cuh"
 
 namespace fofb {
 
 struct Stage0Holder {
   Catalog cat;
+  CellList cells;
   Stage0 s0;
 };
 
@@ -164,6 +166,8 @@ void fofb_destroy(fofb_handle* h) {
   cudaSetDevice(h->device);
   delete reinterpret_cast<Stage0Holder*>(h->catalog);
   h->catalog = nullptr;
+  delete h->fof;
+  h->fof = nullptr;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -253,7 +257,7 @@ int fofb_number_counts(fofb_handle* h, const fofb_params* p, const fofb_matrix* 
   Timed timer(h);
   const View v = to_device(h, *galaxies, h->upload);
   s->cat.build(h, v);
-  s->s0.run(h, *p, s->cat);
+  s->s0.run(h, *p, s->cat, s->cells);
   FOFB_CUDA(cudaMemcpyAsync(N_out, s->s0.N_row.p, sizeof(int32_t) * s->cat.n,
                             N_mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
   timer.stop();
@@ -275,6 +279,119 @@ int fofb_candidate_order(fofb_handle* h, int32_t* rows_out, int32_t rows_mem, in
   FOFB_CUDA(cudaStreamSynchronize(h->stream));
   return FOFB_OK;
   FOFB_CATCH(h)
+}
+
+// ---- stages 1-4 ---------------------------------------------------------------------------------------
+int fofb_fof_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, const fofb_matrix* centres,
+                 int64_t* n_clusters, double* bbox) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(galaxies && centres, "galaxies / centres is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->fof) h->fof = new FofState();
+  h->fof->ran = h->fof->finished = false;
+  Timed timer(h);
+  const View G = to_device(h, *galaxies, h->upload);
+  const View Cn = to_device(h, *centres, h->upload2);
+  FOFB_REQUIRE(G.rows > 0, "galaxy_data is empty");
+  h->fof->run(h, *p, G, Cn);
+  timer.stop();
+  if (n_clusters) *n_clusters = h->fof->merged.K;
+  if (bbox) {
+    bbox[0] = h->fof->cat.gbox.ra_min; bbox[1] = h->fof->cat.gbox.ra_max;
+    bbox[2] = h->fof->cat.gbox.dec_min; bbox[3] = h->fof->cat.gbox.dec_max;
+  }
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_fof_finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int32_t mem, int64_t* n_final) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  if (!h->fof || !h->fof->ran) throw fofb::Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  const double prev_ms = h->last_ms;
+  const int64_t prev_launches = h->launches;
+  Timed timer(h);
+  h->fof->finish(h, rand_ra, rand_dec, mem);
+  timer.stop();
+  h->last_ms += prev_ms;  // run + finish are one FoF() call
+  h->launches += prev_launches;
+  if (n_final) *n_final = h->fof->final_.K;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+static const ClusterList* pick_list(fofb_handle* h, int32_t which) {
+  if (!h->fof || !h->fof->ran) throw fofb::Error(FOFB_ERR_STATE, "no FoF result: call fofb_fof_run first");
+  switch (which) {
+    case 0: return &h->fof->candidates;
+    case 1: return &h->fof->merged;
+    case 2: return &h->fof->merged;  // the BCG stage never replaces a centre on the device path
+    case 3:
+      if (!h->fof->finished) throw fofb::Error(FOFB_ERR_STATE, "final list requested before fofb_fof_finish");
+      return &h->fof->final_;
+    default: throw fofb::Error(FOFB_ERR_INVALID, "which must be 0..3");
+  }
+}
+
+int fofb_fof_sizes(fofb_handle* h, int32_t which, int64_t* n_clusters, int64_t* n_members) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  const ClusterList* L = pick_list(h, which);
+  if (n_clusters) *n_clusters = L->K;
+  if (n_members) *n_members = L->K ? L->total : 0;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_fof_fetch(fofb_handle* h, int32_t which, int64_t* offsets, int32_t* members, int32_t* centre, double* N,
+                   double* D) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  const ClusterList* L = pick_list(h, which);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int K = L->K;
+  if (K == 0) {
+    if (offsets) offsets[0] = 0;
+    return FOFB_OK;
+  }
+  static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+  if (offsets) FOFB_CUDA(cudaMemcpyAsync(offsets, L->off.p, sizeof(int64_t) * (K + 1), cudaMemcpyDeviceToHost, st));
+  if (members && L->total) FOFB_CUDA(cudaMemcpyAsync(members, L->rows.p, sizeof(int32_t) * L->total, cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> cidx(K);
+  FOFB_CUDA(cudaMemcpyAsync(cidx.data(), L->centre.p, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> Nint;
+  if (which == 3) {
+    if (N) {
+      Nint.resize(K);
+      FOFB_CUDA(cudaMemcpyAsync(Nint.data(), L->N.p, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
+    }
+    if (D) FOFB_CUDA(cudaMemcpyAsync(D, L->D.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+  }
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  if (centre) std::memcpy(centre, cidx.data(), sizeof(int32_t) * K);
+  if (which == 3) {
+    if (N) for (int k = 0; k < K; ++k) N[k] = (double)Nint[k];
+  } else {
+    if (N) {  // before stage 4 Cluster.N is still the centre's N(0.5) column (cluster.py:38)
+      std::vector<double> cN(h->fof->m);
+      FOFB_CUDA(cudaMemcpy(cN.data(), h->fof->c_N.p, sizeof(double) * h->fof->m, cudaMemcpyDeviceToHost));
+      for (int k = 0; k < K; ++k) N[k] = cN[cidx[k]];
+    }
+    if (D) for (int k = 0; k < K; ++k) D[k] = 0.0;
+  }
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_fof_stats(fofb_handle* h, int64_t* rounds, int64_t* evaluated) {
+  if (!h || !h->fof) return FOFB_ERR_STATE;
+  if (rounds) *rounds = h->fof->rounds;
+  if (evaluated) *evaluated = h->fof->evaluated;
+  return FOFB_OK;
 }
 
 }  // extern "C"

@@ -159,44 +159,37 @@ void Catalog::build(fofb_handle* h, const View& rows_in) {
                    std::isfinite(zmin) && std::isfinite(zmax),
                "catalogue contains non-finite ra/dec/z values");
   FOFB_REQUIRE(g.z >= -90.0 && g.w <= 90.0, "declination outside [-90, 90] degrees");
-  have_cells = false;
+  dec_absmax = fmax(fabs(g.z), fabs(g.w));
 }
 
-void Catalog::build_cells(fofb_handle* h, double r_max_deg) {
+void CellList::build(fofb_handle* h, const Catalog& cat, double r_max_deg) {
   FOFB_REQUIRE(r_max_deg > 0.0 && std::isfinite(r_max_deg), "cell list needs a positive finite query radius");
   cudaStream_t st = h->stream;
+  const int64_t n = cat.n;
   const int ni = (int)n;
   const int B = 256;
-  const double decabs = fmax(fabs(gbox.dec_min), fabs(gbox.dec_max));
-  cosmin = cos(fmin(89.0, decabs + r_max_deg) * kDeg2Rad);
-  double s_dec = r_max_deg * 1.000001;
-  double s_ra = 1.01 * r_max_deg / cosmin;
+  s_dec = r_max_deg * 1.000001;
+  s_ra = ra_reach(r_max_deg, cat.dec_absmax);
   // keep the table within ~2 cells per galaxy (and 2^30 in total): larger cells are always valid
-  const double ext_ra = gbox.ra_max - gbox.ra_min, ext_dec = gbox.dec_max - gbox.dec_min;
+  const double ext_ra = cat.gbox.ra_max - cat.gbox.ra_min, ext_dec = cat.gbox.dec_max - cat.gbox.dec_min;
   for (;;) {
     const double cells = (floor(ext_ra / s_ra) + 1.0) * (floor(ext_dec / s_dec) + 1.0);
     if (cells <= fmax(1024.0, 2.0 * (double)n) && cells < 1.0e9) break;
     s_ra *= 1.25;
     s_dec *= 1.25;
   }
-  cell_size_ra = s_ra;
-  cell_size_dec = s_dec;
   ncx = (int)floor(ext_ra / s_ra) + 1;
   ncy = (int)floor(ext_dec / s_dec) + 1;
+  ra0 = cat.gbox.ra_min;
+  dec0 = cat.gbox.dec_min;
   const int ncell = ncx * ncy;
-  CellListView cl{};
-  cl.ra0 = gbox.ra_min;
-  cl.dec0 = gbox.dec_min;
-  cl.inv_sra = 1.0 / s_ra;
-  cl.inv_sdec = 1.0 / s_dec;
-  cl.ncx = ncx;
-  cl.ncy = ncy;
+  CellListView cl = view();
 
   unsigned* key_in = key_a.alloc(n);
   unsigned* key_out = key_b.alloc(n);
-  int* val_in = idx_tmp.alloc(n);
+  int* val_in = val_a.alloc(n);
   int* val_out = val_b.alloc(n);
-  k_cell_keys<<<grid_for(n, B), B, 0, st>>>(ni, zra.p, zdec.p, cl, key_in, val_in);
+  k_cell_keys<<<grid_for(n, B), B, 0, st>>>(ni, cat.zra.p, cat.zdec.p, cl, key_in, val_in);
   FOFB_LAUNCH_CHECK(h);
   int bits = 1;
   while ((1ll << bits) < ncell) ++bits;
@@ -204,14 +197,31 @@ void Catalog::build_cells(fofb_handle* h, double r_max_deg) {
   FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, val_in, val_out, ni, 0, bits, st));
   FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, key_in, key_out, val_in, val_out, ni, 0, bits, st));
   count_launch(h, 2 + (bits + 7) / 8);
-  k_cell_gather<<<grid_for(n, B), B, 0, st>>>(ni, val_out, zorder.p, zra.p, zdec.p, c_ra.alloc(n), c_dec.alloc(n),
-                                              c_cos.alloc(n), c_zrank.alloc(n), c_row.alloc(n));
+  k_cell_gather<<<grid_for(n, B), B, 0, st>>>(ni, val_out, cat.zorder.p, cat.zra.p, cat.zdec.p, ra.alloc(n), dec.alloc(n),
+                                              cosdec.alloc(n), zrank.alloc(n), row.alloc(n));
   FOFB_LAUNCH_CHECK(h);
   int* cs = cell_start.alloc((size_t)ncell + 1);
   k_cell_starts<<<grid_for(n + 1, B), B, 0, st>>>(ni, key_out, ncell, cs);
   FOFB_LAUNCH_CHECK(h);
-  have_cells = true;
-  cell_radius = r_max_deg;
+  built = true;
+  radius = r_max_deg;
+}
+
+CellListView CellList::view() const {
+  CellListView v{};
+  v.ra0 = ra0;
+  v.dec0 = dec0;
+  v.inv_sra = 1.0 / s_ra;
+  v.inv_sdec = 1.0 / s_dec;
+  v.ncx = ncx;
+  v.ncy = ncy;
+  v.cell_start = cell_start.p;
+  v.ra = ra.p;
+  v.dec = dec.p;
+  v.cosdec = cosdec.p;
+  v.zrank = zrank.p;
+  v.row = row.p;
+  return v;
 }
 
 CatalogView Catalog::view() const {
@@ -226,19 +236,7 @@ CatalogView Catalog::view() const {
   v.suf = suf.p;
   v.levels = levels.p;
   v.nblocks = nblocks;
-  v.cosmin = cosmin;
-  v.cells.ra0 = gbox.ra_min;
-  v.cells.dec0 = gbox.dec_min;
-  v.cells.inv_sra = 1.0 / cell_size_ra;
-  v.cells.inv_sdec = 1.0 / cell_size_dec;
-  v.cells.ncx = ncx;
-  v.cells.ncy = ncy;
-  v.cells.cell_start = cell_start.p;
-  v.cells.ra = c_ra.p;
-  v.cells.dec = c_dec.p;
-  v.cells.cosdec = c_cos.p;
-  v.cells.zrank = c_zrank.p;
-  v.cells.row = c_row.p;
+  v.dec_absmax = dec_absmax;
   return v;
 }
 

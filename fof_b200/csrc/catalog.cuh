@@ -30,6 +30,12 @@ struct CellListView {
   }
 };
 
+// conservative half-width in RA (degrees) of a bubble of radius r around declination dec
+__host__ __device__ __forceinline__ double ra_reach(double r, double dec) {
+  const double d = fmin(89.0, fabs(dec) + r);
+  return 1.01 * r / cos(d * kDeg2Rad);
+}
+
 struct CatalogView {
   int64_t n;
   const double* zs;      // z ascending
@@ -41,8 +47,7 @@ struct CatalogView {
   const double4* suf;    // per rank: rank..block end
   const double4* levels; // sparse table over blocks, level k at levels + k*nblocks
   int nblocks;
-  double cosmin;         // cos of the largest |dec| (+margin): bounds the RA reach of a bubble
-  CellListView cells;
+  double dec_absmax;     // largest |dec| in the catalogue: bounds the RA reach of a bubble
 };
 
 // Velocity window of a centre at redshift zc as the half-open z-rank range [lo, hi):

@@ -4,29 +4,35 @@
 
 namespace fofb {
 
+struct Catalog;
+
+// (dec, ra) cell list over the catalogue, cells z-rank sorted; sized for one query radius.
+struct CellList {
+  bool built = false;
+  double radius = 0.0;  // the query radius the list was sized for
+  double ra0 = 0, dec0 = 0, s_ra = 1, s_dec = 1;
+  int ncx = 1, ncy = 1;
+  DBuf<double> ra, dec, cosdec;
+  DBuf<int> zrank, row, cell_start, val_a, val_b;
+  DBuf<unsigned> key_a, key_b;
+  void build(fofb_handle* h, const Catalog& cat, double r_max_deg);
+  CellListView view() const;
+};
+
 struct Catalog {
   int64_t n = 0;
   View rows;
   BBox gbox{};             // global (ra_min, ra_max, dec_min, dec_max)  (helper.py:197-202)
   double zmin = 0, zmax = 0;
-  double cosmin = 1.0;
+  double dec_absmax = 0;
   int nblocks = 0;
-  bool have_cells = false;
-  double cell_radius = 0.0;  // the query radius the cell list was sized for
-  double cell_size_ra = 1.0, cell_size_dec = 1.0;
-  int ncx = 1, ncy = 1;
 
   DBuf<double> ra_row, dec_row, z_row;  // row order
   DBuf<double> zs, zra, zdec;           // z-rank order
   DBuf<int> zorder, rank, idx_tmp;
   DBuf<double4> pre, suf, levels, gbox_dev;
-  DBuf<unsigned> key_a, key_b;
-  DBuf<int> val_b;
-  DBuf<double> c_ra, c_dec, c_cos;      // cell order
-  DBuf<int> c_zrank, c_row, cell_start;
 
-  void build(fofb_handle* h, const View& rows);         // z sort + range-bbox tables
-  void build_cells(fofb_handle* h, double r_max_deg);   // (dec, ra) cell list sized for r_max
+  void build(fofb_handle* h, const View& rows);  // z sort + range-bbox tables
   CatalogView view() const;
 };
 

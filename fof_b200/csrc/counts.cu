@@ -97,7 +97,7 @@ __global__ void k_keys_to_rows(int m, const unsigned long long* key, int* rows) 
   if (i < m) rows[i] = 0x7fffffff - (int)(unsigned)(key[i] & 0xffffffffull);
 }
 
-void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat) {
+void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat, CellList& cells) {
   cudaStream_t st = h->stream;
   const int n = (int)cat.n;
   const int B = 256;
@@ -118,10 +118,9 @@ void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat) {
   FOFB_CUDA(cudaMemcpyAsync(&r_max, tmax, sizeof(double), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
   FOFB_REQUIRE(std::isfinite(r_max) && r_max > 0.0, "non-finite angular radius (check redshifts and cosmology)");
-  cat.build_cells(h, r_max);
-  cv = cat.view();
+  cells.build(h, cat, r_max);
   int* N = N_row.alloc(n);
-  k_count<<<grid_for(n, 256), 256, 0, st>>>(cv.cells, n, recs, N);
+  k_count<<<grid_for(n, 256), 256, 0, st>>>(cells.view(), n, recs, N);
   FOFB_LAUNCH_CHECK(h);
 
   unsigned long long* k_all = key_all.alloc(n);

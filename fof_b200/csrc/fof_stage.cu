@@ -1,0 +1,780 @@
+// Stage 1 of FoF() (fof.py:145-246): per-centre virial bubble, hop 1, hop 2 with the element-wise
+// novelty rule, richness gate and the greedy tracker, evaluated as deterministic
+// priority rounds: a centre is evaluated once every higher-priority centre that could claim it as a
+// member has been decided (kernels K7-K9 of DESIGN.md).
+#include <cub/cub.cuh>
+
+#include "fof_stage.cuh"
+
+namespace fofb {
+
+static unsigned char* cub_tmp(fofb_handle* h, size_t bytes) { return h->cub_tmp.alloc(bytes + 256); }
+
+template <class T>
+static T d2h_scalar(fofb_handle* h, const T* dptr) {
+  T v;
+  FOFB_CUDA(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  return v;
+}
+
+
+// ---- per-centre scalars (fof.py:158-175, 277-279; helper.py:182) -------------------------------------
+__global__ void k_centre_prep(View Cn, int m, CatalogView cat, Cosmo cosmo, double vmax, double virial_radius,
+                              double count_radius, double* c_ra, double* c_dec, double* c_cos, double* c_z,
+                              double* c_R1, double* c_thvir, double* c_th05, double* c_mag, double* c_N,
+                              double* c_id, int* c_wlo, int* c_whi, unsigned char* alive, unsigned char* decided) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double ra = Cn.at(i, 0), dec = Cn.at(i, 1), z = Cn.at(i, 2);
+  c_ra[i] = ra;
+  c_dec[i] = dec;
+  c_cos[i] = cos(__dmul_rn(dec, kDeg2Rad));
+  c_z[i] = z;
+  c_mag[i] = Cn.at(i, 5);
+  c_id[i] = Cn.at(i, 6);
+  c_N[i] = Cn.at(i, Cn.cols - 1);  // cluster.py:38: N = center[-1]
+  const double thvir = cosmo_linear_to_angular_dist(cosmo, virial_radius, z);
+  // fof.py:165-175: angle -> comoving transverse length -> angle again (= theta_vir * (1 + z), Q4)
+  const double ang = thvir * kDeg2Rad;
+  const double max_dist_mpc = ang * cosmo_transverse_distance(cosmo, z);
+  c_R1[i] = cosmo_proper_mpc_to_deg(cosmo, max_dist_mpc, z);
+  c_thvir[i] = thvir;
+  c_th05[i] = cosmo_linear_to_angular_dist(cosmo, count_radius, z);
+  int lo, hi;
+  velocity_window(cat.zs, (int)cat.n, z, vmax, &lo, &hi);
+  c_wlo[i] = lo;
+  c_whi[i] = hi;
+  alive[i] = 1;
+  decided[i] = 0;
+}
+
+__global__ void k_iota_i32(int n, int* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+__global__ void k_cos_row(int n, const double* dec, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cos(__dmul_rn(dec[i], kDeg2Rad));
+}
+
+// ---- tracker kill targets (fof.py:238-246, Q3: column 4, first occurrence) ------------------------------
+__global__ void k_col4_keys(View Cn, int m, double* key, int* val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  key[i] = Cn.at(i, 4) + 0.0;  // -0.0 -> +0.0 so equal values sort together
+  val[i] = i;
+}
+
+__global__ void k_kill_targets(View G, int n, int m, const double* skey, const int* sval, int* target, int* t_row,
+                               int* t_count, int* dup) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const double v = G.at(g, 4) + 0.0;
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (skey[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  const int tgt = (lo < m && skey[lo] == v) ? sval[lo] : -1;  // stable sort => smallest centre index first
+  target[g] = tgt;
+  if (tgt >= 0) {
+    if (atomicAdd(t_count + tgt, 1) > 0) atomicAdd(dup, 1);
+    t_row[tgt] = g;
+  }
+}
+
+// ---- centre cell list for the blocking test ----------------------------------------------------------------
+__global__ void k_cc_keys(int m, const double* ra, const double* dec, double ra0, double dec0, double inv_sra,
+                          double inv_sdec, int ncx, int ncy, unsigned* key, int* val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int cx = (int)floor((ra[i] - ra0) * inv_sra), cy = (int)floor((dec[i] - dec0) * inv_sdec);
+  cx = min(max(cx, 0), ncx - 1);
+  cy = min(max(cy, 0), ncy - 1);
+  key[i] = (unsigned)(cy * ncx + cx);
+  val[i] = i;
+}
+
+__global__ void k_cc_starts(int m, const unsigned* key, int ncell, int* start) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > m) return;
+  const int cur = k < m ? (int)key[k] : ncell;
+  const int prev = k > 0 ? (int)key[k - 1] : -1;
+  for (int c = prev + 1; c <= cur; ++c) start[c] = k;
+}
+
+struct CentreCells {
+  double ra0, dec0, inv_sra, inv_sdec;
+  int ncx, ncy;
+  const int* start;
+  const int* idx;
+};
+
+// ---- K9a: which active centres can be evaluated now ----------------------------------------------------------
+// Centre j (higher priority: j < i) can claim centre i as a member only if i lies in j's velocity
+// window and within j's virial search radius (members are a subset of virial_points, fof.py:180-228).
+// i is ready when no alive, undecided such j exists.
+__global__ void k_ready(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
+                        const double* c_cos, const double* c_z, const double* c_R1, const unsigned char* alive,
+                        const unsigned char* decided, const int* t_row, const double* ra_row, const double* dec_row,
+                        const double* cos_row, const double* z_row, double vmax, double R1max, int* ready_flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= na) return;
+  const int i = active[t];
+  // centre i is switched off when the galaxy row carrying its column-4 value joins a cluster (Q3)
+  const int g = t_row[i];
+  if (g < 0) { ready_flag[t] = 1; return; }
+  const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+  const double reach = ra_reach(R1max, dec);
+  int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
+  int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
+      y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
+  x0 = max(x0, 0); y0 = max(y0, 0);
+  x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
+  bool blocked = false;
+  for (int yy = y0; yy <= y1 && !blocked; ++yy) {
+    const int s = cc.start[yy * cc.ncx + x0], e = cc.start[yy * cc.ncx + x1 + 1];
+    for (int k = s; k < e; ++k) {
+      const int j = cc.idx[k];
+      if (j >= i || !alive[j] || decided[j]) continue;
+      if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+      BubbleTest bt;
+      bt.init(c_ra[j], c_dec[j], c_cos[j], c_R1[j]);
+      if (bt.inside(ra, dec, cs)) { blocked = true; break; }
+    }
+  }
+  ready_flag[t] = blocked ? 0 : 1;
+}
+
+__global__ void k_still_active(int na, const int* active, const unsigned char* alive, const unsigned char* decided,
+                               int* flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= na) return;
+  const int i = active[t];
+  flag[t] = (alive[i] && !decided[i]) ? 1 : 0;
+}
+
+// ---- K7: virial bubble of a ready centre, one warp per centre ---------------------------------------------------
+// mode 0: count only (also records the window bbox); mode 1: emit keys (G1 cell key << 32 | row).
+template <int MODE>
+__global__ void k_virial(int nr, const int* ready, CatalogView cat, CellListView cl, const double* c_ra,
+                         const double* c_dec, const double* c_cos, const double* c_R1, const int* c_wlo,
+                         const int* c_whi, int grid_cells, int min_virial, int* nv, double4* bbox1,
+                         const long long* voff, int* cursor, unsigned long long* keys) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nr) return;
+  const int c = ready[w];
+  const int wlo = c_wlo[c], whi = c_whi[c];
+  if (MODE == 1 && nv[w] < min_virial) return;
+  int count = 0;
+  if (whi > wlo) {
+    const double ra = c_ra[c], dec = c_dec[c], R1 = c_R1[c];
+    BBox bb;
+    Box box;
+    int oof = 0;
+    if (lane == 0) {
+      bb = range_bbox(cat, wlo, whi);
+      box = grid_box(bb, grid_cells, ra, dec, R1);
+      // a single centre farther than r outside the grid's bounding box has no neighbours (App. B.1)
+      oof = (ra - R1 > bb.ra_max + 1e-6) || (ra + R1 < bb.ra_min - 1e-6) || (dec - R1 > bb.dec_max + 1e-6) ||
+            (dec + R1 < bb.dec_min - 1e-6);
+      if (MODE == 0) bbox1[w] = make_double4(bb.ra_min, bb.ra_max, bb.dec_min, bb.dec_max);
+    }
+    bb.ra_min = __shfl_sync(0xffffffffu, bb.ra_min, 0); bb.ra_max = __shfl_sync(0xffffffffu, bb.ra_max, 0);
+    bb.dec_min = __shfl_sync(0xffffffffu, bb.dec_min, 0); bb.dec_max = __shfl_sync(0xffffffffu, bb.dec_max, 0);
+    box.ra_lo = __shfl_sync(0xffffffffu, box.ra_lo, 0); box.ra_hi = __shfl_sync(0xffffffffu, box.ra_hi, 0);
+    box.dec_lo = __shfl_sync(0xffffffffu, box.dec_lo, 0); box.dec_hi = __shfl_sync(0xffffffffu, box.dec_hi, 0);
+    oof = __shfl_sync(0xffffffffu, oof, 0);
+    if (!oof) {
+      BubbleTest bt;
+      bt.init(ra, dec, c_cos[c], R1);
+      const double reach = ra_reach(R1, dec);
+      const int x0 = cl.cx_of(ra - reach), x1 = cl.cx_of(ra + reach);
+      const int y0 = cl.cy_of(dec - R1 * 1.000001), y1 = cl.cy_of(dec + R1 * 1.000001);
+      const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
+      GridAxis gx, gy;
+      gx.init(bb.ra_min, bb.ra_max, grid_cells);
+      gy.init(bb.dec_min, bb.dec_max, grid_cells);
+      for (int t = lane; t < ncells; t += 32) {
+        const int yy = y0 + t / nx, xx = x0 + t % nx;
+        const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
+        int a = s, b = e;
+        while (a < b) { const int mid = (a + b) >> 1; if (cl.zrank[mid] < wlo) a = mid + 1; else b = mid; }
+        const int first = a;
+        b = e;
+        while (a < b) { const int mid = (a + b) >> 1; if (cl.zrank[mid] < whi) a = mid + 1; else b = mid; }
+        for (int j = first; j < a; ++j) {
+          const double pra = cl.ra[j], pdec = cl.dec[j];
+          if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) {
+            if (MODE == 0) {
+              ++count;
+            } else {
+              const unsigned long long key =
+                  ((unsigned long long)(unsigned)(gy.digit_clamped(pdec) * grid_cells + gx.digit_clamped(pra)) << 32) |
+                  (unsigned)cl.row[j];
+              const int pos = atomicAdd(cursor + w, 1);
+              keys[voff[w] + pos] = key;
+            }
+          }
+        }
+      }
+    }
+  } else if (MODE == 0 && lane == 0) {
+    bbox1[w] = make_double4(0, 0, 0, 0);
+  }
+  if (MODE == 0) {
+    for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0) nv[w] = count;
+  }
+}
+
+__global__ void k_alloc_sizes(int nr, const int* nv, int min_virial, long long* need) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nr) need[w] = nv[w] >= min_virial ? nv[w] : 0;
+}
+
+// ---- K8a: linking length, friends grid and hop 1 (fof.py:187-206), one warp per centre ------------------------
+__global__ void k_hop1(int nr, const int* ready, const int* nv, const long long* voff, const unsigned long long* keys1,
+                       const double* ra_row, const double* dec_row, const double* cos_row, const double* c_ra,
+                       const double* c_dec, const double* c_cos, const double* c_z, Cosmo cosmo, fofb_params p,
+                       double* LLout, double4* bbox2, int* nF, unsigned long long* keys2) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nr) return;
+  const int n_v = nv[w];
+  if (n_v < p.min_virial) {
+    if (lane == 0) nF[w] = 0;
+    return;
+  }
+  const int c = ready[w];
+  const long long off = voff[w];
+  const double zc = c_z[c], ra = c_ra[c], dec = c_dec[c];
+  const double mean_sep = cosmo_mean_separation(cosmo, (double)n_v, zc, p.max_velocity, p.survey_area);
+  const double LL = cosmo_proper_mpc_to_deg(cosmo, p.linking_length_factor * mean_sep, zc);
+  // bbox of virial_points = the grid f_gsp is built on (fof.py:202)
+  double4 bb = make_double4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+  for (int k = lane; k < n_v; k += 32) {
+    const int row = (int)(unsigned)(keys1[off + k] & 0xffffffffull);
+    const double pra = ra_row[row], pdec = dec_row[row];
+    bb = bbox_merge(bb, make_double4(pra, pra, pdec, pdec));
+  }
+  for (int o = 16; o; o >>= 1) {
+    double4 other;
+    other.x = __shfl_xor_sync(0xffffffffu, bb.x, o); other.y = __shfl_xor_sync(0xffffffffu, bb.y, o);
+    other.z = __shfl_xor_sync(0xffffffffu, bb.z, o); other.w = __shfl_xor_sync(0xffffffffu, bb.w, o);
+    bb = bbox_merge(bb, other);
+  }
+  const BBox b2{bb.x, bb.y, bb.z, bb.w};
+  const bool oof = (ra - LL > b2.ra_max + 1e-6) || (ra + LL < b2.ra_min - 1e-6) || (dec - LL > b2.dec_max + 1e-6) ||
+                   (dec + LL < b2.dec_min - 1e-6);
+  const Box box = grid_box(b2, p.grid_cells, ra, dec, LL);
+  BubbleTest bt;
+  bt.init(ra, dec, c_cos[c], LL);
+  GridAxis gx, gy;
+  gx.init(b2.ra_min, b2.ra_max, p.grid_cells);
+  gy.init(b2.dec_min, b2.dec_max, p.grid_cells);
+  int cnt = 0;
+  for (int k = lane; k < n_v; k += 32) {
+    const int row = (int)(unsigned)(keys1[off + k] & 0xffffffffull);
+    const double pra = ra_row[row], pdec = dec_row[row];
+    const bool fr = !oof && box.contains(pra, pdec) && bt.inside(pra, pdec, cos_row[row]);
+    cnt += fr ? 1 : 0;
+    const unsigned long long cellkey = (unsigned)(gy.digit_clamped(pdec) * p.grid_cells + gx.digit_clamped(pra));
+    keys2[off + k] = (fr ? 0ull : (1ull << 63)) | (cellkey << 32) | (unsigned)k;
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) {
+    nF[w] = cnt;
+    LLout[w] = LL;
+    bbox2[w] = bb;
+  }
+}
+
+__global__ void k_hash_sizes(int nr, const int* nv, const int* nF, int min_virial, long long* cap) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nr) return;
+  long long c = 0;
+  if (nv[w] >= min_virial && nF[w] > 0 && nF[w] < nv[w]) {
+    c = 64;
+    while (c < 16ll * nv[w]) c <<= 1;
+  }
+  cap[w] = c;
+}
+
+// ---- value set for the element-wise novelty rule (fof.py:217-223, Q5) --------------------------------------------
+constexpr unsigned long long kHashEmpty = ~0ull;
+
+__device__ __forceinline__ unsigned long long hash_mix(unsigned long long x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+__device__ __forceinline__ bool value_bits(double v, unsigned long long* bits) {
+  if (v != v) return false;  // NaN equals nothing (np.isin)
+  *bits = (unsigned long long)__double_as_longlong(v + 0.0);
+  return true;
+}
+
+__device__ __forceinline__ void hash_insert(unsigned long long* tab, long long cap, double v) {
+  unsigned long long b;
+  if (!value_bits(v, &b)) return;
+  long long s = (long long)(hash_mix(b) & (unsigned long long)(cap - 1));
+  for (;;) {
+    const unsigned long long old = atomicCAS(tab + s, kHashEmpty, b);
+    if (old == kHashEmpty || old == b) return;
+    s = (s + 1) & (cap - 1);
+  }
+}
+
+__device__ __forceinline__ bool hash_contains(const unsigned long long* tab, long long cap, double v) {
+  unsigned long long b;
+  if (!value_bits(v, &b)) return false;
+  long long s = (long long)(hash_mix(b) & (unsigned long long)(cap - 1));
+  for (;;) {
+    const unsigned long long cur = __ldcg(tab + s);
+    if (cur == b) return true;
+    if (cur == kHashEmpty) return false;
+    s = (s + 1) & (cap - 1);
+  }
+}
+
+// ---- K8b: hop 2 and the richness gate, one warp per centre (fof.py:208-246) ------------------------------------------
+__global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, const long long* voff,
+                       const unsigned long long* keys1, const unsigned long long* keys2, const long long* hoff,
+                       const long long* hcap, unsigned long long* htab, View G, const double* ra_row,
+                       const double* dec_row, const double* cos_row, const double* LLin, const double4* bbox2,
+                       fofb_params p, int* v2row, int* mrows, int* nm_list, unsigned char* admit_flag, int* nM,
+                       int* pass, const int* kill_target, unsigned char* alive, unsigned char* decided) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nr) return;
+  const int c = ready[w];
+  const int n_v = nv[w];
+  int n_members = 0;
+  if (n_v >= p.min_virial) {
+    const long long off = voff[w];
+    const int n_f = nF[w];
+    // V2 order: friends first (in f_gsp's return order), then the rest in f_gsp cell order
+    for (int t = lane; t < n_v; t += 32) {
+      const int k = (int)(unsigned)(keys2[off + t] & 0xffffffffull);
+      const int row = (int)(unsigned)(keys1[off + k] & 0xffffffffull);
+      v2row[off + t] = row;
+      if (t < n_f) mrows[off + t] = row;
+    }
+    n_members = n_f;
+    const long long cap = hcap[w];
+    if (cap > 0) {
+      unsigned long long* tab = htab + hoff[w];
+      __syncwarp();
+      for (int t = lane; t < n_f * G.cols; t += 32) hash_insert(tab, cap, G.at(v2row[off + t / G.cols], t % G.cols));
+      int n_nm = n_v - n_f;  // non-members, kept in V2 order
+      for (int t = lane; t < n_nm; t += 32) nm_list[off + t] = n_f + t;
+      __syncwarp();
+      const double LL = LLin[w];
+      const double4 b4 = bbox2[w];
+      const BBox b2{b4.x, b4.y, b4.z, b4.w};
+      for (int fi = 0; fi < n_f && n_nm > 0; ++fi) {
+        const int frow = v2row[off + fi];
+        const double fra = ra_row[frow], fdec = dec_row[frow];
+        const Box box = grid_box(b2, p.grid_cells, fra, fdec, LL);
+        BubbleTest bt;
+        bt.init(fra, fdec, cos_row[frow], LL);
+        // pass 1: admission of every remaining non-member against the member matrix before this batch
+        int any = 0;
+        for (int base = 0; base < n_nm; base += 32) {
+          const int t = base + lane;
+          bool adm = false;
+          if (t < n_nm) {
+            const int row = v2row[off + nm_list[off + t]];
+            const double pra = ra_row[row], pdec = dec_row[row];
+            if (box.contains(pra, pdec) && bt.inside(pra, pdec, cos_row[row])) {
+              adm = true;
+              for (int col = 0; col < G.cols && adm; ++col) adm = !hash_contains(tab, cap, G.at(row, col));
+            }
+            admit_flag[off + t] = adm ? 1 : 0;
+          }
+          any |= __any_sync(0xffffffffu, adm) ? 1 : 0;
+        }
+        if (!any) continue;
+        __syncwarp();
+        // pass 2: append the admitted rows in order, insert their values, compact the non-member list
+        int kept = 0;
+        for (int base = 0; base < n_nm; base += 32) {
+          const int t = base + lane;
+          const bool in = t < n_nm;
+          const bool adm = in && admit_flag[off + t];
+          const int vpos = in ? nm_list[off + t] : 0;
+          const unsigned ma = __ballot_sync(0xffffffffu, adm), mk = __ballot_sync(0xffffffffu, in && !adm);
+          const unsigned below = (1u << lane) - 1u;
+          if (adm) {
+            const int row = v2row[off + vpos];
+            mrows[off + n_members + __popc(ma & below)] = row;
+            for (int col = 0; col < G.cols; ++col) hash_insert(tab, cap, G.at(row, col));
+          }
+          __syncwarp();
+          if (in && !adm) nm_list[off + kept + __popc(mk & below)] = vpos;  // kept + rank <= t: never ahead of reads
+          n_members += __popc(ma);
+          kept += __popc(mk);
+          __syncwarp();
+        }
+        n_nm = kept;
+        __threadfence_block();
+        __syncwarp();
+      }
+    }
+  }
+  const bool ok = n_members >= p.richness;
+  if (lane == 0) {
+    nM[w] = n_members;
+    pass[w] = ok ? 1 : 0;
+    decided[c] = 1;
+  }
+  if (ok) {  // tracker: members that are candidate centres never seed a cluster later (fof.py:238-246)
+    const long long off = voff[w];
+    for (int t = lane; t < n_members; t += 32) {
+      const int tgt = kill_target[mrows[off + t]];
+      if (tgt > c) alive[tgt] = 0;
+    }
+  }
+}
+
+__global__ void k_commit_sizes(int nr, const int* pass, const int* nM, long long* len) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nr) len[w] = pass[w] ? nM[w] : 0;
+}
+
+__global__ void k_commit(int nr, const int* ready, const int* pass, const int* nM, const long long* voff,
+                         const int* mrows, const long long* dst_off, const long long* slot_of, long long pool_base,
+                         int pool_k0, int* pool_rows, int* pool_centre, long long* pool_off, int* pool_len) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nr || !pass[w]) return;
+  const long long src = voff[w], dst = pool_base + dst_off[w];
+  const int len = nM[w];
+  for (int t = lane; t < len; t += 32) pool_rows[dst + t] = mrows[src + t];
+  if (lane == 0) {
+    const int slot = pool_k0 + (int)slot_of[w];
+    pool_centre[slot] = ready[w];
+    pool_off[slot] = dst;
+    pool_len[slot] = len;
+  }
+}
+
+__global__ void k_pass_to_ll(int nr, const int* pass, long long* out) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nr) out[w] = pass[w];
+}
+
+// candidates in priority order: gather from the pool following the sorted slot permutation
+__global__ void k_list_sizes(int K, const int* slot, const int* pool_len, long long* len) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) len[k] = pool_len[slot[k]];
+}
+
+__global__ void k_list_gather(int K, const int* slot, const int* pool_centre, const long long* pool_off,
+                              const int* pool_len, const int* pool_rows, const long long* off, int* centre, int* rows) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const int s = slot[k];
+  const long long src = pool_off[s], dst = off[k];
+  for (int t = lane; t < pool_len[s]; t += 32) rows[dst + t] = pool_rows[src + t];
+  if (lane == 0) centre[k] = pool_centre[s];
+}
+
+// exclusive scan of len[0..n) into off[0..n]; returns the total (host)
+static long long scan_offsets(fofb_handle* h, const long long* len, long long* off, int n) {
+  if (n == 0) return 0;
+  size_t bytes = 0;
+  FOFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len, off, n, h->stream));
+  FOFB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp(h, bytes), bytes, len, off, n, h->stream));
+  count_launch(h, 2);
+  long long last_off, last_len;
+  FOFB_CUDA(cudaMemcpyAsync(&last_off, off + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaMemcpyAsync(&last_len, len + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  const long long total = last_off + last_len;
+  FOFB_CUDA(cudaMemcpyAsync(off + n, &total, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  return total;
+}
+
+static int select_flagged(fofb_handle* h, const int* in, const int* flags, int* out, int n, int* d_count) {
+  if (n == 0) return 0;
+  size_t bytes = 0;
+  FOFB_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, in, flags, out, d_count, n, h->stream));
+  FOFB_CUDA(cub::DeviceSelect::Flagged(cub_tmp(h, bytes), bytes, in, flags, out, d_count, n, h->stream));
+  count_launch(h, 2);
+  return d2h_scalar(h, d_count);
+}
+
+static void segmented_sort(fofb_handle* h, const unsigned long long* in, unsigned long long* out, long long total,
+                           int nseg, const long long* off) {
+  if (total == 0 || nseg == 0) return;
+  size_t bytes = 0;
+  FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, in, out, total, nseg, off, off + 1, h->stream));
+  FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, in, out, total, nseg, off, off + 1, h->stream));
+  count_launch(h, 4);
+}
+
+void fof_overlap_and_bcg(fofb_handle* h, FofState& S);  // overlap.cu
+
+void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const View& Cn_in) {
+  cudaStream_t st = h->stream;
+  ran = finished = false;
+  params = p;
+  G = G_in;
+  Cn = Cn_in;
+  FOFB_REQUIRE(G.cols >= 8 && Cn.cols >= 8, "FoF needs the 8-column layout (ra, dec, z, z_lower, z_upper, RMag, ID, N)");
+  FOFB_REQUIRE(G.cols == Cn.cols, "galaxy_data and candidate_centers must have the same number of columns");
+  FOFB_REQUIRE(G.cols <= 64, "too many columns");
+  n = (int)G.rows;
+  m = (int)Cn.rows;
+  const int B = 256;
+  const Cosmo cosmo = device_cosmo(h, p);
+  cat.build(h, G);
+  CatalogView cv = cat.view();
+  k_cos_row<<<grid_for(n, B), B, 0, st>>>(n, cat.dec_row.p, cos_row.alloc(n));
+  FOFB_LAUNCH_CHECK(h);
+  candidates.K = merged.K = bcg.K = final_.K = 0;
+  candidates.total = merged.total = bcg.total = final_.total = 0;
+  pool_used = 0;
+  pool_K = 0;
+  rounds = 0;
+  evaluated = 0;
+  if (m == 0) {
+    ran = true;
+    return;
+  }
+  const size_t mm = (size_t)m;
+  k_centre_prep<<<grid_for(m, B), B, 0, st>>>(Cn, m, cv, cosmo, p.max_velocity, p.virial_radius, p.count_radius,
+                                              c_ra.alloc(mm), c_dec.alloc(mm), c_cos.alloc(mm), c_z.alloc(mm),
+                                              c_R1.alloc(mm), c_thvir.alloc(mm), c_th05.alloc(mm), c_mag.alloc(mm),
+                                              c_N.alloc(mm), c_id.alloc(mm), c_wlo.alloc(mm), c_whi.alloc(mm),
+                                              alive.alloc(mm), decided.alloc(mm));
+  FOFB_LAUNCH_CHECK(h);
+  size_t bytes = 0;
+  long long* scal_p = scal.alloc(16);
+  double* dmax = reinterpret_cast<double*>(scal_p);
+  FOFB_CUDA(cub::DeviceReduce::Max(nullptr, bytes, c_R1.p, dmax, m, st));
+  FOFB_CUDA(cub::DeviceReduce::Max(cub_tmp(h, bytes), bytes, c_R1.p, dmax, m, st));
+  FOFB_CUDA(cub::DeviceReduce::Max(cub_tmp(h, bytes), bytes, c_th05.p, dmax + 1, m, st));
+  count_launch(h, 4);
+  double r2[2];
+  FOFB_CUDA(cudaMemcpyAsync(r2, dmax, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  R1max = r2[0];
+  FOFB_REQUIRE(std::isfinite(R1max) && R1max > 0 && std::isfinite(r2[1]) && r2[1] > 0,
+               "non-finite search radius (check centre redshifts)");
+  big.build(h, cat, R1max);
+  small.build(h, cat, r2[1]);
+
+  // tracker kill targets
+  {
+    double* key_in = sort_keys_d.alloc(mm);
+    double* key_out = sort_keys_d2.alloc(mm);
+    int* val_in = sort_vals.alloc(mm);
+    int* val_out = sort_vals2.alloc(mm);
+    k_col4_keys<<<grid_for(m, B), B, 0, st>>>(Cn, m, key_in, val_in);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, val_in, val_out, m, 0, 64, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, key_in, key_out, val_in, val_out, m, 0, 64, st));
+    count_launch(h, 8);
+    int* trow = t_row.alloc(mm);
+    int* tcnt = t_count.alloc(mm + 1);
+    FOFB_CUDA(cudaMemsetAsync(trow, 0xff, sizeof(int) * mm, st));
+    FOFB_CUDA(cudaMemsetAsync(tcnt, 0, sizeof(int) * (mm + 1), st));
+    k_kill_targets<<<grid_for(n, B), B, 0, st>>>(G, n, m, key_out, val_out, kill_target.alloc(n), trow, tcnt, tcnt + mm);
+    FOFB_LAUNCH_CHECK(h);
+    if (d2h_scalar(h, tcnt + mm) != 0)
+      throw Error(FOFB_ERR_UNSUPPORTED,
+                  "two galaxy rows share a column-4 (z_upper) value with the same candidate centre; the tracker of "
+                  "fof.py:238-246 keys on that column and the device path requires it to identify a galaxy uniquely");
+  }
+  // centre cell list
+  {
+    cc_sdec = R1max * 1.000001;
+    double cabs = 0.0;
+    {  // centres may lie outside the galaxy bbox: bound |dec| by 90
+      cabs = fmin(89.0, cat.dec_absmax + 1.0);
+    }
+    cc_sra = ra_reach(R1max, cabs);
+    // bbox of centres: reuse catalogue bbox padded; clamp handles outliers
+    cc_ra0 = cat.gbox.ra_min;
+    cc_dec0 = cat.gbox.dec_min;
+    const double ext_ra = cat.gbox.ra_max - cat.gbox.ra_min, ext_dec = cat.gbox.dec_max - cat.gbox.dec_min;
+    for (;;) {
+      const double cells = (floor(ext_ra / cc_sra) + 1.0) * (floor(ext_dec / cc_sdec) + 1.0);
+      if (cells <= fmax(1024.0, 2.0 * (double)m) && cells < 1.0e9) break;
+      cc_sra *= 1.25;
+      cc_sdec *= 1.25;
+    }
+    cc_ncx = (int)floor(ext_ra / cc_sra) + 1;
+    cc_ncy = (int)floor(ext_dec / cc_sdec) + 1;
+    const int ncell = cc_ncx * cc_ncy;
+    unsigned* ka = cc_key_a.alloc(mm);
+    unsigned* kb = cc_key_b.alloc(mm);
+    int* va = cc_val_a.alloc(mm);
+    int* vb = cc_idx.alloc(mm);
+    k_cc_keys<<<grid_for(m, B), B, 0, st>>>(m, c_ra.p, c_dec.p, cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx,
+                                            cc_ncy, ka, va);
+    FOFB_LAUNCH_CHECK(h);
+    int bits = 1;
+    while ((1ll << bits) < ncell) ++bits;
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ka, kb, va, vb, m, 0, bits, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, ka, kb, va, vb, m, 0, bits, st));
+    count_launch(h, 4);
+    k_cc_starts<<<grid_for(m + 1, B), B, 0, st>>>(m, kb, ncell, cc_start.alloc((size_t)ncell + 1));
+    FOFB_LAUNCH_CHECK(h);
+  }
+  CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p};
+  CellListView clbig = big.view();
+
+  // ---- priority rounds ---------------------------------------------------------------------------
+  int* act = active_a.alloc(mm);
+  int* act_next = active_b.alloc(mm);
+  k_iota_i32<<<grid_for(m, B), B, 0, st>>>(m, act);
+  FOFB_LAUNCH_CHECK(h);
+  int na = m;
+  int* d_count = reinterpret_cast<int*>(scal_p + 8);
+  pool_centre.alloc(mm);
+  pool_off.alloc(mm);
+  pool_len.alloc(mm);
+  while (na > 0) {
+    ++rounds;
+    int* fl = flags.alloc((size_t)na);
+    k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, alive.p, decided.p,
+                                               t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
+                                               p.max_velocity, R1max, fl);
+    FOFB_LAUNCH_CHECK(h);
+    int* rdy = ready.alloc((size_t)na);
+    const int nr_all = select_flagged(h, act, fl, rdy, na, d_count);
+    if (nr_all == 0) throw Error(FOFB_ERR_INTERNAL, "priority rounds made no progress");
+    // evaluate the ready centres in bounded batches
+    const int kBatch = 1 << 16;
+    for (int b0 = 0; b0 < nr_all; b0 += kBatch) {
+      const int nr = std::min(kBatch, nr_all - b0);
+      const int* rb = rdy + b0;
+      evaluated += nr;
+      const int wblocks = grid_for((int64_t)nr * 32, 128);
+      int* nv_p = nv.alloc(nr);
+      double4* bb1 = bbox1.alloc(nr);
+      k_virial<0><<<wblocks, 128, 0, st>>>(nr, rb, cv, clbig, c_ra.p, c_dec.p, c_cos.p, c_R1.p, c_wlo.p, c_whi.p,
+                                           p.grid_cells, p.min_virial, nv_p, bb1, nullptr, nullptr, nullptr);
+      FOFB_LAUNCH_CHECK(h);
+      long long* need = hcap.alloc((size_t)nr + 1);
+      long long* vo = voff.alloc((size_t)nr + 1);
+      k_alloc_sizes<<<grid_for(nr, B), B, 0, st>>>(nr, nv_p, p.min_virial, need);
+      FOFB_LAUNCH_CHECK(h);
+      const long long total_v = scan_offsets(h, need, vo, nr);
+      FOFB_REQUIRE(total_v < (1ll << 31), "virial scratch exceeds 2^31 entries in one batch");
+      int* nF_p = nF.alloc(nr);
+      int* nM_p = nM.alloc(nr);
+      int* pass_p = pass.alloc(nr);
+      long long* ho = hoff.alloc((size_t)nr + 1);
+      const size_t tv = (size_t)std::max<long long>(total_v, 1);
+      int* v2 = v2row.alloc(tv);
+      int* mr = mrows.alloc(tv);
+      int* nml = nm_list.alloc(tv);
+      unsigned char* adm = ismember.alloc(tv);
+      double* LLp = LL.alloc(nr);
+      double4* bb2 = bbox2.alloc(nr);
+      unsigned long long* k1 = keys1.alloc(tv);
+      unsigned long long* k1s = keys1b.alloc(tv);
+      unsigned long long* k2 = keys2.alloc(tv);
+      unsigned long long* k2s = keys2b.alloc(tv);
+      long long total_h = 0;
+      if (total_v > 0) {
+        int* cur = cursor.alloc(nr);
+        FOFB_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * nr, st));
+        k_virial<1><<<wblocks, 128, 0, st>>>(nr, rb, cv, clbig, c_ra.p, c_dec.p, c_cos.p, c_R1.p, c_wlo.p, c_whi.p,
+                                             p.grid_cells, p.min_virial, nv_p, bb1, vo, cur, k1);
+        FOFB_LAUNCH_CHECK(h);
+        segmented_sort(h, k1, k1s, total_v, nr, vo);
+        k_hop1<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, vo, k1s, cat.ra_row.p, cat.dec_row.p, cos_row.p, c_ra.p, c_dec.p,
+                                        c_cos.p, c_z.p, cosmo, p, LLp, bb2, nF_p, k2);
+        FOFB_LAUNCH_CHECK(h);
+        segmented_sort(h, k2, k2s, total_v, nr, vo);
+        k_hash_sizes<<<grid_for(nr, B), B, 0, st>>>(nr, nv_p, nF_p, p.min_virial, need);
+        FOFB_LAUNCH_CHECK(h);
+        total_h = scan_offsets(h, need, ho, nr);
+        if (total_h > 0) {
+          unsigned long long* tab = htab.alloc((size_t)total_h);
+          FOFB_CUDA(cudaMemsetAsync(tab, 0xff, sizeof(unsigned long long) * (size_t)total_h, st));
+        }
+      } else {
+        FOFB_CUDA(cudaMemsetAsync(nF_p, 0, sizeof(int) * nr, st));
+        FOFB_CUDA(cudaMemsetAsync(ho, 0, sizeof(long long) * ((size_t)nr + 1), st));
+      }
+      k_hop2<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, k1s, k2s, ho, need, htab.p, G, cat.ra_row.p,
+                                      cat.dec_row.p, cos_row.p, LLp, bb2, p, v2, mr, nml, adm, nM_p, pass_p,
+                                      kill_target.p, alive.p, decided.p);
+      FOFB_LAUNCH_CHECK(h);
+      // commit the clusters that passed the richness gate
+      long long* len = need;  // reuse
+      long long* dst = ho;    // reuse
+      k_commit_sizes<<<grid_for(nr, B), B, 0, st>>>(nr, pass_p, nM_p, len);
+      FOFB_LAUNCH_CHECK(h);
+      const long long add = scan_offsets(h, len, dst, nr);
+      if (add > 0) {
+        long long* pl = moff.alloc((size_t)nr + 1);
+        long long* slot = reinterpret_cast<long long*>(keys2.alloc(tv > (size_t)nr + 1 ? tv : (size_t)nr + 1));
+        k_pass_to_ll<<<grid_for(nr, B), B, 0, st>>>(nr, pass_p, pl);
+        FOFB_LAUNCH_CHECK(h);
+        const long long newK = scan_offsets(h, pl, slot, nr);
+        // grow the pool, preserving its contents
+        if ((size_t)(pool_used + add) > pool_rows.cap) {
+          DBuf<int> bigger;
+          bigger.alloc((size_t)(pool_used + add) * 2 + 1024);
+          if (pool_used) FOFB_CUDA(cudaMemcpyAsync(bigger.p, pool_rows.p, sizeof(int) * pool_used, cudaMemcpyDeviceToDevice, st));
+          FOFB_CUDA(cudaStreamSynchronize(st));
+          std::swap(bigger.p, pool_rows.p);
+          std::swap(bigger.cap, pool_rows.cap);
+        }
+        k_commit<<<wblocks, 128, 0, st>>>(nr, rb, pass_p, nM_p, vo, mr, dst, slot, pool_used, pool_K, pool_rows.p,
+                                          pool_centre.p, pool_off.p, pool_len.p);
+        FOFB_LAUNCH_CHECK(h);
+        pool_used += add;
+        pool_K += (int)newK;
+      }
+    }
+    // next active list
+    k_still_active<<<grid_for(na, B), B, 0, st>>>(na, act, alive.p, decided.p, fl);
+    FOFB_LAUNCH_CHECK(h);
+    na = select_flagged(h, act, fl, act_next, na, d_count);
+    std::swap(act, act_next);
+  }
+
+  // ---- candidates in priority order (= the order the sequential loop appends them, fof.py:232) ------
+  candidates.K = pool_K;
+  candidates.total = pool_used;
+  if (pool_K > 0) {
+    const size_t K = (size_t)pool_K;
+    int* slot_in = sort_vals.alloc(std::max(K, mm));
+    int* slot_out = sort_vals2.alloc(std::max(K, mm));
+    int* key_out = flags.alloc(std::max(K, mm));
+    k_iota_i32<<<grid_for(pool_K, B), B, 0, st>>>(pool_K, slot_in);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, pool_centre.p, key_out, slot_in, slot_out, pool_K, 0, 32, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, pool_centre.p, key_out, slot_in, slot_out, pool_K, 0, 32, st));
+    count_launch(h, 6);
+    long long* len = hcap.alloc(K + 1);
+    long long* off = candidates.off.alloc(K + 1);
+    k_list_sizes<<<grid_for(pool_K, B), B, 0, st>>>(pool_K, slot_out, pool_len.p, len);
+    FOFB_LAUNCH_CHECK(h);
+    const long long tot = scan_offsets(h, len, off, pool_K);
+    if (tot != pool_used) throw Error(FOFB_ERR_INTERNAL, "candidate pool accounting mismatch");
+    k_list_gather<<<grid_for((int64_t)pool_K * 32, 128), 128, 0, st>>>(pool_K, slot_out, pool_centre.p, pool_off.p, pool_len.p,
+                                                                       pool_rows.p, off, candidates.centre.alloc(K),
+                                                                       candidates.rows.alloc((size_t)std::max<long long>(tot, 1)));
+    FOFB_LAUNCH_CHECK(h);
+  }
+  fof_overlap_and_bcg(h, *this);
+  ran = true;
+}
+
+}  // namespace fofb

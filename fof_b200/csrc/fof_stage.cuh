@@ -1,0 +1,68 @@
+// State of the FoF() pipeline (fof.py:98-392) kept in the handle between run / finish / fetch.
+#pragma once
+#include "catalog_host.cuh"
+
+namespace fofb {
+
+// A list of clusters: member rows of cluster k are rows[off[k] .. off[k+1]) in reference order.
+struct ClusterList {
+  int K = 0;
+  int64_t total = 0;
+  DBuf<int> centre;       // index into the candidate-centre matrix; >= m: galaxy row (centre - m) of a BCG-created cluster
+  DBuf<long long> off;    // K + 1
+  DBuf<int> rows;         // galaxy row indices
+  DBuf<int> N;            // Cluster.N
+  DBuf<double> D;         // Cluster.D
+};
+
+struct FofState {
+  bool ran = false, finished = false;
+  int n = 0, m = 0;
+  View G, Cn;
+  Catalog cat;
+  CellList big;    // sized for the stage-1 virial search radius
+  CellList small;  // sized for theta_0.5 (overdensity counts)
+  fofb_params params{};
+
+  // per-centre (index = priority)
+  DBuf<double> c_ra, c_dec, c_cos, c_z, c_R1, c_thvir, c_th05, c_mag, c_N, c_id;
+  DBuf<int> c_wlo, c_whi;
+  DBuf<unsigned char> alive, decided;
+  DBuf<int> t_row, t_count;  // per centre: the galaxy row whose membership switches it off (-1: none)
+  DBuf<int> kill_target;   // per galaxy row: first centre whose column 4 equals the row's column 4, or -1
+  DBuf<double> cos_row;
+
+  // centre cell list (blocking test)
+  DBuf<int> cc_start, cc_idx;
+  DBuf<unsigned> cc_key_a, cc_key_b;
+  DBuf<int> cc_val_a;
+  double cc_ra0 = 0, cc_dec0 = 0, cc_sra = 1, cc_sdec = 1;
+  int cc_ncx = 1, cc_ncy = 1;
+  double R1max = 0;
+
+  // round scratch
+  DBuf<int> active_a, active_b, ready, flags, counts, nv, nF, nM, cursor, pass;
+  DBuf<long long> voff, hoff, hcap, moff;
+  DBuf<unsigned long long> keys1, keys1b, keys2, keys2b, htab;
+  DBuf<int> v2row, mrows, nm_list;
+  DBuf<unsigned char> ismember;
+  DBuf<double> LL;
+  DBuf<double4> bbox1, bbox2;
+  DBuf<long long> scal;    // device scalars
+  DBuf<double> sort_keys_d, sort_keys_d2;
+  DBuf<int> sort_vals, sort_vals2;
+
+  // candidate clusters accumulated over rounds (unordered), then ordered lists per stage
+  DBuf<int> pool_rows, pool_centre, pool_len;
+  DBuf<long long> pool_off;
+  int64_t pool_used = 0;
+  int pool_K = 0;
+  ClusterList candidates, merged, bcg, final_;
+  int rounds = 0;
+  int64_t evaluated = 0;
+
+  void run(fofb_handle* h, const fofb_params& p, const View& G, const View& Cn);
+  void finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int mem);
+};
+
+}  // namespace fofb

@@ -1,0 +1,611 @@
+// Stages 2-4 of FoF() (fof.py:258-392): ordered overlap contests between candidate clusters,
+// the BCG recentring check, own-member N(0.5) recount and the 300-point overdensity
+// (kernels K10, K11 of DESIGN.md).
+#include <cub/cub.cuh>
+
+#include "fof_stage.cuh"
+
+namespace fofb {
+
+static unsigned char* cub_tmp(fofb_handle* h, size_t bytes) { return h->cub_tmp.alloc(bytes + 256); }
+
+template <class T>
+static T d2h_scalar(fofb_handle* h, const T* dptr) {
+  T v;
+  FOFB_CUDA(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  return v;
+}
+
+static long long scan_offsets(fofb_handle* h, const long long* len, long long* off, int n) {
+  if (n == 0) return 0;
+  size_t bytes = 0;
+  FOFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len, off, n, h->stream));
+  FOFB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp(h, bytes), bytes, len, off, n, h->stream));
+  count_launch(h, 2);
+  long long last_off, last_len;
+  FOFB_CUDA(cudaMemcpyAsync(&last_off, off + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaMemcpyAsync(&last_len, len + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  const long long total = last_off + last_len;
+  FOFB_CUDA(cudaMemcpyAsync(off + n, &total, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  return total;
+}
+
+struct OverlapScratch {
+  DBuf<double> kz, kz_sorted, ids, ids_sorted, idk, idk_sorted;
+  DBuf<int> kidx, kidx_sorted, first_by_id, idv, idv_sorted;
+  DBuf<int> wlo, whi, ecount, ev_a, ev_c, ev_loser, state, flag;
+  DBuf<long long> eoff, elen, loff, soff;
+  DBuf<unsigned long long> ekey, ekey_sorted, lkey, lkey_sorted;
+  DBuf<double4> bbox;
+  DBuf<unsigned char> keep;
+  DBuf<int> sel, selcount;
+};
+
+__global__ void k_iota(int n, int* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+__global__ void k_cluster_z(int K, const int* centre, const double* c_z, const double* c_id, double* kz, int* kidx,
+                            double* idk, int* idv) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  kz[k] = c_z[centre[k]];
+  kidx[k] = k;
+  idk[k] = c_id[centre[k]] + 0.0;
+  idv[k] = k;
+}
+
+// candidates[gal_id_space == id][0]: the first cluster carrying each gal_id (fof.py:288)
+__global__ void k_first_by_id(int K, const double* idk_sorted, const int* idv_sorted, int* first_by_id) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= K) return;
+  int s = t;
+  const double v = idk_sorted[t];
+  // runs are short; walk back to the start of the run of equal ids (stable sort => ascending k)
+  while (s > 0 && idk_sorted[s - 1] == v) --s;
+  first_by_id[idv_sorted[t]] = (v == v) ? idv_sorted[s] : -1;  // NaN id matches nothing
+}
+
+// Per cluster a (one warp): velocity window over the candidate-cluster list, its bounding box, and the
+// overlapping centres inside theta_vir(a.z) in GriSPy's return order (fof.py:270-283).
+template <int MODE>
+__global__ void k_overlap_events(int K, const int* centre, const double* kz_sorted, const int* kidx_sorted,
+                                 const double* c_ra, const double* c_dec, const double* c_cos, const double* c_z,
+                                 const double* c_thvir, double vmax, int grid_cells, int* ecount, const long long* eoff,
+                                 unsigned long long* ekey) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= K) return;
+  const int ca = centre[a];
+  const double ra = c_ra[ca], dec = c_dec[ca], z = c_z[ca], r = c_thvir[ca];
+  int lo, hi;
+  velocity_window(kz_sorted, K, z, vmax, &lo, &hi);
+  double4 bb = make_double4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+  for (int t = lo + lane; t < hi; t += 32) {
+    const int cc = centre[kidx_sorted[t]];
+    bb = bbox_merge(bb, make_double4(c_ra[cc], c_ra[cc], c_dec[cc], c_dec[cc]));
+  }
+  for (int o = 16; o; o >>= 1) {
+    double4 other;
+    other.x = __shfl_xor_sync(0xffffffffu, bb.x, o); other.y = __shfl_xor_sync(0xffffffffu, bb.y, o);
+    other.z = __shfl_xor_sync(0xffffffffu, bb.z, o); other.w = __shfl_xor_sync(0xffffffffu, bb.w, o);
+    bb = bbox_merge(bb, other);
+  }
+  const BBox b{bb.x, bb.y, bb.z, bb.w};
+  const Box box = grid_box(b, grid_cells, ra, dec, r);
+  BubbleTest bt;
+  bt.init(ra, dec, c_cos[ca], r);
+  GridAxis gx, gy;
+  gx.init(b.ra_min, b.ra_max, grid_cells);
+  gy.init(b.dec_min, b.dec_max, grid_cells);
+  int cnt = 0;
+  for (int base = lo; base < hi; base += 32) {
+    const int t = base + lane;
+    bool hit = false;
+    int kc = 0;
+    double pra = 0, pdec = 0;
+    if (t < hi) {
+      kc = kidx_sorted[t];
+      const int cc = centre[kc];
+      pra = c_ra[cc]; pdec = c_dec[cc];
+      hit = box.contains(pra, pdec) && bt.inside(pra, pdec, c_cos[cc]);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (MODE == 1 && hit) {
+      const unsigned long long cellkey = (unsigned)(gy.digit_clamped(pdec) * grid_cells + gx.digit_clamped(pra));
+      ekey[eoff[a] + cnt + __popc(mask & ((1u << lane) - 1u))] = (cellkey << 32) | (unsigned)kc;
+    }
+    cnt += __popc(mask);
+  }
+  if (MODE == 0 && lane == 0) ecount[a] = cnt;
+}
+
+__global__ void k_to_ll(int n, const int* in, long long* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// member IDs (column 6) per candidate cluster, to be segment-sorted for the subset test
+__global__ void k_member_ids(long long total, const int* rows, View G, double* ids) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) ids[i] = G.at(rows[i], 6);
+}
+
+// Per event (one warp): partner lookup, the "c is not a subset of center" test (helper.py:138-146 via
+// fof.py:297-300) and the static loser of the contest (cluster.py:65-82).
+__global__ void k_event_static(int K, long long E, const long long* eoff, const unsigned long long* ekey_sorted,
+                               const int* first_by_id, const int* centre, const double* c_id, const double* c_N,
+                               const double* c_mag, const long long* moff, const double* ids_sorted, int* ev_a,
+                               int* ev_c, int* ev_loser, int* state) {
+  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  // owner a of event e: last a with eoff[a] <= e
+  int lo = 0, hi = K;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (eoff[mid] <= e) lo = mid; else hi = mid;
+  }
+  const int a = lo;
+  const int kc = (int)(unsigned)(ekey_sorted[e] & 0xffffffffull);
+  const int c = first_by_id[kc];
+  const int ca = centre[a];
+  bool eligible = false;
+  int loser = -1;
+  if (c >= 0 && !(c_id[ca] == c_id[centre[c]])) {
+    // any member id of c missing from a's (sorted) ids?
+    const long long a0 = moff[a], a1 = moff[a + 1], s0 = moff[c], s1 = moff[c + 1];
+    bool missing = false;
+    for (long long t = s0 + lane; t < s1 && !missing; t += 32) {
+      const double v = ids_sorted[t];
+      long long x = a0, y = a1;
+      while (x < y) {
+        const long long mid = (x + y) >> 1;
+        if (ids_sorted[mid] < v) x = mid + 1; else y = mid;
+      }
+      if (!(x < a1 && ids_sorted[x] == v)) missing = true;
+    }
+    eligible = __any_sync(0xffffffffu, missing);
+    const int cc = centre[c];
+    const double Nc = c_N[cc], Na = c_N[ca];
+    if (Nc > Na) loser = a;
+    else if (Nc < Na) loser = c;
+    else if (fabs(c_mag[cc]) > fabs(c_mag[ca])) loser = a;
+    else loser = c;
+  }
+  if (lane == 0) {
+    ev_a[e] = a;
+    ev_c[e] = c;
+    ev_loser[e] = eligible ? loser : -1;
+    state[e] = eligible ? 0 : 2;  // 0 undecided, 1 fired, 2 not fired
+  }
+}
+
+__global__ void k_loser_keys(long long E, const int* ev_loser, int K, unsigned long long* key) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int l = ev_loser[e];
+  key[e] = ((unsigned long long)(unsigned)(l < 0 ? K : l) << 32) | (unsigned)e;
+}
+
+__global__ void k_loser_starts(long long E, const unsigned long long* key, int K, long long* start) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > E) return;
+  const int cur = k < E ? (int)(key[k] >> 32) : K + 1;
+  const int prev = k > 0 ? (int)(key[k - 1] >> 32) : -1;
+  for (int c = prev + 1; c <= cur && c <= K + 1; ++c) start[c] = k;
+}
+
+// One relaxation round of the ordered contests: an event fires iff it is eligible and neither of its
+// clusters lost an earlier fired event (fof.py:294-310 with the in-place mutation of Q6).
+__global__ void k_event_round(long long E, const int* ev_a, const int* ev_c, const long long* lstart,
+                              const unsigned long long* lkey_sorted, volatile int* state, int* undecided) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E || state[e] != 0) return;
+  bool dead = false, pending = false;
+  const int xs[2] = {ev_a[e], ev_c[e]};
+  for (int s = 0; s < 2 && !dead; ++s) {
+    const int x = xs[s];
+    for (long long t = lstart[x]; t < lstart[x + 1]; ++t) {
+      const long long e2 = (long long)(unsigned)(lkey_sorted[t] & 0xffffffffull);
+      if (e2 >= e) break;
+      const int st = state[e2];
+      if (st == 1) { dead = true; break; }
+      if (st == 0) pending = true;
+    }
+  }
+  if (dead) state[e] = 2;
+  else if (!pending) state[e] = 1;
+  else atomicAdd(undecided, 1);
+}
+
+__global__ void k_cluster_keep(int K, const long long* lstart, const unsigned long long* lkey_sorted, const int* state,
+                               int* keep) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= K) return;
+  int alive = 1;
+  for (long long t = lstart[x]; t < lstart[x + 1]; ++t)
+    if (state[(long long)(unsigned)(lkey_sorted[t] & 0xffffffffull)] == 1) { alive = 0; break; }
+  keep[x] = alive;
+}
+
+__global__ void k_sublist_sizes(int K2, const int* sel, const long long* off, long long* len) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K2) len[k] = off[sel[k] + 1] - off[sel[k]];
+}
+
+__global__ void k_sublist_gather(int K2, const int* sel, const int* centre, const long long* off, const int* rows,
+                                 const long long* off2, int* centre2, int* rows2) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K2) return;
+  const int s = sel[k];
+  const long long src = off[s], dst = off2[k], len = off[s + 1] - off[s];
+  for (long long t = lane; t < len; t += 32) rows2[dst + t] = rows[src + t];
+  if (lane == 0) centre2[k] = centre[s];
+}
+
+static void sublist(fofb_handle* h, const ClusterList& in, const int* keep_flags, ClusterList& out, OverlapScratch& sc) {
+  cudaStream_t st = h->stream;
+  out.K = 0;
+  out.total = 0;
+  if (in.K == 0) return;
+  const int B = 256;
+  int* iota = sc.flag.alloc(in.K);
+  k_iota<<<grid_for(in.K, B), B, 0, st>>>(in.K, iota);
+  FOFB_LAUNCH_CHECK(h);
+  int* sel = sc.sel.alloc(in.K);
+  int* dcount = sc.selcount.alloc(1);
+  size_t bytes = 0;
+  FOFB_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, iota, keep_flags, sel, dcount, in.K, st));
+  FOFB_CUDA(cub::DeviceSelect::Flagged(cub_tmp(h, bytes), bytes, iota, keep_flags, sel, dcount, in.K, st));
+  count_launch(h, 2);
+  const int K2 = d2h_scalar(h, dcount);
+  out.K = K2;
+  if (K2 == 0) return;
+  long long* len = sc.elen.alloc((size_t)K2 + 1);
+  long long* off2 = out.off.alloc((size_t)K2 + 1);
+  k_sublist_sizes<<<grid_for(K2, B), B, 0, st>>>(K2, sel, in.off.p, len);
+  FOFB_LAUNCH_CHECK(h);
+  out.total = scan_offsets(h, len, off2, K2);
+  k_sublist_gather<<<grid_for((int64_t)K2 * 32, 128), 128, 0, st>>>(K2, sel, in.centre.p, in.off.p, in.rows.p, off2,
+                                                                    out.centre.alloc(K2),
+                                                                    out.rows.alloc((size_t)std::max<long long>(out.total, 1)));
+  FOFB_LAUNCH_CHECK(h);
+}
+
+// ---- stage 3: would the BCG replacement of fof.py:346-367 ever fire? -----------------------------------------------
+__global__ void k_bcg_check(int K, const int* centre, const long long* off, const int* rows, View G,
+                            const double* ra_row, const double* dec_row, const double* cos_row, const double* c_ra,
+                            const double* c_dec, const double* c_cos, const double* c_thvir, const double* c_mag,
+                            const double* c_id, double frac, int grid_cells, int* fired) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const int c = centre[k];
+  const long long s0 = off[k], s1 = off[k + 1];
+  double4 bb = make_double4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+  for (long long t = s0 + lane; t < s1; t += 32) {
+    const int row = rows[t];
+    bb = bbox_merge(bb, make_double4(ra_row[row], ra_row[row], dec_row[row], dec_row[row]));
+  }
+  for (int o = 16; o; o >>= 1) {
+    double4 other;
+    other.x = __shfl_xor_sync(0xffffffffu, bb.x, o); other.y = __shfl_xor_sync(0xffffffffu, bb.y, o);
+    other.z = __shfl_xor_sync(0xffffffffu, bb.z, o); other.w = __shfl_xor_sync(0xffffffffu, bb.w, o);
+    bb = bbox_merge(bb, other);
+  }
+  const BBox b{bb.x, bb.y, bb.z, bb.w};
+  const double r = frac * c_thvir[c];
+  const Box box = grid_box(b, grid_cells, c_ra[c], c_dec[c], r);
+  BubbleTest bt;
+  bt.init(c_ra[c], c_dec[c], c_cos[c], r);
+  const double mag = fabs(c_mag[c]);
+  bool fire = false;
+  // conservative: ANY in-radius member with |col 3| > |bcg_absMag| and col 4 != gal_id could become the
+  // "brightest" pick, whatever the mask against existing centres removes
+  for (long long t = s0 + lane; t < s1; t += 32) {
+    const int row = rows[t];
+    if (box.contains(ra_row[row], dec_row[row]) && bt.inside(ra_row[row], dec_row[row], cos_row[row]) &&
+        fabs(G.at(row, 3)) > mag && G.at(row, 4) != c_id[c])
+      fire = true;
+  }
+  if (__any_sync(0xffffffffu, fire) && lane == 0) atomicAdd(fired, 1);
+}
+
+static OverlapScratch& scratch() {
+  static OverlapScratch* s = new OverlapScratch();  // device buffers live until process exit
+  return *s;
+}
+
+void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
+  cudaStream_t st = h->stream;
+  OverlapScratch& sc = scratch();
+  const int B = 256;
+  const int K = S.candidates.K;
+  S.merged.K = S.bcg.K = 0;
+  S.merged.total = S.bcg.total = 0;
+  if (K == 0) return;
+  const fofb_params& p = S.params;
+  size_t bytes = 0;
+  // clusters sorted by centre redshift -> velocity windows over the candidate list
+  k_cluster_z<<<grid_for(K, B), B, 0, st>>>(K, S.candidates.centre.p, S.c_z.p, S.c_id.p, sc.kz.alloc(K), sc.kidx.alloc(K),
+                                            sc.idk.alloc(K), sc.idv.alloc(K));
+  FOFB_LAUNCH_CHECK(h);
+  sc.kz_sorted.alloc(K); sc.kidx_sorted.alloc(K); sc.idk_sorted.alloc(K); sc.idv_sorted.alloc(K);
+  FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, sc.kz.p, sc.kz_sorted.p, sc.kidx.p, sc.kidx_sorted.p, K, 0, 64, st));
+  FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, sc.kz.p, sc.kz_sorted.p, sc.kidx.p, sc.kidx_sorted.p, K, 0, 64, st));
+  FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, sc.idk.p, sc.idk_sorted.p, sc.idv.p, sc.idv_sorted.p, K, 0, 64, st));
+  count_launch(h, 16);
+  k_first_by_id<<<grid_for(K, B), B, 0, st>>>(K, sc.idk_sorted.p, sc.idv_sorted.p, sc.first_by_id.alloc(K));
+  FOFB_LAUNCH_CHECK(h);
+  // events
+  const int wblocks = grid_for((int64_t)K * 32, 128);
+  int* ecount = sc.ecount.alloc(K);
+  k_overlap_events<0><<<wblocks, 128, 0, st>>>(K, S.candidates.centre.p, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
+                                               S.c_cos.p, S.c_z.p, S.c_thvir.p, p.max_velocity, p.grid_cells, ecount, nullptr, nullptr);
+  FOFB_LAUNCH_CHECK(h);
+  long long* elen = sc.elen.alloc((size_t)K + 1);
+  long long* eoff = sc.eoff.alloc((size_t)K + 1);
+  k_to_ll<<<grid_for(K, B), B, 0, st>>>(K, ecount, elen);
+  FOFB_LAUNCH_CHECK(h);
+  const long long E = scan_offsets(h, elen, eoff, K);
+  FOFB_REQUIRE(E < (1ll << 31), "too many overlap events");
+  // event states [0, E) followed by the per-cluster keep flags
+  int* keep_flags = sc.state.alloc((size_t)std::max<long long>(E, 1) + K + 8) + std::max<long long>(E, 1);
+  if (E > 0) {
+    unsigned long long* ekey = sc.ekey.alloc((size_t)E);
+    unsigned long long* ekey_s = sc.ekey_sorted.alloc((size_t)E);
+    k_overlap_events<1><<<wblocks, 128, 0, st>>>(K, S.candidates.centre.p, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
+                                                 S.c_cos.p, S.c_z.p, S.c_thvir.p, p.max_velocity, p.grid_cells, ecount, eoff, ekey);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
+    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
+    count_launch(h, 4);
+    // sorted member ids per candidate cluster
+    const long long total = S.candidates.total;
+    double* ids = sc.ids.alloc((size_t)total);
+    double* ids_s = sc.ids_sorted.alloc((size_t)total);
+    k_member_ids<<<grid_for(total, B), B, 0, st>>>(total, S.candidates.rows.p, S.G, ids);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ids, ids_s, total, K, S.candidates.off.p, S.candidates.off.p + 1, st));
+    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ids, ids_s, total, K, S.candidates.off.p, S.candidates.off.p + 1, st));
+    count_launch(h, 4);
+    int* ev_a = sc.ev_a.alloc((size_t)E);
+    int* ev_c = sc.ev_c.alloc((size_t)E);
+    int* ev_l = sc.ev_loser.alloc((size_t)E);
+    int* state = sc.state.p;
+    k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, S.candidates.centre.p, S.c_id.p,
+                                                          S.c_N.p, S.c_mag.p, S.candidates.off.p, ids_s, ev_a, ev_c, ev_l, state);
+    FOFB_LAUNCH_CHECK(h);
+    // per-cluster lists of the events it would lose, in event order
+    unsigned long long* lkey = sc.lkey.alloc((size_t)E);
+    unsigned long long* lkey_s = sc.lkey_sorted.alloc((size_t)E);
+    k_loser_keys<<<grid_for(E, B), B, 0, st>>>(E, ev_l, K, lkey);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, lkey, lkey_s, (int)E, 0, 64, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp(h, bytes), bytes, lkey, lkey_s, (int)E, 0, 64, st));
+    count_launch(h, 8);
+    long long* lstart = sc.loff.alloc((size_t)K + 3);
+    k_loser_starts<<<grid_for(E + 1, B), B, 0, st>>>(E, lkey_s, K, lstart);
+    FOFB_LAUNCH_CHECK(h);
+    int* und = sc.selcount.alloc(1);
+    for (int it = 0;; ++it) {
+      FOFB_CUDA(cudaMemsetAsync(und, 0, sizeof(int), st));
+      k_event_round<<<grid_for(E, B), B, 0, st>>>(E, ev_a, ev_c, lstart, lkey_s, state, und);
+      FOFB_LAUNCH_CHECK(h);
+      if (d2h_scalar(h, und) == 0) break;
+      if (it > 100000) throw Error(FOFB_ERR_INTERNAL, "overlap contests did not converge");
+    }
+    k_cluster_keep<<<grid_for(K, B), B, 0, st>>>(K, lstart, lkey_s, state, keep_flags);
+    FOFB_LAUNCH_CHECK(h);
+  } else {
+    FOFB_CUDA(cudaMemsetAsync(keep_flags, 1, sizeof(int) * K, st));  // any non-zero value keeps
+  }
+  sublist(h, S.candidates, keep_flags, S.merged, sc);
+
+  // stage 3: BCG recentring (fof.py:318-371).  Under the pipeline's column layout the replacement
+  // test compares |z_lower| with |RMag| and never fires; the device path verifies that.
+  if (S.merged.K > 0) {
+    int* fired = sc.selcount.alloc(1);
+    FOFB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), st));
+    k_bcg_check<<<grid_for((int64_t)S.merged.K * 32, 128), 128, 0, st>>>(
+        S.merged.K, S.merged.centre.p, S.merged.off.p, S.merged.rows.p, S.G, S.cat.ra_row.p, S.cat.dec_row.p, S.cos_row.p,
+        S.c_ra.p, S.c_dec.p, S.c_cos.p, S.c_thvir.p, S.c_mag.p, S.c_id.p, p.bcg_fraction, p.grid_cells, fired);
+    FOFB_LAUNCH_CHECK(h);
+    if (d2h_scalar(h, fired) != 0)
+      throw Error(FOFB_ERR_UNSUPPORTED,
+                  "BCG recentring (fof.py:346-367) would replace a centre: |column 3| exceeds |column 5| for a member "
+                  "near a cluster centre. The device path implements the pipeline column layout, where this never happens.");
+  }
+  // bcg_clusters == merged clusters (same order)
+  S.bcg.K = S.merged.K;
+  S.bcg.total = S.merged.total;
+}
+
+// ---- stage 4 ----------------------------------------------------------------------------------------------------------
+// N := number of OWN members within theta_0.5 of the centre (fof.py:377-379; helper.py:181-188)
+__global__ void k_own_count(int K, const int* centre, const long long* off, const int* rows, const double* ra_row,
+                            const double* dec_row, const double* cos_row, const double* c_ra, const double* c_dec,
+                            const double* c_cos, const double* c_th05, int grid_cells, int* N_out) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const int c = centre[k];
+  const long long s0 = off[k], s1 = off[k + 1];
+  double4 bb = make_double4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+  for (long long t = s0 + lane; t < s1; t += 32) {
+    const int row = rows[t];
+    bb = bbox_merge(bb, make_double4(ra_row[row], ra_row[row], dec_row[row], dec_row[row]));
+  }
+  for (int o = 16; o; o >>= 1) {
+    double4 other;
+    other.x = __shfl_xor_sync(0xffffffffu, bb.x, o); other.y = __shfl_xor_sync(0xffffffffu, bb.y, o);
+    other.z = __shfl_xor_sync(0xffffffffu, bb.z, o); other.w = __shfl_xor_sync(0xffffffffu, bb.w, o);
+    bb = bbox_merge(bb, other);
+  }
+  const BBox b{bb.x, bb.y, bb.z, bb.w};
+  const double ra = c_ra[c], dec = c_dec[c], r = c_th05[c];
+  const bool oof = (ra - r > b.ra_max + 1e-6) || (ra + r < b.ra_min - 1e-6) || (dec - r > b.dec_max + 1e-6) ||
+                   (dec + r < b.dec_min - 1e-6);
+  const Box box = grid_box(b, grid_cells, ra, dec, r);
+  BubbleTest bt;
+  bt.init(ra, dec, c_cos[c], r);
+  int cnt = 0;
+  if (!oof)
+    for (long long t = s0 + lane; t < s1; t += 32) {
+      const int row = rows[t];
+      if (box.contains(ra_row[row], dec_row[row]) && bt.inside(ra_row[row], dec_row[row], cos_row[row])) ++cnt;
+    }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) N_out[k] = cnt;
+}
+
+// per cluster: window bbox and the "all 300 points out of field" flag (helper.py:207-213, App. B.1)
+__global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, const int* c_wlo, const int* c_whi,
+                          const double* c_th05, const double* rra, const double* rdec, double4* bbox, int* all_oof) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const int c = centre[k];
+  const int lo = c_wlo[c], hi = c_whi[c];
+  BBox b{0, 0, 0, 0};
+  if (lane == 0 && hi > lo) b = range_bbox(cat, lo, hi);
+  b.ra_min = __shfl_sync(0xffffffffu, b.ra_min, 0); b.ra_max = __shfl_sync(0xffffffffu, b.ra_max, 0);
+  b.dec_min = __shfl_sync(0xffffffffu, b.dec_min, 0); b.dec_max = __shfl_sync(0xffffffffu, b.dec_max, 0);
+  const double r = c_th05[c];
+  bool all = true;
+  for (int t = lane; t < npts; t += 32) {
+    const double ra = rra[(long long)k * npts + t], dec = rdec[(long long)k * npts + t];
+    const bool oof = (ra - r > b.ra_max + 1e-6) || (ra + r < b.ra_min - 1e-6) || (dec - r > b.dec_max + 1e-6) ||
+                     (dec + r < b.dec_min - 1e-6);
+    if (!oof) all = false;
+  }
+  all = __all_sync(0xffffffffu, all);
+  if (lane == 0) {
+    bbox[k] = make_double4(b.ra_min, b.ra_max, b.dec_min, b.dec_max);
+    all_oof[k] = (all || hi <= lo) ? 1 : 0;
+  }
+}
+
+// one thread per (cluster, random point): galaxies of the centre's velocity window within theta_0.5
+__global__ void k_od_count(long long total, int npts, const int* centre, CellListView cl, const int* c_wlo,
+                           const int* c_whi, const double* c_th05, const double4* bbox, const int* all_oof,
+                           const double* rra, const double* rdec, int grid_cells, int* counts) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int k = (int)(q / npts);
+  int cnt = 0;
+  if (!all_oof[k]) {
+    const int c = centre[k];
+    const int wlo = c_wlo[c], whi = c_whi[c];
+    const double r = c_th05[c];
+    const double ra = rra[q], dec = rdec[q];
+    const double4 b4 = bbox[k];
+    const BBox b{b4.x, b4.y, b4.z, b4.w};
+    const Box box = grid_box(b, grid_cells, ra, dec, r);
+    BubbleTest bt;
+    bt.init(ra, dec, cos(__dmul_rn(dec, kDeg2Rad)), r);
+    const double reach = ra_reach(r, dec);
+    const int x0 = cl.cx_of(ra - reach), x1 = cl.cx_of(ra + reach);
+    const int y0 = cl.cy_of(dec - r * 1.000001), y1 = cl.cy_of(dec + r * 1.000001);
+    for (int yy = y0; yy <= y1; ++yy)
+      for (int xx = x0; xx <= x1; ++xx) {
+        const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
+        int a = s, bnd = e;
+        while (a < bnd) { const int mid = (a + bnd) >> 1; if (cl.zrank[mid] < wlo) a = mid + 1; else bnd = mid; }
+        const int first = a;
+        bnd = e;
+        while (a < bnd) { const int mid = (a + bnd) >> 1; if (cl.zrank[mid] < whi) a = mid + 1; else bnd = mid; }
+        for (int j = first; j < a; ++j) {
+          const double pra = cl.ra[j], pdec = cl.dec[j];
+          if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
+        }
+      }
+  }
+  counts[q] = cnt;
+}
+
+// D = (N - mean) / rms over the 300 counts (helper.py:216-221), and the final selection (fof.py:385-390)
+__global__ void k_od_finish(int K, int npts, const int* counts, const int* N_own, const long long* off, double overdensity,
+                            int min_count, int richness, double* D_out, int* keep) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  long long s1 = 0, s2 = 0;
+  for (int t = lane; t < npts; t += 32) {
+    const long long v = counts[(long long)k * npts + t];
+    s1 += v;
+    s2 += v * v;
+  }
+  for (int o = 16; o; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    const double mean = __ddiv_rn((double)s1, (double)npts);
+    const double rms = sqrt(__ddiv_rn((double)s2, (double)npts));
+    const double D = __ddiv_rn(__dsub_rn((double)N_own[k], mean), rms);
+    D_out[k] = D;
+    keep[k] = (N_own[k] >= min_count && (off[k + 1] - off[k]) >= richness && D >= overdensity) ? 1 : 0;
+  }
+}
+
+__global__ void k_gather_nd(int K2, const int* sel, const int* N_in, const double* D_in, int* N_out, double* D_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K2) return;
+  N_out[k] = N_in[sel[k]];
+  D_out[k] = D_in[sel[k]];
+}
+
+void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int mem) {
+  cudaStream_t st = h->stream;
+  OverlapScratch& sc = scratch();
+  const fofb_params& p = params;
+  if (!ran) throw Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
+  final_.K = 0;
+  final_.total = 0;
+  finished = true;
+  const int K = merged.K;
+  if (K == 0) return;
+  const int npts = p.n_random;
+  FOFB_REQUIRE(npts > 0, "n_random must be positive");
+  FOFB_REQUIRE(rand_ra && rand_dec, "random points are null");
+  const long long total = (long long)K * npts;
+  const double *rra = rand_ra, *rdec = rand_dec;
+  if (mem == 0) {
+    double* a = h->upload2.alloc((size_t)total * 2);
+    FOFB_CUDA(cudaMemcpyAsync(a, rand_ra, sizeof(double) * total, cudaMemcpyHostToDevice, st));
+    FOFB_CUDA(cudaMemcpyAsync(a + total, rand_dec, sizeof(double) * total, cudaMemcpyHostToDevice, st));
+    rra = a;
+    rdec = a + total;
+  }
+  const int B = 256;
+  const int wblocks = grid_for((int64_t)K * 32, 128);
+  int* N_own = merged.N.alloc(K);
+  double* D = merged.D.alloc(K);
+  k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,
+                                       c_ra.p, c_dec.p, c_cos.p, c_th05.p, p.grid_cells, N_own);
+  FOFB_LAUNCH_CHECK(h);
+  double4* bb = sc.bbox.alloc(K);
+  int* oof = sc.ecount.alloc(K);
+  k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, bb, oof);
+  FOFB_LAUNCH_CHECK(h);
+  int* counts = sc.ev_a.alloc((size_t)total);
+  k_od_count<<<grid_for(total, 128), 128, 0, st>>>(total, npts, merged.centre.p, small.view(), c_wlo.p, c_whi.p, c_th05.p, bb,
+                                                   oof, rra, rdec, p.grid_cells, counts);
+  FOFB_LAUNCH_CHECK(h);
+  int* keep = sc.state.alloc(K);
+  k_od_finish<<<wblocks, 128, 0, st>>>(K, npts, counts, N_own, merged.off.p, p.overdensity, p.min_count, p.richness, D, keep);
+  FOFB_LAUNCH_CHECK(h);
+  sublist(h, merged, keep, final_, sc);
+  if (final_.K > 0) {
+    k_gather_nd<<<grid_for(final_.K, B), B, 0, st>>>(final_.K, sc.sel.p, N_own, D, final_.N.alloc(final_.K), final_.D.alloc(final_.K));
+    FOFB_LAUNCH_CHECK(h);
+  }
+}
+
+}  // namespace fofb

@@ -11,6 +11,7 @@ struct QueryRec {  // one bubble query: cell-box bounds, radius, z-rank window
 };
 
 struct Catalog;
+struct CellList;
 
 struct Stage0 {
   bool valid = false;
@@ -20,7 +21,7 @@ struct Stage0 {
   DBuf<double> theta, theta_max;
   DBuf<int> N_row, cand_rows, num_sel;
   DBuf<unsigned long long> key_all, key_sel, key_sorted;
-  void run(fofb_handle* h, const fofb_params& p, Catalog& cat);
+  void run(fofb_handle* h, const fofb_params& p, Catalog& cat, CellList& cells);
 };
 
 }  // namespace fofb

@@ -104,6 +104,33 @@ int fofb_number_counts(fofb_handle* h, const fofb_params* p, const fofb_matrix* 
                        int32_t* N_out, int32_t N_mem, int64_t* n_candidates);
 int fofb_candidate_order(fofb_handle* h, int32_t* rows_out, int32_t rows_mem, int64_t capacity);
 
+/* ---- stages 1-4: FoF() (fof.py:98-392) ---------------------------------------------------------------
+ * fofb_fof_run    : stage 1 (per-centre virial bubble, hop 1 / hop 2, richness gate, greedy tracker,
+ *                   fof.py:145-246), stage 2 (ordered overlap contests, fof.py:258-314; cluster.py:65-82)
+ *                   and stage 3 (BCG check, fof.py:318-371).  `galaxies` (n x C) and `centres` (m x C),
+ *                   C >= 8, in the column layout above; row i of `centres` has priority i.  On return
+ *                   *n_clusters is the number of clusters that reach stage 4 and bbox[4] =
+ *                   (ra_min, ra_max, dec_min, dec_max) of `galaxies` (the bounds helper.py:197-202 draws
+ *                   its uniform points from).
+ * fofb_fof_finish : stage 4 (fof.py:374-392): N := own members within theta_0.5, D from n_random points
+ *                   per cluster.  rand_ra / rand_dec hold n_clusters * n_random values, cluster-major, drawn
+ *                   by the CALLER from numpy's legacy global RNG exactly as helper.py:197-202 does (RA block
+ *                   then Dec block per cluster), so a seeded reference run and this path see the same points.
+ * fofb_fof_sizes / fofb_fof_fetch : read a cluster list kept in the handle.  which = 0 candidates after
+ *                   stage 1, 1 after overlap removal, 2 after the BCG stage, 3 final.  offsets[K+1] (int64),
+ *                   members[total] (int32 galaxy row indices in the reference's member order), centre[K]
+ *                   (int32 row of `centres`), N[K] (float64 Cluster.N), D[K] (float64 Cluster.D).
+ *                   Any output pointer may be NULL.
+ */
+int fofb_fof_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, const fofb_matrix* centres,
+                 int64_t* n_clusters, double* bbox);
+int fofb_fof_finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int32_t mem, int64_t* n_final);
+int fofb_fof_sizes(fofb_handle* h, int32_t which, int64_t* n_clusters, int64_t* n_members);
+int fofb_fof_fetch(fofb_handle* h, int32_t which, int64_t* offsets, int32_t* members, int32_t* centre, double* N,
+                   double* D);
+/* diagnostics of the last fofb_fof_run: priority rounds and centres actually evaluated */
+int fofb_fof_stats(fofb_handle* h, int64_t* rounds, int64_t* evaluated);
+
 #ifdef __cplusplus
 }
 #endif
