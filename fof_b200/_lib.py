@@ -78,6 +78,9 @@ def load():
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
+        "fofb_three_sigma": (C.c_int, [vp, P(Params), i64, vp, P(Matrix), vp, vp, vp]),
+        "fofb_virial": (C.c_int, [vp, P(Params), i64, vp, P(Matrix), vp]),
+        "fofb_bootstrap_indices": (C.c_int, [i64, i64, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -197,6 +200,30 @@ class Handle:
         self.check(self.lib.fofb_fof_fetch(self.h, which, off.ctypes.data, mem.ctypes.data, cen.ctypes.data,
                                            N.ctypes.data, D.ctypes.data))
         return off, mem, cen, N, D
+
+    # ---- stages 5-6 ----------------------------------------------------------------------------
+    def three_sigma(self, offsets, members, centres, params):
+        """(out_offsets int64[K+1], out_index int32[kept]) -- positions inside each cluster."""
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        cen = np.ascontiguousarray(centres, dtype=np.float64)
+        K = len(off) - 1
+        m, keep = matrix_of(members)
+        out_off = np.zeros(K + 1, dtype=np.int64)
+        out_idx = np.empty(max(int(off[-1]), 1), dtype=np.int32)
+        self.check(self.lib.fofb_three_sigma(self.h, C.byref(params), K, off.ctypes.data, C.byref(m), cen.ctypes.data,
+                                             out_off.ctypes.data, out_idx.ctypes.data))
+        del keep
+        return out_off, out_idx[:out_off[K]]
+
+    def virial(self, offsets, members, params):
+        """(K, 8): mass, mass_err, vel_disp, vel_disp_err, radius, total_absmag, mean z, n."""
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        K = len(off) - 1
+        m, keep = matrix_of(members)
+        out = np.empty((K, 8))
+        self.check(self.lib.fofb_virial(self.h, C.byref(params), K, off.ctypes.data, C.byref(m), out.ctypes.data))
+        del keep
+        return out
 
     def fof_stats(self):
         r, e = C.c_int64(), C.c_int64()

@@ -5,6 +5,7 @@
 #include "catalog_host.cuh"
 #include "stage0.cuh"
 #include "fof_stage.cuh"
+#include "clean.cuh"
 
 namespace fofb {
 
@@ -168,6 +169,8 @@ void fofb_destroy(fofb_handle* h) {
   h->catalog = nullptr;
   delete h->fof;
   h->fof = nullptr;
+  delete h->clean;
+  h->clean = nullptr;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -391,6 +394,52 @@ int fofb_fof_stats(fofb_handle* h, int64_t* rounds, int64_t* evaluated) {
   if (!h || !h->fof) return FOFB_ERR_STATE;
   if (rounds) *rounds = h->fof->rounds;
   if (evaluated) *evaluated = h->fof->evaluated;
+  return FOFB_OK;
+}
+
+// ---- stages 5-6 ---------------------------------------------------------------------------------------
+int fofb_three_sigma(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* offsets, const fofb_matrix* members,
+                     const double* centres, int64_t* out_offsets, int32_t* out_index) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(offsets && members && centres && out_offsets && out_index, "three_sigma: null argument");
+  FOFB_REQUIRE(K >= 0 && K < (1ll << 31), "three_sigma: bad K");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->clean) h->clean = new CleanState();
+  Timed timer(h);
+  const View M = to_device(h, *members, h->upload);
+  h->clean->three_sigma(h, *p, (int)K, reinterpret_cast<const long long*>(offsets), M, centres, p->n_bins,
+                        reinterpret_cast<long long*>(out_offsets), out_index);
+  timer.stop();
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_virial(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* offsets, const fofb_matrix* members,
+                double* out) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(offsets && members && out, "virial: null argument");
+  FOFB_REQUIRE(K >= 0 && K < (1ll << 31), "virial: bad K");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->clean) h->clean = new CleanState();
+  Timed timer(h);
+  const View M = to_device(h, *members, h->upload);
+  h->clean->virial(h, *p, (int)K, reinterpret_cast<const long long*>(offsets), M, out);
+  timer.stop();
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out) {
+  if (n < 1 || count < 0 || !out) return FOFB_ERR_INVALID;
+  if (n == 1) {
+    for (int64_t i = 0; i < count; ++i) out[i] = 0;
+    return FOFB_OK;
+  }
+  fofb::bootstrap_indices_host(n, count, out);
   return FOFB_OK;
 }
 

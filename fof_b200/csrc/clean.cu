@@ -1,0 +1,481 @@
+// Stage 5 (three_sigma / interloper_removal, fof.py:396-516) and stage 6 (virial mass estimator,
+// analysis/mass_estimator.py:36-112,148-184; mass_analysis.py:8-44) over label-sorted members
+// (kernels K12, K13 of DESIGN.md).
+#include <cub/cub.cuh>
+
+#include <random>
+
+#include "clean.cuh"
+
+namespace fofb {
+
+static unsigned char* cub_tmp(fofb_handle* h, size_t bytes) { return h->cub_tmp.alloc(bytes + 256); }
+
+// owner cluster of member t: last k with off[k] <= t
+__device__ __forceinline__ int owner_of(const long long* off, int K, long long t) {
+  int lo = 0, hi = K;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---- numpy's pairwise summation (add.reduce on a contiguous float64 vector), serial -------------
+// Same blocking as numpy/core/src/umath/loops_utils.h.src pairwise_sum: < 8 plain loop, <= 128 eight
+// accumulators, else split in halves rounded to a multiple of 8.
+template <class F>
+__device__ __forceinline__ double np_pairwise_leaf(F get, long long lo, long long n) {  // n <= 128
+  if (n < 8) {
+    double res = 0.0;
+    for (long long i = 0; i < n; ++i) res = __dadd_rn(res, get(lo + i));
+    return res;
+  }
+  double r[8];
+  for (int j = 0; j < 8; ++j) r[j] = get(lo + j);
+  long long i;
+  for (i = 8; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], get(lo + i + j));
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, get(lo + i));
+  return res;
+}
+
+template <class F>
+__device__ double np_pairwise_sum(F get, long long lo, long long n) {
+  if (n <= 128) return np_pairwise_leaf(get, lo, n);
+  // numpy recurses on halves (n2 = n/2 rounded down to a multiple of 8); explicit post-order stack
+  long long s_lo[40], s_n[40];
+  double s_left[40];
+  int s_state[40];
+  int sp = 0;
+  s_lo[0] = lo; s_n[0] = n; s_state[0] = 0;
+  double ret = 0.0;
+  while (sp >= 0) {
+    const long long cl = s_lo[sp], cn = s_n[sp];
+    if (cn <= 128) {
+      ret = np_pairwise_leaf(get, cl, cn);
+      --sp;
+      continue;
+    }
+    long long n2 = cn / 2;
+    n2 -= n2 % 8;
+    if (s_state[sp] == 0) {
+      s_state[sp] = 1;
+      ++sp;
+      s_lo[sp] = cl; s_n[sp] = n2; s_state[sp] = 0;
+    } else if (s_state[sp] == 1) {
+      s_left[sp] = ret;
+      s_state[sp] = 2;
+      ++sp;
+      s_lo[sp] = cl + n2; s_n[sp] = cn - n2; s_state[sp] = 0;
+    } else {
+      ret = __dadd_rn(s_left[sp], ret);
+      --sp;
+    }
+  }
+  return ret;
+}
+
+// ---- K12a: per member velocity and projected radius (fof.py:418-431) ---------------------------------
+__global__ void k_member_vr(long long total, int K, const long long* off, View M, const double* cen, Cosmo cosmo,
+                            double* vel, double* rad, double* dA_out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int k = owner_of(off, K, t);
+  const double cra = cen[3 * k], cdec = cen[3 * k + 1], cz = cen[3 * k + 2];
+  vel[t] = redshift_to_velocity(M.at(t, 2), cz);
+  const double sep = vincenty_rad(__dmul_rn(cra, kDeg2Rad), __dmul_rn(cdec, kDeg2Rad), __dmul_rn(M.at(t, 0), kDeg2Rad),
+                                  __dmul_rn(M.at(t, 1), kDeg2Rad));
+  const double dA = cosmo_angular_diameter_distance(cosmo, cz);
+  rad[t] = __dmul_rn(__dmul_rn(__dmul_rn(sep, kRad2Deg), dA), kDeg2Rad);
+  if (t == off[k]) dA_out[k] = dA;
+}
+
+// ---- K12b: radial bins (np.linspace + np.digitize, fof.py:436-437), stable partition by bin -----------
+__global__ void k_bin_members(int K, const long long* off, const double* rad, int nbins, int* perm, int* bin_start) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const long long s0 = off[k];
+  const int n = (int)(off[k + 1] - s0);
+  int* bs = bin_start + (long long)k * (nbins + 2);
+  if (n == 0) {
+    for (int b = lane; b < nbins + 2; b += 32) bs[b] = 0;
+    return;
+  }
+  double mn = INFINITY, mx = -INFINITY;
+  for (int t = lane; t < n; t += 32) {
+    const double r = rad[s0 + t];
+    mn = fmin(mn, r);
+    mx = fmax(mx, r);
+  }
+  for (int o = 16; o; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  // np.linspace(start, stop, num): step = (stop-start)/(num-1); y = arange(num)*step + start; y[-1] = stop
+  const int div = nbins - 1;
+  const double delta = __dsub_rn(mx, mn);
+  const double step = div > 0 ? __ddiv_rn(delta, (double)div) : 0.0;
+  auto edge = [&](int i) -> double {
+    if (i == nbins - 1 && nbins > 1) return mx;
+    if (div <= 0) return mn;
+    if (step == 0.0) return __dadd_rn(__dmul_rn(__ddiv_rn((double)i, (double)div), delta), mn);
+    return __dadd_rn(__dmul_rn((double)i, step), mn);
+  };
+  // digitize (bins increasing, right=False): index = #edges <= x
+  int pos = 0;
+  for (int b = 1; b <= nbins; ++b) {
+    if (lane == 0) bs[b] = pos;
+    for (int base = 0; base < n; base += 32) {
+      const int t = base + lane;
+      bool in = false;
+      if (t < n) {
+        const double x = rad[s0 + t];
+        int cnt = 0;
+        for (int i = 0; i < nbins; ++i) cnt += edge(i) <= x ? 1 : 0;
+        in = cnt == b;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (in) perm[s0 + pos + __popc(m & ((1u << lane) - 1u))] = t;
+      pos += __popc(m);
+    }
+  }
+  if (lane == 0) {
+    bs[0] = 0;
+    bs[nbins + 1] = pos;
+  }
+}
+
+// ---- K12c: iterative 3-sigma clipping of one radial bin, one thread per (cluster, bin) (fof.py:439-492)
+__global__ void k_clip_bins(int K, int nbins, const long long* off, const double* vel, const double* rad, int* perm,
+                            const int* bin_start, double* dev, int* kept) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)K * nbins) return;
+  const int k = (int)(g / nbins), b = (int)(g % nbins) + 1;
+  const long long s0 = off[k];
+  const int* bs = bin_start + (long long)k * (nbins + 2);
+  const int lo = bs[b], hi = (b == nbins) ? bs[nbins + 1] : bs[b + 1];
+  int* p = perm + s0 + lo;   // this bin's members (positions inside the cluster), reordered in place
+  double* d = dev + s0 + lo;
+  int len = hi - lo;
+  bool changed = true;
+  while (changed && len > 0) {
+    changed = false;
+    if (len > 2) {
+      auto getv = [&](long long i) -> double { return vel[s0 + p[i]]; };
+      const double mean = __ddiv_rn(np_pairwise_sum(getv, 0, len), (double)len);
+      for (int i = 0; i < len; ++i) d[i] = fabs(__dsub_rn(vel[s0 + p[i]], mean));
+      // stable insertion sort by deviation (np.argsort; ties pinned to the stable order)
+      for (int i = 1; i < len; ++i) {
+        const double di = d[i];
+        const int pi = p[i];
+        int j = i - 1;
+        while (j >= 0 && d[j] > di) {
+          d[j + 1] = d[j];
+          p[j + 1] = p[j];
+          --j;
+        }
+        d[j + 1] = di;
+        p[j + 1] = pi;
+      }
+      if (rad[s0 + p[len - 1]] != 0.0) {  // the largest deviation is not the cluster centre itself
+        const int m = len - 1;
+        if (m > 1) {
+          const double bin_mean = __ddiv_rn(np_pairwise_sum(getv, 0, m), (double)m);
+          double acc = 0.0;  // builtin sum(): sequential
+          for (int i = 0; i < m; ++i) {
+            const double x = __dsub_rn(vel[s0 + p[i]], bin_mean);
+            acc = __dadd_rn(acc, __dmul_rn(x, x));
+          }
+          const double disp = __ddiv_rn(acc, (double)(m - 1));
+          if (fabs(__dsub_rn(vel[s0 + p[len - 1]], bin_mean)) > __dmul_rn(3.0, sqrt(disp))) {
+            --len;
+            changed = true;
+          }
+        }
+      }
+    }
+  }
+  kept[g] = len;
+}
+
+__global__ void k_kept_per_cluster(int K, int nbins, const int* kept, long long* len) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  long long s = 0;
+  for (int b = 0; b < nbins; ++b) s += kept[(long long)k * nbins + b];
+  len[k] = s;
+}
+
+__global__ void k_emit_cleaned(int K, int nbins, const long long* off, const int* perm, const int* bin_start,
+                               const int* kept, const long long* out_off, int* out_index) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const long long s0 = off[k];
+  const int* bs = bin_start + (long long)k * (nbins + 2);
+  long long dst = out_off[k];
+  for (int b = 1; b <= nbins; ++b) {
+    const int lo = bs[b];
+    const int len = kept[(long long)k * nbins + b - 1];
+    for (int t = lane; t < len; t += 32) out_index[dst + t] = perm[s0 + lo + t];
+    dst += len;
+  }
+}
+
+void CleanState::three_sigma(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
+                             const double* centres_host, int nbins, long long* out_off_host, int* out_index_host) {
+  cudaStream_t st = h->stream;
+  FOFB_REQUIRE(K >= 0 && nbins >= 1 && nbins <= 4096, "three_sigma: bad K or n_bins");
+  out_off_host[0] = 0;
+  if (K == 0) return;
+  const long long total = off_host[K];
+  FOFB_REQUIRE(total == M.rows, "three_sigma: offsets do not cover the member matrix");
+  FOFB_REQUIRE(M.cols >= 3, "three_sigma: members need ra, dec, z columns");
+  const int B = 256;
+  const Cosmo cosmo = device_cosmo(h, p);
+  long long* off = d_off.alloc((size_t)K + 1);
+  double* cen = d_cen.alloc((size_t)K * 3);
+  FOFB_CUDA(cudaMemcpyAsync(off, off_host, sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice, st));
+  FOFB_CUDA(cudaMemcpyAsync(cen, centres_host, sizeof(double) * (size_t)K * 3, cudaMemcpyHostToDevice, st));
+  const size_t tt = (size_t)std::max<long long>(total, 1);
+  double* vel = d_vel.alloc(tt);
+  double* rad = d_rad.alloc(tt);
+  double* dev = d_dev.alloc(tt);
+  int* perm = d_perm.alloc(tt);
+  int* bstart = d_bin_start.alloc((size_t)K * (nbins + 2));
+  int* kept = d_kept.alloc((size_t)K * nbins);
+  if (total > 0) {
+    k_member_vr<<<grid_for(total, B), B, 0, st>>>(total, K, off, M, cen, cosmo, vel, rad, d_dA.alloc(K));
+    FOFB_LAUNCH_CHECK(h);
+  }
+  k_bin_members<<<grid_for((int64_t)K * 32, 128), 128, 0, st>>>(K, off, rad, nbins, perm, bstart);
+  FOFB_LAUNCH_CHECK(h);
+  k_clip_bins<<<grid_for((int64_t)K * nbins, 64), 64, 0, st>>>(K, nbins, off, vel, rad, perm, bstart, dev, kept);
+  FOFB_LAUNCH_CHECK(h);
+  long long* len = d_len.alloc((size_t)K + 1);
+  long long* ooff = d_out_off.alloc((size_t)K + 1);
+  k_kept_per_cluster<<<grid_for(K, B), B, 0, st>>>(K, nbins, kept, len);
+  FOFB_LAUNCH_CHECK(h);
+  size_t bytes = 0;
+  FOFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len, ooff, K, st));
+  FOFB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp(h, bytes), bytes, len, ooff, K, st));
+  count_launch(h, 2);
+  int* oidx = d_out_index.alloc(tt);
+  k_emit_cleaned<<<grid_for((int64_t)K * 32, 128), 128, 0, st>>>(K, nbins, off, perm, bstart, kept, ooff, oidx);
+  FOFB_LAUNCH_CHECK(h);
+  FOFB_CUDA(cudaMemcpyAsync(out_off_host, ooff, sizeof(long long) * K, cudaMemcpyDeviceToHost, st));
+  long long last_len = 0;
+  FOFB_CUDA(cudaMemcpyAsync(&last_len, len + (K - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  out_off_host[K] = out_off_host[K - 1] + last_len;
+  if (out_off_host[K] > 0)
+    FOFB_CUDA(cudaMemcpyAsync(out_index_host, oidx, sizeof(int) * out_off_host[K], cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---- stage 6 ----------------------------------------------------------------------------------------------
+// numpy legacy randint(0, n) stream after np.random.seed(1): MT19937 words, masked, rejected if > n-1
+// (astropy bootstrap under NumpyRNGContext(1), mass_estimator.py:178-184).
+static void mt_stream(std::vector<unsigned>& out, size_t count) {
+  std::mt19937 gen(1u);
+  out.resize(count);
+  for (size_t i = 0; i < count; ++i) out[i] = (unsigned)gen();
+}
+
+void bootstrap_indices_host(long long n, long long count, int* out) {
+  std::mt19937 gen(1u);
+  unsigned mask = (unsigned)(n - 1);
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  for (long long i = 0; i < count; ++i) {
+    unsigned v;
+    do { v = (unsigned)gen() & mask; } while (v > (unsigned)(n - 1));
+    out[i] = (int)v;
+  }
+}
+
+constexpr int kVirialThreads = 256;
+constexpr int kBootNum = 100;
+
+// One CTA per cluster.
+__global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const long long* off, View M, Cosmo cosmo,
+                                                                const unsigned* mt, long long mt_len, double mass_unit,
+                                                                double* out, int* status) {
+  const int k = blockIdx.x;
+  if (k >= K) return;
+  const long long s0 = off[k];
+  const int n = (int)(off[k + 1] - s0);
+  const int tid = threadIdx.x;
+  __shared__ double sh[kVirialThreads];
+  __shared__ double boot[kBootNum];
+  __shared__ double s_zbar, s_vdisp, s_zavg_err;
+  __shared__ int s_scan[kVirialThreads];
+  __shared__ long long s_taken;
+  __shared__ int s_fail;
+  double* o = out + (long long)k * 8;
+  if (n < 2) {
+    if (tid == 0) {
+      for (int i = 0; i < 8; ++i) o[i] = NAN;
+      o[7] = n;
+    }
+    return;
+  }
+  auto getz = [&](long long i) -> double { return M.at(s0 + i, 2); };
+  if (tid == 0) {
+    s_zbar = __ddiv_rn(np_pairwise_sum(getz, 0, n), (double)n);  // np.mean
+    auto getv2 = [&](long long i) -> double {
+      const double v = redshift_to_velocity(M.at(s0 + i, 2), s_zbar);
+      return __dmul_rn(v, v);
+    };
+    s_vdisp = __ddiv_rn(np_pairwise_sum(getv2, 0, n), (double)(n - 1));  // np.sum(v**2)/(n-1)
+    // velocity_error: z_average_err = sqrt(sum(zerr**2)) / n   (builtin sum: sequential)
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double z = M.at(s0 + i, 2);
+      const double e = fmax(fabs(__dsub_rn(M.at(s0 + i, 3), z)), fabs(__dsub_rn(M.at(s0 + i, 4), z)));
+      acc = __dadd_rn(acc, __dmul_rn(e, e));
+    }
+    s_zavg_err = __ddiv_rn(sqrt(acc), (double)n);
+    s_taken = 0;
+    s_fail = 0;
+  }
+  for (int i = tid; i < kBootNum; i += kVirialThreads) boot[i] = 0.0;
+  __syncthreads();
+  const double zbar = s_zbar;
+  // harmonic term: (1/n) * (sum(1/err^2))^-1   (order-free reduction; tolerance 1e-9)
+  double part = 0.0, mag = 0.0;
+  for (int i = tid; i < n; i += kVirialThreads) {
+    const double z = M.at(s0 + i, 2);
+    const double v = redshift_to_velocity(z, zbar);
+    const double e = fmax(fabs(M.at(s0 + i, 3) - z), fabs(M.at(s0 + i, 4) - z));
+    const double zd = sqrt(s_zavg_err * s_zavg_err + e * e);
+    const double a = s_zavg_err / zbar, b = zd / (z - zbar);
+    const double err = fabs(v) * sqrt(a * a + b * b);
+    part += 1.0 / (err * err);
+    mag += pow(10.0, -0.4 * M.at(s0 + i, 5));
+  }
+  typedef cub::BlockReduce<double, kVirialThreads> Reduce;
+  __shared__ typename Reduce::TempStorage rtmp;
+  const double inv_err_sum = Reduce(rtmp).Sum(part);
+  __syncthreads();
+  const double mag_sum = Reduce(rtmp).Sum(mag);
+  __syncthreads();
+  // pair sum over i < j of 1 / (sep_deg * d_A * pi/180 * h)
+  const double dA = cosmo_angular_diameter_distance(cosmo, zbar);
+  double psum = 0.0;
+  const long long npairs = (long long)n * (n - 1) / 2;
+  for (long long q = tid; q < npairs; q += kVirialThreads) {
+    // unrank q -> (i, j), i < j, row-major over the upper triangle
+    const double nn = (double)n - 0.5;
+    long long i = (long long)floor(nn - sqrt(nn * nn - 2.0 * (double)q));
+    long long before = i * (2LL * n - i - 1) / 2;
+    while (before > q) { --i; before = i * (2LL * n - i - 1) / 2; }
+    while (before + (n - i - 1) <= q) { before += n - i - 1; ++i; }
+    const long long j = i + 1 + (q - before);
+    const double sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
+                                    __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
+    const double actual = sep * kRad2Deg * dA * kDeg2Rad * cosmo.h;
+    psum += 1.0 / actual;
+  }
+  const double total_sep = Reduce(rtmp).Sum(psum);
+  __syncthreads();
+  // bootstrap: 100 resamples of n-1 indices from the masked MT19937 stream
+  unsigned mask = (unsigned)(n - 1);
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  const long long want = (long long)kBootNum * (n - 1);
+  typedef cub::BlockScan<int, kVirialThreads> Scan;
+  __shared__ typename Scan::TempStorage stmp;
+  for (long long base = 0; base < mt_len; base += kVirialThreads) {
+    __syncthreads();
+    const long long taken = s_taken;
+    if (taken >= want) break;
+    const long long w = base + tid;
+    unsigned val = 0;
+    int ok = 0;
+    if (w < mt_len) {
+      val = mt[w] & mask;
+      ok = val <= (unsigned)(n - 1) ? 1 : 0;
+    }
+    int rank, agg;
+    Scan(stmp).ExclusiveSum(ok, rank, agg);
+    if (ok) {
+      const long long ord = taken + rank;
+      if (ord < want) {
+        const double v = redshift_to_velocity(M.at(s0 + val, 2), zbar);
+        atomicAdd(&boot[(int)(ord / (n - 1))], v * v);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_taken = taken + agg;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_taken < want) s_fail = 1;
+    // statistic: sum(x^2) / (len(x) - 1) with len(x) = n - 1; np.std over the 100 values
+    double mean = 0.0;
+    for (int r = 0; r < kBootNum; ++r) {
+      boot[r] = boot[r] / (double)(n - 2);
+      mean += boot[r];
+    }
+    mean /= kBootNum;
+    double var = 0.0;
+    for (int r = 0; r < kBootNum; ++r) var += (boot[r] - mean) * (boot[r] - mean);
+    const double bootstrap_disp = sqrt(var / kBootNum);
+    const double harmonic = (1.0 / n) * (1.0 / inv_err_sum);
+    const double combined = sqrt(harmonic * harmonic + bootstrap_disp * bootstrap_disp);
+    const double radius = (double)n * (double)(n - 1) / total_sep;
+    const double mass = 1.5 * kPi * (s_vdisp * radius) * mass_unit;
+    o[0] = mass;
+    o[1] = mass * (combined / s_vdisp);
+    o[2] = s_vdisp;
+    o[3] = combined;
+    o[4] = radius;
+    o[5] = -2.5 * log10(mag_sum);
+    o[6] = zbar;
+    o[7] = (double)n;
+    if (s_fail) atomicAdd(status, 1);
+  }
+}
+
+void CleanState::virial(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
+                        double* out_host) {
+  cudaStream_t st = h->stream;
+  if (K == 0) return;
+  const long long total = off_host[K];
+  FOFB_REQUIRE(total == M.rows, "virial: offsets do not cover the member matrix");
+  FOFB_REQUIRE(M.cols >= 6, "virial: members need columns ra, dec, z, z_lower, z_upper, RMag");
+  int nmax = 0;
+  for (int k = 0; k < K; ++k) nmax = std::max<long long>(nmax, off_host[k + 1] - off_host[k]);
+  const Cosmo cosmo = device_cosmo(h, p);
+  // masked rejection keeps >= half of the words on average; 4x + slack bounds the need generously
+  const size_t need = (size_t)kBootNum * (size_t)std::max(nmax, 2) * 4 + 65536;
+  if (need > mt_len) {
+    std::vector<unsigned> words;
+    mt_stream(words, need);
+    unsigned* d = d_mt.alloc(need);
+    FOFB_CUDA(cudaMemcpyAsync(d, words.data(), sizeof(unsigned) * need, cudaMemcpyHostToDevice, st));
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    mt_len = need;
+  }
+  long long* off = d_off.alloc((size_t)K + 1);
+  FOFB_CUDA(cudaMemcpyAsync(off, off_host, sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice, st));
+  double* out = d_props.alloc((size_t)K * 8);
+  int* status = d_kept.alloc(1);
+  FOFB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  // (km/s)^2 Mpc / G in solar masses: CODATA-2018 G, IAU-2015 GM_sun and au
+  const double pc_m = 149597870700.0 * 648000.0 / kPi;
+  const double msun_kg = 1.3271244e20 / 6.6743e-11;
+  const double mass_unit = 1.0e6 * (1.0e6 * pc_m) / 6.6743e-11 / msun_kg;
+  k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status);
+  FOFB_LAUNCH_CHECK(h);
+  int bad = 0;
+  FOFB_CUDA(cudaMemcpyAsync(out_host, out, sizeof(double) * (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaMemcpyAsync(&bad, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  if (bad) throw Error(FOFB_ERR_INTERNAL, "bootstrap random stream exhausted");
+}
+
+}  // namespace fofb

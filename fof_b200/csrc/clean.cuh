@@ -1,0 +1,21 @@
+// Stage 5/6 scratch kept in the handle (see clean.cu).
+#pragma once
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace fofb {
+
+struct CleanState {
+  DBuf<long long> d_off, d_len, d_out_off;
+  DBuf<double> d_cen, d_vel, d_rad, d_dev, d_dA, d_props;
+  DBuf<int> d_perm, d_bin_start, d_kept, d_out_index;
+  DBuf<unsigned> d_mt;
+  size_t mt_len = 0;
+  void three_sigma(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
+                   const double* centres_host, int nbins, long long* out_off_host, int* out_index_host);
+  void virial(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M, double* out_host);
+};
+
+void bootstrap_indices_host(long long n, long long count, int* out);
+
+}  // namespace fofb

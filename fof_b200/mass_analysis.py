@@ -1,0 +1,33 @@
+"""Drop-in for /root/reference/FoF/mass_analysis.py:8-44."""
+import numpy as np
+
+from . import _lib
+from .cluster import CleanedCluster
+from .fof import _pack
+from .params import cosmo
+from .units import Q
+
+
+def find_masses(data, estimator, device=0):
+    """mass_analysis.py:8-44: wrap every cluster in a CleanedCluster carrying its virial mass, velocity
+    dispersion (a variance, km^2/s^2), projected radius and total absolute magnitude."""
+    if estimator not in ("virial", "projected"):
+        raise ValueError("estimator must be 'virial' or 'projected'")
+    if estimator == "projected":
+        raise NotImplementedError("projected_mass_estimator (mass_estimator.py:115-145) is not on the device path yet")
+    if not len(data):
+        return []
+    h = _lib.get_handle(device)
+    p = _lib.default_params(H0=cosmo.H0, Om0=cosmo.Om0, Ode0=cosmo.Ode0)
+    off, members = _pack(data)
+    props = h.virial(off, members, p)
+    new_cs = []
+    for k, c in enumerate(data):
+        m, me, vd, vde, r, absmag = props[k, :6]
+        new_c = CleanedCluster(c.center_attributes, c.galaxies, Q(m, "Msun/littleh"), Q(me, "Msun/littleh"),
+                               Q(vd, "km2/s2"), Q(vde, "km2/s2"), Q(r, "Mpc/littleh"), float(absmag))
+        new_c.D = c.D
+        new_c.flag_poor = c.flag_poor
+        assert new_c.gal_id == c.gal_id, "Different cluster has been added"
+        new_cs.append(new_c)
+    return new_cs

@@ -131,6 +131,27 @@ int fofb_fof_fetch(fofb_handle* h, int32_t which, int64_t* offsets, int32_t* mem
 /* diagnostics of the last fofb_fof_run: priority rounds and centres actually evaluated */
 int fofb_fof_stats(fofb_handle* h, int64_t* rounds, int64_t* evaluated);
 
+/* ---- stage 5: three_sigma / interloper_removal (fof.py:396-516) -----------------------------------------
+ * K clusters; cluster k owns rows offsets[k] .. offsets[k+1] of `members` (>= 3 columns: ra, dec, z) and has
+ * centre (ra, dec, z) = centres[3k .. 3k+2] (host).  For each cluster the members are binned in n_bins radial
+ * bins and clipped iteratively at 3 sigma in velocity.  out_offsets[K+1] and out_index[<= total] (host)
+ * receive, per cluster, the positions (0-based inside the cluster) of the surviving members in the
+ * reference's output order (bins concatenated, each bin sorted by its last deviation sort).
+ * The richness filter of fof.py:514 is the caller's one-liner.
+ *
+ * ---- stage 6: virial_mass_estimator + find_masses (mass_estimator.py:36-112,148-184; mass_analysis.py:8-44) ---
+ * out[8k .. 8k+7] (host) = cluster_mass [Msun/h], mass_err, vel_disp [km^2/s^2], vel_disp_err,
+ * projected_radius [Mpc/h], total_absmag, mean redshift, member count.  `members` needs the first six columns.
+ *
+ * fofb_bootstrap_indices (host): the first `count` values of np.random.randint(0, n) after np.random.seed(1),
+ * i.e. the index stream astropy.stats.bootstrap consumes under NumpyRNGContext(1).
+ */
+int fofb_three_sigma(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* offsets, const fofb_matrix* members,
+                     const double* centres, int64_t* out_offsets, int32_t* out_index);
+int fofb_virial(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* offsets, const fofb_matrix* members,
+                double* out);
+int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif
