@@ -81,6 +81,10 @@ def load():
         "fofb_three_sigma": (C.c_int, [vp, P(Params), i64, vp, P(Matrix), vp, vp, vp]),
         "fofb_virial": (C.c_int, [vp, P(Params), i64, vp, P(Matrix), vp]),
         "fofb_bootstrap_indices": (C.c_int, [i64, i64, vp]),
+        "fofb_pipeline_begin": (C.c_int, [vp, P(Params), P(Matrix), dbl, dbl, dbl, P(i64)]),
+        "fofb_pipeline_finish": (C.c_int, [vp, vp, i32, P(i64), P(i64)]),
+        "fofb_pipeline_fetch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "fofb_pipeline_stats": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -224,6 +228,43 @@ class Handle:
         self.check(self.lib.fofb_virial(self.h, C.byref(params), K, off.ctypes.data, C.byref(m), out.ctypes.data))
         del keep
         return out
+
+    # ---- whole job ------------------------------------------------------------------------------
+    def pipeline_begin(self, galaxies, params, zmin, zmax_gal, zmax_cen):
+        m, keep = matrix_of(galaxies)
+        k = C.c_int64()
+        self.check(self.lib.fofb_pipeline_begin(self.h, C.byref(params), C.byref(m), zmin, zmax_gal, zmax_cen,
+                                                C.byref(k)))
+        del keep
+        return k.value
+
+    def pipeline_finish(self, u):
+        """u: host ndarray (K, 2, n_random) of [0, 1) samples, or a (device_ptr, ) tuple for resident samples."""
+        k, t = C.c_int64(), C.c_int64()
+        if isinstance(u, tuple):
+            ptr, mem = u[0], 1
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+            ptr, mem = u.ctypes.data, 0
+        self.check(self.lib.fofb_pipeline_finish(self.h, ptr, mem, C.byref(k), C.byref(t)))
+        return k.value, t.value
+
+    def pipeline_fetch(self, K, total):
+        off = np.zeros(K + 1, dtype=np.int64)
+        rows = np.empty(total, dtype=np.int32)
+        cen = np.empty(K, dtype=np.int32)
+        N = np.empty(K)
+        D = np.empty(K)
+        props = np.empty((K, 8))
+        self.check(self.lib.fofb_pipeline_fetch(self.h, off.ctypes.data, rows.ctypes.data, cen.ctypes.data,
+                                                N.ctypes.data, D.ctypes.data, props.ctypes.data))
+        return off, rows, cen, N, D, props
+
+    def pipeline_stats(self):
+        s = np.zeros(6, dtype=np.int64)
+        self.lib.fofb_pipeline_stats(self.h, s.ctypes.data)
+        return dict(zip(("galaxies_after_zcut", "candidate_centres", "stage1_clusters", "stage1_members",
+                         "priority_rounds", "centres_evaluated"), s.tolist()))
 
     def fof_stats(self):
         r, e = C.c_int64(), C.c_int64()

@@ -6,6 +6,7 @@
 #include "stage0.cuh"
 #include "fof_stage.cuh"
 #include "clean.cuh"
+#include "pipeline.cuh"
 
 namespace fofb {
 
@@ -171,6 +172,8 @@ void fofb_destroy(fofb_handle* h) {
   h->fof = nullptr;
   delete h->clean;
   h->clean = nullptr;
+  delete h->pipe;
+  h->pipe = nullptr;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -440,6 +443,74 @@ int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out) {
     return FOFB_OK;
   }
   fofb::bootstrap_indices_host(n, count, out);
+  return FOFB_OK;
+}
+
+// ---- whole job -------------------------------------------------------------------------------------------
+int fofb_pipeline_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double zmin, double zmax_gal,
+                        double zmax_cen, int64_t* n_clusters) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(galaxies, "galaxies is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->pipe) h->pipe = new Pipeline();
+  Timed timer(h);
+  const View raw = to_device(h, *galaxies, h->upload);
+  h->pipe->begin(h, *p, raw, zmin, zmax_gal, zmax_cen);
+  timer.stop();
+  if (n_clusters) *n_clusters = h->pipe->fof.merged.K;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_pipeline_finish(fofb_handle* h, const double* u, int32_t mem, int64_t* n_final, int64_t* n_members) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  if (!h->pipe || !h->pipe->began) throw fofb::Error(FOFB_ERR_STATE, "fofb_pipeline_finish called before fofb_pipeline_begin");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  const double prev_ms = h->last_ms;
+  const int64_t prev_launches = h->launches;
+  Timed timer(h);
+  h->pipe->finish(h, u, mem);
+  timer.stop();
+  h->last_ms += prev_ms;
+  h->launches += prev_launches;
+  if (n_final) *n_final = h->pipe->K_out;
+  if (n_members) *n_members = h->pipe->total_out;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
+                        double* props) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  if (!h->pipe || !h->pipe->finished) throw fofb::Error(FOFB_ERR_STATE, "fofb_pipeline_fetch called before fofb_pipeline_finish");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  Pipeline& P = *h->pipe;
+  const int K = P.K_out;
+  if (K == 0) {
+    if (offsets) offsets[0] = 0;
+    return FOFB_OK;
+  }
+  if (offsets) FOFB_CUDA(cudaMemcpyAsync(offsets, P.out_off.p, sizeof(int64_t) * (K + 1), cudaMemcpyDeviceToHost, st));
+  if (member_rows) FOFB_CUDA(cudaMemcpyAsync(member_rows, P.out_rows.p, sizeof(int32_t) * P.total_out, cudaMemcpyDeviceToHost, st));
+  if (centre_row) FOFB_CUDA(cudaMemcpyAsync(centre_row, P.out_centre.p, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
+  if (N) FOFB_CUDA(cudaMemcpyAsync(N, P.out_N.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+  if (D) FOFB_CUDA(cudaMemcpyAsync(D, P.out_D.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+  if (props) FOFB_CUDA(cudaMemcpyAsync(props, P.props.p, sizeof(double) * K * 8, cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_pipeline_stats(fofb_handle* h, int64_t* s) {
+  if (!h || !h->pipe || !s) return FOFB_ERR_STATE;
+  Pipeline& P = *h->pipe;
+  s[0] = P.n_g; s[1] = P.m_c; s[2] = P.fof.candidates.K; s[3] = P.fof.candidates.total;
+  s[4] = P.fof.rounds; s[5] = P.fof.evaluated;
   return FOFB_OK;
 }
 

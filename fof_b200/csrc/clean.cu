@@ -226,21 +226,15 @@ __global__ void k_emit_cleaned(int K, int nbins, const long long* off, const int
   }
 }
 
-void CleanState::three_sigma(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
-                             const double* centres_host, int nbins, long long* out_off_host, int* out_index_host) {
+long long CleanState::three_sigma_core(fofb_handle* h, const fofb_params& p, int K, const long long* off, long long total,
+                                       const View& M, const double* cen, int nbins) {
   cudaStream_t st = h->stream;
   FOFB_REQUIRE(K >= 0 && nbins >= 1 && nbins <= 4096, "three_sigma: bad K or n_bins");
-  out_off_host[0] = 0;
-  if (K == 0) return;
-  const long long total = off_host[K];
+  if (K == 0) return 0;
   FOFB_REQUIRE(total == M.rows, "three_sigma: offsets do not cover the member matrix");
   FOFB_REQUIRE(M.cols >= 3, "three_sigma: members need ra, dec, z columns");
   const int B = 256;
   const Cosmo cosmo = device_cosmo(h, p);
-  long long* off = d_off.alloc((size_t)K + 1);
-  double* cen = d_cen.alloc((size_t)K * 3);
-  FOFB_CUDA(cudaMemcpyAsync(off, off_host, sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice, st));
-  FOFB_CUDA(cudaMemcpyAsync(cen, centres_host, sizeof(double) * (size_t)K * 3, cudaMemcpyHostToDevice, st));
   const size_t tt = (size_t)std::max<long long>(total, 1);
   double* vel = d_vel.alloc(tt);
   double* rad = d_rad.alloc(tt);
@@ -267,13 +261,28 @@ void CleanState::three_sigma(fofb_handle* h, const fofb_params& p, int K, const 
   int* oidx = d_out_index.alloc(tt);
   k_emit_cleaned<<<grid_for((int64_t)K * 32, 128), 128, 0, st>>>(K, nbins, off, perm, bstart, kept, ooff, oidx);
   FOFB_LAUNCH_CHECK(h);
-  FOFB_CUDA(cudaMemcpyAsync(out_off_host, ooff, sizeof(long long) * K, cudaMemcpyDeviceToHost, st));
-  long long last_len = 0;
+  long long last_off = 0, last_len = 0;
+  FOFB_CUDA(cudaMemcpyAsync(&last_off, ooff + (K - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaMemcpyAsync(&last_len, len + (K - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
-  out_off_host[K] = out_off_host[K - 1] + last_len;
-  if (out_off_host[K] > 0)
-    FOFB_CUDA(cudaMemcpyAsync(out_index_host, oidx, sizeof(int) * out_off_host[K], cudaMemcpyDeviceToHost, st));
+  const long long kept_total = last_off + last_len;
+  FOFB_CUDA(cudaMemcpyAsync(ooff + K, &kept_total, sizeof(long long), cudaMemcpyHostToDevice, st));
+  return kept_total;
+}
+
+void CleanState::three_sigma(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
+                             const double* centres_host, int nbins, long long* out_off_host, int* out_index_host) {
+  cudaStream_t st = h->stream;
+  out_off_host[0] = 0;
+  if (K == 0) return;
+  long long* off = d_off.alloc((size_t)K + 1);
+  double* cen = d_cen.alloc((size_t)K * 3);
+  FOFB_CUDA(cudaMemcpyAsync(off, off_host, sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice, st));
+  FOFB_CUDA(cudaMemcpyAsync(cen, centres_host, sizeof(double) * (size_t)K * 3, cudaMemcpyHostToDevice, st));
+  const long long kept_total = three_sigma_core(h, p, K, off, off_host[K], M, cen, nbins);
+  FOFB_CUDA(cudaMemcpyAsync(out_off_host, d_out_off.p, sizeof(long long) * ((size_t)K + 1), cudaMemcpyDeviceToHost, st));
+  if (kept_total > 0)
+    FOFB_CUDA(cudaMemcpyAsync(out_index_host, d_out_index.p, sizeof(int) * kept_total, cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -440,15 +449,11 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   }
 }
 
-void CleanState::virial(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
-                        double* out_host) {
+void CleanState::virial_core(fofb_handle* h, const fofb_params& p, int K, const long long* off, const View& M, int nmax,
+                             double* out) {
   cudaStream_t st = h->stream;
   if (K == 0) return;
-  const long long total = off_host[K];
-  FOFB_REQUIRE(total == M.rows, "virial: offsets do not cover the member matrix");
   FOFB_REQUIRE(M.cols >= 6, "virial: members need columns ra, dec, z, z_lower, z_upper, RMag");
-  int nmax = 0;
-  for (int k = 0; k < K; ++k) nmax = std::max<long long>(nmax, off_host[k + 1] - off_host[k]);
   const Cosmo cosmo = device_cosmo(h, p);
   // masked rejection keeps >= half of the words on average; 4x + slack bounds the need generously
   const size_t need = (size_t)kBootNum * (size_t)std::max(nmax, 2) * 4 + 65536;
@@ -460,10 +465,7 @@ void CleanState::virial(fofb_handle* h, const fofb_params& p, int K, const long 
     FOFB_CUDA(cudaStreamSynchronize(st));
     mt_len = need;
   }
-  long long* off = d_off.alloc((size_t)K + 1);
-  FOFB_CUDA(cudaMemcpyAsync(off, off_host, sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice, st));
-  double* out = d_props.alloc((size_t)K * 8);
-  int* status = d_kept.alloc(1);
+  int* status = d_status.alloc(1);
   FOFB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   // (km/s)^2 Mpc / G in solar masses: CODATA-2018 G, IAU-2015 GM_sun and au
   const double pc_m = 149597870700.0 * 648000.0 / kPi;
@@ -472,10 +474,25 @@ void CleanState::virial(fofb_handle* h, const fofb_params& p, int K, const long 
   k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status);
   FOFB_LAUNCH_CHECK(h);
   int bad = 0;
-  FOFB_CUDA(cudaMemcpyAsync(out_host, out, sizeof(double) * (size_t)K * 8, cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaMemcpyAsync(&bad, status, sizeof(int), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
   if (bad) throw Error(FOFB_ERR_INTERNAL, "bootstrap random stream exhausted");
+}
+
+void CleanState::virial(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
+                        double* out_host) {
+  cudaStream_t st = h->stream;
+  if (K == 0) return;
+  const long long total = off_host[K];
+  FOFB_REQUIRE(total == M.rows, "virial: offsets do not cover the member matrix");
+  int nmax = 0;
+  for (int k = 0; k < K; ++k) nmax = std::max<long long>(nmax, off_host[k + 1] - off_host[k]);
+  long long* off = d_off.alloc((size_t)K + 1);
+  FOFB_CUDA(cudaMemcpyAsync(off, off_host, sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice, st));
+  double* out = d_props.alloc((size_t)K * 8);
+  virial_core(h, p, K, off, M, nmax, out);
+  FOFB_CUDA(cudaMemcpyAsync(out_host, out, sizeof(double) * (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
 }
 
 }  // namespace fofb

@@ -8,9 +8,14 @@ namespace fofb {
 struct CleanState {
   DBuf<long long> d_off, d_len, d_out_off;
   DBuf<double> d_cen, d_vel, d_rad, d_dev, d_dA, d_props;
-  DBuf<int> d_perm, d_bin_start, d_kept, d_out_index;
+  DBuf<int> d_perm, d_bin_start, d_kept, d_out_index, d_status;
   DBuf<unsigned> d_mt;
   size_t mt_len = 0;
+  // device-resident cores: results stay in d_out_off (K+1) / d_out_index; returns the kept total
+  long long three_sigma_core(fofb_handle* h, const fofb_params& p, int K, const long long* d_off_in, long long total,
+                             const View& M, const double* d_cen_in, int nbins);
+  void virial_core(fofb_handle* h, const fofb_params& p, int K, const long long* d_off_in, const View& M, int nmax,
+                   double* d_out);
   void three_sigma(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
                    const double* centres_host, int nbins, long long* out_off_host, int* out_index_host);
   void virial(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M, double* out_host);

@@ -92,6 +92,7 @@ inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block
 struct Catalog;    // catalog.cu
 struct FofState;   // fof_stage.cu
 struct CleanState; // clean.cu
+struct Pipeline;   // pipeline.cu
 
 }  // namespace fofb
 
@@ -108,6 +109,7 @@ struct fofb_handle {
   fofb::Catalog* catalog = nullptr;
   fofb::FofState* fof = nullptr;
   fofb::CleanState* clean = nullptr;
+  fofb::Pipeline* pipe = nullptr;
   fofb::DBuf<unsigned char> cub_tmp;
   fofb::DBuf<double> upload;      // staging for host matrices
   fofb::DBuf<double> upload2;

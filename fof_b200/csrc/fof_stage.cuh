@@ -63,6 +63,9 @@ struct FofState {
 
   void run(fofb_handle* h, const fofb_params& p, const View& G, const View& Cn);
   void finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int mem);
+  // u: K x 2 x n_random samples of [0, 1) (per cluster the RA block, then the Dec block)
+  void finish_unit(fofb_handle* h, const double* u, int mem);
+  DBuf<double> unit_pts;
 };
 
 }  // namespace fofb

@@ -561,6 +561,42 @@ __global__ void k_gather_nd(int K2, const int* sel, const int* N_in, const doubl
   D_out[k] = D_in[sel[k]];
 }
 
+// helper.py:197-202: np.random.uniform(low, high) == low + (high - low) * next_double, separate roundings
+__global__ void k_scale_points(long long total, int npts, const double* u, double ra_lo, double ra_range, double dec_lo,
+                               double dec_range, double* ra, double* dec) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const long long k = q / npts, i = q % npts;
+  ra[q] = __dadd_rn(ra_lo, __dmul_rn(ra_range, u[(2 * k) * npts + i]));
+  dec[q] = __dadd_rn(dec_lo, __dmul_rn(dec_range, u[(2 * k + 1) * npts + i]));
+}
+
+void FofState::finish_unit(fofb_handle* h, const double* u, int mem) {
+  if (!ran) throw Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
+  const int K = merged.K;
+  if (K == 0) {
+    finish(h, nullptr, nullptr, 1);
+    return;
+  }
+  FOFB_REQUIRE(u != nullptr, "uniform samples are null");
+  cudaStream_t st = h->stream;
+  const int npts = params.n_random;
+  const long long total = (long long)K * npts;
+  const double* du = u;
+  if (mem == 0) {
+    double* a = h->upload2.alloc((size_t)total * 2);
+    FOFB_CUDA(cudaMemcpyAsync(a, u, sizeof(double) * total * 2, cudaMemcpyHostToDevice, st));
+    du = a;
+  }
+  double* pts = unit_pts.alloc((size_t)total * 2);
+  // volatile-free host arithmetic: high - low is one rounding, as in numpy
+  const double ra_range = cat.gbox.ra_max - cat.gbox.ra_min, dec_range = cat.gbox.dec_max - cat.gbox.dec_min;
+  k_scale_points<<<grid_for(total, 256), 256, 0, st>>>(total, npts, du, cat.gbox.ra_min, ra_range, cat.gbox.dec_min,
+                                                       dec_range, pts, pts + total);
+  FOFB_LAUNCH_CHECK(h);
+  finish(h, pts, pts + total, 1);
+}
+
 void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int mem) {
   cudaStream_t st = h->stream;
   OverlapScratch& sc = scratch();

@@ -1,0 +1,28 @@
+// Device-resident whole-job pipeline state (see pipeline.cu).
+#pragma once
+#include "catalog_host.cuh"
+#include "clean.cuh"
+#include "fof_stage.cuh"
+#include "stage0.cuh"
+
+namespace fofb {
+
+struct Pipeline {
+  bool began = false, finished = false;
+  fofb_params params{};
+  Catalog cat;       // on the raw input (stage 0)
+  CellList cells;
+  Stage0 s0;
+  FofState fof;      // on the z-cut main_arr
+  CleanState clean;
+  int n_in = 0, n_g = 0, m_c = 0;
+  int K_out = 0;
+  long long total_out = 0;
+  DBuf<int> flags, iotas, counter, g_src, c_src, selected, out_grow, out_rows, out_centre;
+  DBuf<double> g_rows, c_rows, m_rows, m_rows2, centres, props, out_N, out_D;
+  DBuf<long long> lens, out_off;
+  void begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen);
+  void finish(fofb_handle* h, const double* u, int mem);
+};
+
+}  // namespace fofb

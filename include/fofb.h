@@ -152,6 +152,26 @@ int fofb_virial(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* 
                 double* out);
 int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out);
 
+/* ---- whole job: pipeline.py:62-64,80-99,113,173 with every intermediate on the device ---------------------
+ * fofb_pipeline_begin : candidate_center_search on `galaxies` (n x 7), the z cuts of pipeline.py:80-86
+ *                       (galaxies zmin <= z <= zmax_gal, centres zmin <= z <= zmax_cen), FoF() stages 1-3.
+ *                       *n_clusters = clusters reaching the overdensity stage.
+ * fofb_pipeline_finish: `u` holds n_clusters * 2 * n_random samples of [0, 1) in numpy stream order (per
+ *                       cluster the RA block then the Dec block, i.e. np.random.random_sample((K, 2, n)));
+ *                       the points are low + (high - low) * u as in helper.py:197-202.  Then stage 4,
+ *                       interloper_removal (richness filter of fof.py:514 included) and find_masses("virial").
+ * fofb_pipeline_fetch : offsets[K+1], member_rows[total] and centre_row[K] index rows of the INPUT matrix;
+ *                       N[K], D[K], props[K x 8] as in fofb_virial.  NULL pointers are skipped.
+ */
+int fofb_pipeline_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double zmin, double zmax_gal,
+                        double zmax_cen, int64_t* n_clusters);
+int fofb_pipeline_finish(fofb_handle* h, const double* u, int32_t mem, int64_t* n_final, int64_t* n_members);
+int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
+                        double* props);
+/* sizes seen by the last pipeline run: galaxies after the z cut, candidate centres, stage-1 candidate clusters,
+ * total stage-1 members, priority rounds, centres evaluated */
+int fofb_pipeline_stats(fofb_handle* h, int64_t* stats6);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,3 +58,23 @@ def test_three_sigma_single_cluster(lib):
     assert np.array_equal(got, want)
     want7 = O.three_sigma(c, members, 7)
     assert np.array_equal(fof.three_sigma(c, members, 7), want7)
+
+
+@pytest.mark.parametrize("n,seed", [(6000, 12), (30000, 31)])
+def test_whole_job_equals_staged_facade(lib, n, seed):
+    """The device-resident pipeline (what bench.py times) returns what the staged facade returns."""
+    from fof_b200 import pipeline
+    arr, ref = _oracle_run(n, seed)
+    np.random.seed(4242)
+    cat = pipeline.find_clusters(arr)
+    assert len(cat) == len(ref["virial"])
+    ids = arr[:, 6]
+    for k, r in enumerate(ref["virial"]):
+        assert np.array_equal(ids[cat.members(k)], r["galaxies"][:, 6])
+        assert ids[cat.centre_row[k]] == r["center"][6]
+        assert cat.N[k] == r["N"] and cat.D[k] == r["D"]
+        for j, key in enumerate(("cluster_mass", "mass_err", "vel_disp", "vel_disp_err", "projected_radius",
+                                 "total_absmag")):
+            assert abs(cat.props[k, j] - r[key]) <= REL * abs(r[key]), (key, cat.props[k, j], r[key])
+    lab = cat.labels()
+    assert lab.shape == (n,) and (lab >= -1).all()
