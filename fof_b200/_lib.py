@@ -66,6 +66,8 @@ def load():
         "fofb_last_error": (C.c_char_p, [vp]),
         "fofb_synchronize": (C.c_int, [vp]),
         "fofb_last_timing": (C.c_int, [vp, P(dbl), P(i64)]),
+        "fofb_profile_enable": (C.c_int, [vp, i32]),
+        "fofb_profile_read": (C.c_int, [vp, C.c_char_p, i64]),
         "fofb_comoving_distance": (C.c_int, [P(Params), i64, vp, vp]),
         "fofb_angular_diameter_distance": (C.c_int, [P(Params), i64, vp, vp]),
         "fofb_linear_to_angular_dist": (C.c_int, [P(Params), dbl, i64, vp, vp]),
@@ -151,6 +153,19 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def profile(self, on):
+        self.check(self.lib.fofb_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{kernel: (total_ms, launches)} accumulated since the last reset."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.fofb_profile_read(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split()
+            out[name] = (float(ms), int(cnt))
+        return out
 
     def last_timing(self):
         ms, k = C.c_double(), C.c_int64()

@@ -83,6 +83,7 @@ struct Timed {  // CUDA-event bracket around one compute call
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->last_ms = ms;
+    h->prof.resolve();
   }
 };
 
@@ -195,6 +196,22 @@ int fofb_last_timing(const fofb_handle* h, double* device_ms, int64_t* kernel_la
   if (!h) return FOFB_ERR_INVALID;
   if (device_ms) *device_ms = h->last_ms;
   if (kernel_launches) *kernel_launches = h->launches;
+  return FOFB_OK;
+}
+
+int fofb_profile_enable(fofb_handle* h, int32_t on) {
+  if (!h) return FOFB_ERR_INVALID;
+  h->prof.on = on != 0;
+  if (on == 2) h->prof.acc.clear();  // 2 = enable and reset the accumulators
+  return FOFB_OK;
+}
+
+int fofb_profile_read(fofb_handle* h, char* buf, int64_t capacity) {
+  if (!h || !buf || capacity <= 0) return FOFB_ERR_INVALID;
+  std::string out;
+  for (auto& kv : h->prof.acc) out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+  if ((int64_t)out.size() + 1 > capacity) return FOFB_ERR_INVALID;
+  std::memcpy(buf, out.c_str(), out.size() + 1);
   return FOFB_OK;
 }
 

@@ -111,8 +111,7 @@ void Catalog::build(fofb_handle* h, const View& rows_in) {
   double* dec = dec_row.alloc(n);
   double* z = z_row.alloc(n);
   int* idx = idx_tmp.alloc(n);
-  k_extract<<<grid_for(n, B), B, 0, st>>>(rows, ni, ra, dec, z, idx);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_extract", k_extract<<<grid_for(n, B), B, 0, st>>>(rows, ni, ra, dec, z, idx));
 
   // K2a: stable radix sort by redshift
   double* zs_p = zs.alloc(n);
@@ -134,8 +133,7 @@ void Catalog::build(fofb_handle* h, const View& rows_in) {
   double4* pre_p = pre.alloc(n);
   double4* suf_p = suf.alloc(n);
   double4* lev_p = levels.alloc((size_t)nlev * nblocks);
-  k_bbox_blocks<<<nblocks, kBBoxBlock, 0, st>>>(ni, zra_p, zdec_p, pre_p, suf_p, lev_p);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_bbox_blocks", k_bbox_blocks<<<nblocks, kBBoxBlock, 0, st>>>(ni, zra_p, zdec_p, pre_p, suf_p, lev_p));
   for (int k = 1; k < nlev; ++k) {
     k_bbox_level<<<grid_for(nblocks, B), B, 0, st>>>(nblocks, k, lev_p + (size_t)(k - 1) * nblocks, lev_p + (size_t)k * nblocks);
     FOFB_LAUNCH_CHECK(h);
@@ -197,9 +195,8 @@ void CellList::build(fofb_handle* h, const Catalog& cat, double r_max_deg) {
   FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, val_in, val_out, ni, 0, bits, st));
   FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, key_in, key_out, val_in, val_out, ni, 0, bits, st));
   count_launch(h, 2 + (bits + 7) / 8);
-  k_cell_gather<<<grid_for(n, B), B, 0, st>>>(ni, val_out, cat.zorder.p, cat.zra.p, cat.zdec.p, ra.alloc(n), dec.alloc(n),
-                                              cosdec.alloc(n), zrank.alloc(n), row.alloc(n));
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_cell_gather", k_cell_gather<<<grid_for(n, B), B, 0, st>>>(ni, val_out, cat.zorder.p, cat.zra.p, cat.zdec.p, ra.alloc(n), dec.alloc(n),
+                                              cosdec.alloc(n), zrank.alloc(n), row.alloc(n)));
   int* cs = cell_start.alloc((size_t)ncell + 1);
   k_cell_starts<<<grid_for(n + 1, B), B, 0, st>>>(ni, key_out, ncell, cs);
   FOFB_LAUNCH_CHECK(h);

@@ -243,13 +243,10 @@ long long CleanState::three_sigma_core(fofb_handle* h, const fofb_params& p, int
   int* bstart = d_bin_start.alloc((size_t)K * (nbins + 2));
   int* kept = d_kept.alloc((size_t)K * nbins);
   if (total > 0) {
-    k_member_vr<<<grid_for(total, B), B, 0, st>>>(total, K, off, M, cen, cosmo, vel, rad, d_dA.alloc(K));
-    FOFB_LAUNCH_CHECK(h);
+    FOFB_PROFILED(h, "k_member_vr", k_member_vr<<<grid_for(total, B), B, 0, st>>>(total, K, off, M, cen, cosmo, vel, rad, d_dA.alloc(K)));
   }
-  k_bin_members<<<grid_for((int64_t)K * 32, 128), 128, 0, st>>>(K, off, rad, nbins, perm, bstart);
-  FOFB_LAUNCH_CHECK(h);
-  k_clip_bins<<<grid_for((int64_t)K * nbins, 64), 64, 0, st>>>(K, nbins, off, vel, rad, perm, bstart, dev, kept);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_bin_members", k_bin_members<<<grid_for((int64_t)K * 32, 128), 128, 0, st>>>(K, off, rad, nbins, perm, bstart));
+  FOFB_PROFILED(h, "k_clip_bins", k_clip_bins<<<grid_for((int64_t)K * nbins, 64), 64, 0, st>>>(K, nbins, off, vel, rad, perm, bstart, dev, kept));
   long long* len = d_len.alloc((size_t)K + 1);
   long long* ooff = d_out_off.alloc((size_t)K + 1);
   k_kept_per_cluster<<<grid_for(K, B), B, 0, st>>>(K, nbins, kept, len);
@@ -471,8 +468,7 @@ void CleanState::virial_core(fofb_handle* h, const fofb_params& p, int K, const 
   const double pc_m = 149597870700.0 * 648000.0 / kPi;
   const double msun_kg = 1.3271244e20 / 6.6743e-11;
   const double mass_unit = 1.0e6 * (1.0e6 * pc_m) / 6.6743e-11 / msun_kg;
-  k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_virial_mass", k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status));
   int bad = 0;
   FOFB_CUDA(cudaMemcpyAsync(&bad, status, sizeof(int), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));

@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <map>
 
 #include "../../include/fofb.h"
 #include "cosmo.cuh"
@@ -96,8 +97,32 @@ struct Pipeline;   // pipeline.cu
 
 }  // namespace fofb
 
+namespace fofb {
+// Optional per-kernel CUDA-event timing (bench.py reads it for the roofline of the dominant kernel).
+struct KernelProfile {
+  bool on = false;
+  struct Pending { const char* name; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, std::pair<double, int64_t>> acc;  // name -> (ms, launches)
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void resolve() {  // call after the stream is synchronised
+    for (auto& p : pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { auto& r = acc[p.name]; r.first += ms; r.second += 1; }
+      pool.push_back(p.a); pool.push_back(p.b);
+    }
+    pending.clear();
+  }
+};
+}  // namespace fofb
+
 struct fofb_handle {
   int device = 0;
+  fofb::KernelProfile prof;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -126,6 +151,17 @@ Cosmo host_cosmo(const fofb_params& p);
 View to_device(fofb_handle* h, const fofb_matrix& m, DBuf<double>& staging);
 
 inline void count_launch(fofb_handle* h, int k = 1) { h->launches += k; }
+
+// FOFB_PROFILED(h, "name", kernel<<<...>>>(...)): launch + check, with event timing when enabled
+#define FOFB_PROFILED(h, name, ...)                                   \
+  do {                                                                \
+    cudaEvent_t _ea = nullptr, _eb = nullptr;                         \
+    if ((h)->prof.on) { _ea = (h)->prof.get(); _eb = (h)->prof.get(); cudaEventRecord(_ea, (h)->stream); } \
+    __VA_ARGS__;                                                      \
+    if ((h)->prof.on) { cudaEventRecord(_eb, (h)->stream); (h)->prof.pending.push_back({name, _ea, _eb}); } \
+    ::fofb::count_launch(h);                                          \
+    FOFB_CUDA(cudaGetLastError());                                    \
+  } while (0)
 
 #define FOFB_LAUNCH_CHECK(h)          \
   do {                                \

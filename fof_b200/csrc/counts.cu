@@ -105,9 +105,8 @@ void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat, CellList& c
   QueryRec* recs = rec.alloc(n);
   double* th = theta.alloc(n);
   CatalogView cv = cat.view();
-  k_count_prep<<<grid_for(n, B), B, 0, st>>>(cv, cosmo, p.count_radius, p.max_velocity, p.min_window, p.grid_cells,
-                                             recs, th);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_count_prep", k_count_prep<<<grid_for(n, B), B, 0, st>>>(cv, cosmo, p.count_radius, p.max_velocity, p.min_window, p.grid_cells,
+                                             recs, th));
   // largest query radius sizes the cell list
   double* tmax = theta_max.alloc(1);
   size_t bytes = 0;
@@ -120,8 +119,7 @@ void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat, CellList& c
   FOFB_REQUIRE(std::isfinite(r_max) && r_max > 0.0, "non-finite angular radius (check redshifts and cosmology)");
   cells.build(h, cat, r_max);
   int* N = N_row.alloc(n);
-  k_count<<<grid_for(n, 256), 256, 0, st>>>(cells.view(), n, recs, N);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_count", k_count<<<grid_for(n, 256), 256, 0, st>>>(cells.view(), n, recs, N));
 
   unsigned long long* k_all = key_all.alloc(n);
   unsigned long long* k_sel = key_sel.alloc(n);

@@ -551,12 +551,11 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
     return;
   }
   const size_t mm = (size_t)m;
-  k_centre_prep<<<grid_for(m, B), B, 0, st>>>(Cn, m, cv, cosmo, p.max_velocity, p.virial_radius, p.count_radius,
+  FOFB_PROFILED(h, "k_centre_prep", k_centre_prep<<<grid_for(m, B), B, 0, st>>>(Cn, m, cv, cosmo, p.max_velocity, p.virial_radius, p.count_radius,
                                               c_ra.alloc(mm), c_dec.alloc(mm), c_cos.alloc(mm), c_z.alloc(mm),
                                               c_R1.alloc(mm), c_thvir.alloc(mm), c_th05.alloc(mm), c_mag.alloc(mm),
                                               c_N.alloc(mm), c_id.alloc(mm), c_wlo.alloc(mm), c_whi.alloc(mm),
-                                              alive.alloc(mm), decided.alloc(mm));
-  FOFB_LAUNCH_CHECK(h);
+                                              alive.alloc(mm), decided.alloc(mm)));
   size_t bytes = 0;
   long long* scal_p = scal.alloc(16);
   double* dmax = reinterpret_cast<double*>(scal_p);
@@ -588,8 +587,7 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
     int* tcnt = t_count.alloc(mm + 1);
     FOFB_CUDA(cudaMemsetAsync(trow, 0xff, sizeof(int) * mm, st));
     FOFB_CUDA(cudaMemsetAsync(tcnt, 0, sizeof(int) * (mm + 1), st));
-    k_kill_targets<<<grid_for(n, B), B, 0, st>>>(G, n, m, key_out, val_out, kill_target.alloc(n), trow, tcnt, tcnt + mm);
-    FOFB_LAUNCH_CHECK(h);
+    FOFB_PROFILED(h, "k_kill_targets", k_kill_targets<<<grid_for(n, B), B, 0, st>>>(G, n, m, key_out, val_out, kill_target.alloc(n), trow, tcnt, tcnt + mm));
     if (d2h_scalar(h, tcnt + mm) != 0)
       throw Error(FOFB_ERR_UNSUPPORTED,
                   "two galaxy rows share a column-4 (z_upper) value with the same candidate centre; the tracker of "
@@ -647,10 +645,9 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
   while (na > 0) {
     ++rounds;
     int* fl = flags.alloc((size_t)na);
-    k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, alive.p, decided.p,
+    FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, alive.p, decided.p,
                                                t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
-                                               p.max_velocity, R1max, fl);
-    FOFB_LAUNCH_CHECK(h);
+                                               p.max_velocity, R1max, fl));
     int* rdy = ready.alloc((size_t)na);
     const int nr_all = select_flagged(h, act, fl, rdy, na, d_count);
     if (nr_all == 0) throw Error(FOFB_ERR_INTERNAL, "priority rounds made no progress");
@@ -663,9 +660,8 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
       const int wblocks = grid_for((int64_t)nr * 32, 128);
       int* nv_p = nv.alloc(nr);
       double4* bb1 = bbox1.alloc(nr);
-      k_virial<0><<<wblocks, 128, 0, st>>>(nr, rb, cv, clbig, c_ra.p, c_dec.p, c_cos.p, c_R1.p, c_wlo.p, c_whi.p,
-                                           p.grid_cells, p.min_virial, nv_p, bb1, nullptr, nullptr, nullptr);
-      FOFB_LAUNCH_CHECK(h);
+      FOFB_PROFILED(h, "k_virial_count", k_virial<0><<<wblocks, 128, 0, st>>>(nr, rb, cv, clbig, c_ra.p, c_dec.p, c_cos.p, c_R1.p, c_wlo.p, c_whi.p,
+                                           p.grid_cells, p.min_virial, nv_p, bb1, nullptr, nullptr, nullptr));
       long long* need = hcap.alloc((size_t)nr + 1);
       long long* vo = voff.alloc((size_t)nr + 1);
       k_alloc_sizes<<<grid_for(nr, B), B, 0, st>>>(nr, nv_p, p.min_virial, need);
@@ -691,13 +687,11 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
       if (total_v > 0) {
         int* cur = cursor.alloc(nr);
         FOFB_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * nr, st));
-        k_virial<1><<<wblocks, 128, 0, st>>>(nr, rb, cv, clbig, c_ra.p, c_dec.p, c_cos.p, c_R1.p, c_wlo.p, c_whi.p,
-                                             p.grid_cells, p.min_virial, nv_p, bb1, vo, cur, k1);
-        FOFB_LAUNCH_CHECK(h);
+        FOFB_PROFILED(h, "k_virial_fill", k_virial<1><<<wblocks, 128, 0, st>>>(nr, rb, cv, clbig, c_ra.p, c_dec.p, c_cos.p, c_R1.p, c_wlo.p, c_whi.p,
+                                             p.grid_cells, p.min_virial, nv_p, bb1, vo, cur, k1));
         segmented_sort(h, k1, k1s, total_v, nr, vo);
-        k_hop1<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, vo, k1s, cat.ra_row.p, cat.dec_row.p, cos_row.p, c_ra.p, c_dec.p,
-                                        c_cos.p, c_z.p, cosmo, p, LLp, bb2, nF_p, k2);
-        FOFB_LAUNCH_CHECK(h);
+        FOFB_PROFILED(h, "k_hop1", k_hop1<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, vo, k1s, cat.ra_row.p, cat.dec_row.p, cos_row.p, c_ra.p, c_dec.p,
+                                        c_cos.p, c_z.p, cosmo, p, LLp, bb2, nF_p, k2));
         segmented_sort(h, k2, k2s, total_v, nr, vo);
         k_hash_sizes<<<grid_for(nr, B), B, 0, st>>>(nr, nv_p, nF_p, p.min_virial, need);
         FOFB_LAUNCH_CHECK(h);
@@ -710,10 +704,9 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
         FOFB_CUDA(cudaMemsetAsync(nF_p, 0, sizeof(int) * nr, st));
         FOFB_CUDA(cudaMemsetAsync(ho, 0, sizeof(long long) * ((size_t)nr + 1), st));
       }
-      k_hop2<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, k1s, k2s, ho, need, htab.p, G, cat.ra_row.p,
+      FOFB_PROFILED(h, "k_hop2", k_hop2<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, k1s, k2s, ho, need, htab.p, G, cat.ra_row.p,
                                       cat.dec_row.p, cos_row.p, LLp, bb2, p, v2, mr, nml, adm, nM_p, pass_p,
-                                      kill_target.p, alive.p, decided.p);
-      FOFB_LAUNCH_CHECK(h);
+                                      kill_target.p, alive.p, decided.p));
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse
       long long* dst = ho;    // reuse

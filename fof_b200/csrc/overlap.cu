@@ -378,9 +378,8 @@ void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
     int* ev_c = sc.ev_c.alloc((size_t)E);
     int* ev_l = sc.ev_loser.alloc((size_t)E);
     int* state = sc.state.p;
-    k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, S.candidates.centre.p, S.c_id.p,
-                                                          S.c_N.p, S.c_mag.p, S.candidates.off.p, ids_s, ev_a, ev_c, ev_l, state);
-    FOFB_LAUNCH_CHECK(h);
+    FOFB_PROFILED(h, "k_event_static", k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, S.candidates.centre.p, S.c_id.p,
+                                                          S.c_N.p, S.c_mag.p, S.candidates.off.p, ids_s, ev_a, ev_c, ev_l, state));
     // per-cluster lists of the events it would lose, in event order
     unsigned long long* lkey = sc.lkey.alloc((size_t)E);
     unsigned long long* lkey_s = sc.lkey_sorted.alloc((size_t)E);
@@ -623,17 +622,15 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   const int wblocks = grid_for((int64_t)K * 32, 128);
   int* N_own = merged.N.alloc(K);
   double* D = merged.D.alloc(K);
-  k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,
-                                       c_ra.p, c_dec.p, c_cos.p, c_th05.p, p.grid_cells, N_own);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_own_count", k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,
+                                       c_ra.p, c_dec.p, c_cos.p, c_th05.p, p.grid_cells, N_own));
   double4* bb = sc.bbox.alloc(K);
   int* oof = sc.ecount.alloc(K);
   k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, bb, oof);
   FOFB_LAUNCH_CHECK(h);
   int* counts = sc.ev_a.alloc((size_t)total);
-  k_od_count<<<grid_for(total, 128), 128, 0, st>>>(total, npts, merged.centre.p, small.view(), c_wlo.p, c_whi.p, c_th05.p, bb,
-                                                   oof, rra, rdec, p.grid_cells, counts);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_od_count", k_od_count<<<grid_for(total, 128), 128, 0, st>>>(total, npts, merged.centre.p, small.view(), c_wlo.p, c_whi.p, c_th05.p, bb,
+                                                   oof, rra, rdec, p.grid_cells, counts));
   int* keep = sc.state.alloc(K);
   k_od_finish<<<wblocks, 128, 0, st>>>(K, npts, counts, N_own, merged.off.p, p.overdensity, p.min_count, p.richness, D, keep);
   FOFB_LAUNCH_CHECK(h);

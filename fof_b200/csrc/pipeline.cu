@@ -147,8 +147,7 @@ void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, doub
   FOFB_REQUIRE(n_g > 0, "no galaxy passes the redshift cut");
   const int ocols = 8;
   double* G = g_rows.alloc((size_t)n_g * ocols);
-  k_build_rows<<<grid_for((int64_t)n_g * ocols, B), B, 0, st>>>(n_g, gsrc, raw, s0.N_row.p, G, ocols);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_build_rows", k_build_rows<<<grid_for((int64_t)n_g * ocols, B), B, 0, st>>>(n_g, gsrc, raw, s0.N_row.p, G, ocols));
   // candidate centres in priority order
   const int m0 = (int)s0.n_candidates;
   m_c = 0;
@@ -164,8 +163,7 @@ void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, doub
   }
   double* C = c_rows.alloc((size_t)std::max(m_c, 1) * ocols);
   if (m_c > 0) {
-    k_build_rows<<<grid_for((int64_t)m_c * ocols, B), B, 0, st>>>(m_c, csrc, raw, s0.N_row.p, C, ocols);
-    FOFB_LAUNCH_CHECK(h);
+    FOFB_PROFILED(h, "k_build_rows", k_build_rows<<<grid_for((int64_t)m_c * ocols, B), B, 0, st>>>(m_c, csrc, raw, s0.N_row.p, C, ocols));
   }
   View Gv, Cv;
   Gv.data = G; Gv.rows = n_g; Gv.cols = ocols; Gv.rs = ocols; Gv.cs = 1;
@@ -189,8 +187,7 @@ void Pipeline::finish(fofb_handle* h, const double* u, int mem) {
   // stage 5 on the final clusters
   const int cols = 8;
   double* M = m_rows.alloc((size_t)F.total * cols);
-  k_gather_members<<<grid_for(F.total * cols, B), B, 0, st>>>(F.total, F.rows.p, fof.G.data, cols, M);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_gather_members", k_gather_members<<<grid_for(F.total * cols, B), B, 0, st>>>(F.total, F.rows.p, fof.G.data, cols, M));
   double* cen = centres.alloc((size_t)K * 3);
   k_cluster_centres<<<grid_for(K, B), B, 0, st>>>(K, F.centre.p, fof.c_ra.p, fof.c_dec.p, fof.c_z.p, cen);
   FOFB_LAUNCH_CHECK(h);
@@ -222,8 +219,7 @@ void Pipeline::finish(fofb_handle* h, const double* u, int mem) {
   FOFB_LAUNCH_CHECK(h);
   // stage 6 on the cleaned members
   double* M2 = m_rows2.alloc((size_t)total_out * cols);
-  k_gather_members<<<grid_for(total_out * cols, B), B, 0, st>>>(total_out, grow, fof.G.data, cols, M2);
-  FOFB_LAUNCH_CHECK(h);
+  FOFB_PROFILED(h, "k_gather_members", k_gather_members<<<grid_for(total_out * cols, B), B, 0, st>>>(total_out, grow, fof.G.data, cols, M2));
   View M2v;
   M2v.data = M2; M2v.rows = total_out; M2v.cols = cols; M2v.rs = cols; M2v.cs = 1;
   int* dmax = counter.p + 1;

@@ -82,6 +82,11 @@ int fofb_synchronize(fofb_handle* h);
 /* CUDA-event time [ms] of the kernels launched by the last compute call, and their count.    */
 int fofb_last_timing(const fofb_handle* h, double* device_ms, int64_t* kernel_launches);
 
+/* Per-kernel CUDA-event timing of the library's own kernels (recorded on the launching stream).
+ * on = 1 enable, 2 enable and reset, 0 disable.  fofb_profile_read writes "name total_ms launches" lines. */
+int fofb_profile_enable(fofb_handle* h, int32_t on);
+int fofb_profile_read(fofb_handle* h, char* buf, int64_t capacity);
+
 /* ---- host scalar helpers: analysis/methods.py (no GPU needed) ----------------------------------
  * fofb_linear_to_angular_dist : analysis/methods.py:12-32   h^-1 Mpc (proper) at z -> degrees
  * fofb_mean_separation        : analysis/methods.py:35-65   Mpc

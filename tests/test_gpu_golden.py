@@ -1,0 +1,37 @@
+"""GPU path against the golden vectors of the unmodified reference (no oracle in the loop)."""
+import numpy as np
+import pytest
+
+from golden_util import fixtures, load, fof_inputs, split
+
+pytestmark = pytest.mark.gpu
+KEYS = ("cluster_mass", "mass_err", "vel_disp", "vel_disp_err", "projected_radius", "total_absmag")
+
+
+@pytest.mark.parametrize("path", fixtures(), ids=lambda p: p.split("/")[-1][:-4])
+def test_gpu_reproduces_reference_golden(lib, path):
+    from fof_b200 import fof, mass_analysis, params
+    g = load(path)
+    main_arr, centres = fof.candidate_center_search(g["table"], max_velocity=params.max_velocity, fname="G")
+    assert np.array_equal(main_arr[:, 7], g["N"])
+    assert np.array_equal(np.sort(centres[:, 6]), np.sort(g["candidate_ids"]))
+    _, gal, cen = fof_inputs(g)  # the reference's own candidate order
+    np.random.seed(g["rng_seed"])
+    clusters = fof.FoF(gal, cen, richness=g["richness"], overdensity=g["overdensity"], max_velocity=params.max_velocity,
+                       linking_length_factor=g["b"], virial_radius=params.max_radius)
+    assert [c.gal_id for c in clusters] == g["cluster_centre_ids"].tolist()
+    for c, ids, N, D in zip(clusters, split(g["cluster_off"], g["cluster_member_ids"]), g["cluster_N"], g["cluster_D"]):
+        assert np.array_equal(c.galaxies[:, 6], ids)
+        assert c.N == N and (c.D == D or (np.isnan(c.D) and np.isnan(D)))
+    old = params.richness
+    params.richness = g["richness"]
+    try:
+        cleaned, removed = fof.interloper_removal(clusters)
+    finally:
+        params.richness = old
+    assert removed == g["number_removed"].tolist()
+    for c, ids in zip(cleaned, split(g["cleaned_off"], g["cleaned_member_ids"])):
+        assert np.array_equal(c.galaxies[:, 6], ids)
+    vir = mass_analysis.find_masses(cleaned, "virial")
+    got = np.array([[float(getattr(v, k)) for k in KEYS] for v in vir]).reshape(-1, len(KEYS))
+    np.testing.assert_allclose(got, g["virial"], rtol=1e-9)

@@ -1,0 +1,47 @@
+"""Cross-check of the oracle against the reference's own control flow, executed live (build container only)."""
+import numpy as np
+import pytest
+
+from fof_b200.mock import make_catalog
+from oracle import fof_oracle as O
+from oracle import run_reference as RR
+
+pytestmark = pytest.mark.skipif(not RR.available(), reason="/root/reference is not mounted here")
+
+
+def test_live_reference_run_matches_oracle():
+    import logging
+    logging.disable(logging.CRITICAL)
+    ref = RR.load_reference()
+    df = make_catalog(2000, seed=41)
+    R = RR.run_pipeline(ref, df, seed=5)
+    p = O.Params()
+    main_arr, cand = O.candidate_center_search(df.values, p, "fast")
+    assert np.array_equal(main_arr, R["main_arr"])
+    g = main_arr[(main_arr[:, 2] >= 0.5) & (main_arr[:, 2] <= 2.52)]
+    c = R["candidate_centers"]
+    c = c[(c[:, 2] >= 0.5) & (c[:, 2] <= 2.5)]
+    np.random.seed(5)
+    cl = O.FoF(g, c, p, "fast")
+    assert len(cl) == len(R["clusters"])
+    for x, (attrs, members, N, D) in zip(cl, R["clusters"]):
+        assert np.array_equal(x.galaxies, members) and x.N == N and x.D == D
+    cleaned, removed = O.interloper_removal(cl, p)
+    assert removed == R["number_removed"]
+    vir = O.find_masses(cleaned)
+    for a, b in zip(vir, R["virial"]):
+        for k in ("cluster_mass", "mass_err", "vel_disp", "vel_disp_err", "projected_radius", "total_absmag"):
+            assert abs(a[k] - b[k]) <= 1e-12 * abs(b[k])
+
+
+def test_shim_cosmology_known_answers():
+    """SURVEY.md Appendix C."""
+    ref = RR.load_reference()
+    import astropy.units as u
+    lad = ref.analysis_methods.linear_to_angular_dist
+    for z, want in ((0.5, 0.097513), (1.0, 0.074324), (2.0, 0.071108)):
+        assert abs(lad(1.5 * u.Mpc / u.littleh, z).value - want) < 5e-7
+    ms = ref.analysis_methods.mean_separation
+    for n, want in ((12, 6.893), (100, 3.400), (1000, 1.578), (10000, 0.733)):
+        got = 0.2 * ms(n, 1.0, 0.1 * u.deg, 2000 * u.km / u.s, survey_area=1.7).value
+        assert abs(got - want) < 2e-3
