@@ -236,13 +236,12 @@ def main():
 
     def step(resident):
         K = h.pipeline_begin(dev if resident else host_np, p, *ZCUT)
-        u = np.random.random_sample((K, 2, p.n_random))
-        Kf, total = h.pipeline_finish(u)
+        Kf, total = h.pipeline_finish_np_random()  # overdensity points: np.random's MT19937 stream, advanced on the device
         ms, launches = h.last_timing()
         out = None
         if not resident:
             out = h.pipeline_fetch(Kf, total)
-        stats.update(K=K, Kf=Kf, total=total, launches=launches, device_ms=ms, u_bytes=u.nbytes)
+        stats.update(K=K, Kf=Kf, total=total, launches=launches, device_ms=ms, u_bytes=2 * 624 * 4)
         return out
 
     def timed(resident, steps):

@@ -77,6 +77,8 @@ def load():
         "fofb_candidate_order": (C.c_int, [vp, vp, i32, i64]),
         "fofb_fof_run": (C.c_int, [vp, P(Params), P(Matrix), P(Matrix), P(i64), vp]),
         "fofb_fof_finish": (C.c_int, [vp, vp, vp, i32, P(i64)]),
+        "fofb_fof_finish_mt": (C.c_int, [vp, vp, P(i32), P(i64)]),
+        "fofb_pipeline_finish_mt": (C.c_int, [vp, vp, P(i32), P(i64), P(i64)]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
@@ -205,6 +207,29 @@ class Handle:
         k = C.c_int64()
         self.check(self.lib.fofb_fof_finish(self.h, ra.ctypes.data, dec.ctypes.data, 0, C.byref(k)))
         return k.value
+
+    @staticmethod
+    def _numpy_mt_state():
+        name, key, pos, has_gauss, cached = np.random.get_state()
+        if name != "MT19937":
+            raise RuntimeError("numpy's legacy generator is not MT19937")
+        return np.ascontiguousarray(key, dtype=np.uint32).copy(), C.c_int32(int(pos)), has_gauss, cached
+
+    def fof_finish_np_random(self):
+        """Stage 4 with the points drawn on the device from np.random's own MT19937 state, which is advanced
+        exactly as helper.py:197-202 would advance it."""
+        key, pos, has_gauss, cached = self._numpy_mt_state()
+        k = C.c_int64()
+        self.check(self.lib.fofb_fof_finish_mt(self.h, key.ctypes.data, C.byref(pos), C.byref(k)))
+        np.random.set_state(("MT19937", key, pos.value, has_gauss, cached))
+        return k.value
+
+    def pipeline_finish_np_random(self):
+        key, pos, has_gauss, cached = self._numpy_mt_state()
+        k, t = C.c_int64(), C.c_int64()
+        self.check(self.lib.fofb_pipeline_finish_mt(self.h, key.ctypes.data, C.byref(pos), C.byref(k), C.byref(t)))
+        np.random.set_state(("MT19937", key, pos.value, has_gauss, cached))
+        return k.value, t.value
 
     def fof_fetch(self, which=3):
         """(offsets int64[K+1], members int32[total], centre int32[K], N float64[K], D float64[K])."""

@@ -346,6 +346,23 @@ int fofb_fof_finish(fofb_handle* h, const double* rand_ra, const double* rand_de
   FOFB_CATCH(h)
 }
 
+int fofb_fof_finish_mt(fofb_handle* h, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  if (!h->fof || !h->fof->ran) throw fofb::Error(FOFB_ERR_STATE, "fofb_fof_finish_mt called before fofb_fof_run");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  const double prev_ms = h->last_ms;
+  const int64_t prev_launches = h->launches;
+  Timed timer(h);
+  h->fof->finish_mt(h, mt_key, mt_pos);
+  timer.stop();
+  h->last_ms += prev_ms;
+  h->launches += prev_launches;
+  if (n_final) *n_final = h->fof->final_.K;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
 static const ClusterList* pick_list(fofb_handle* h, int32_t which) {
   if (!h->fof || !h->fof->ran) throw fofb::Error(FOFB_ERR_STATE, "no FoF result: call fofb_fof_run first");
   switch (which) {
@@ -490,6 +507,25 @@ int fofb_pipeline_finish(fofb_handle* h, const double* u, int32_t mem, int64_t* 
   const int64_t prev_launches = h->launches;
   Timed timer(h);
   h->pipe->finish(h, u, mem);
+  timer.stop();
+  h->last_ms += prev_ms;
+  h->launches += prev_launches;
+  if (n_final) *n_final = h->pipe->K_out;
+  if (n_members) *n_members = h->pipe->total_out;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_pipeline_finish_mt(fofb_handle* h, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final, int64_t* n_members) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  if (!h->pipe || !h->pipe->began) throw fofb::Error(FOFB_ERR_STATE, "fofb_pipeline_finish_mt called before fofb_pipeline_begin");
+  FOFB_REQUIRE(mt_key && mt_pos, "MT19937 state is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  const double prev_ms = h->last_ms;
+  const int64_t prev_launches = h->launches;
+  Timed timer(h);
+  h->pipe->finish(h, nullptr, 0, mt_key, mt_pos);
   timer.stop();
   h->last_ms += prev_ms;
   h->launches += prev_launches;

@@ -303,13 +303,23 @@ void bootstrap_indices_host(long long n, long long count, int* out) {
   }
 }
 
+// per-member sin/cos of longitude and latitude for the O(n^2) pair sum
+__global__ void k_member_trig(long long total, View M, double4* trig) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  double sl, cl, sp, cp;
+  sincos(__dmul_rn(M.at(t, 0), kDeg2Rad), &sl, &cl);
+  sincos(__dmul_rn(M.at(t, 1), kDeg2Rad), &sp, &cp);
+  trig[t] = make_double4(sl, cl, sp, cp);
+}
+
 constexpr int kVirialThreads = 256;
 constexpr int kBootNum = 100;
 
 // One CTA per cluster.
-__global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const long long* off, View M, Cosmo cosmo,
-                                                                const unsigned* mt, long long mt_len, double mass_unit,
-                                                                double* out, int* status) {
+__global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const long long* off, View M, const double4* trig,
+                                                                Cosmo cosmo, const unsigned* mt, long long mt_len,
+                                                                double mass_unit, double* out, int* status) {
   const int k = blockIdx.x;
   if (k >= K) return;
   const long long s0 = off[k];
@@ -372,19 +382,31 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   // pair sum over i < j of 1 / (sep_deg * d_A * pi/180 * h)
   const double dA = cosmo_angular_diameter_distance(cosmo, zbar);
   double psum = 0.0;
-  const long long npairs = (long long)n * (n - 1) / 2;
-  for (long long q = tid; q < npairs; q += kVirialThreads) {
-    // unrank q -> (i, j), i < j, row-major over the upper triangle
-    const double nn = (double)n - 0.5;
-    long long i = (long long)floor(nn - sqrt(nn * nn - 2.0 * (double)q));
-    long long before = i * (2LL * n - i - 1) / 2;
-    while (before > q) { --i; before = i * (2LL * n - i - 1) / 2; }
-    while (before + (n - i - 1) <= q) { before += n - i - 1; ++i; }
-    const long long j = i + 1 + (q - before);
-    const double sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
-                                    __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
-    const double actual = sep * kRad2Deg * dA * kDeg2Rad * cosmo.h;
-    psum += 1.0 / actual;
+  {
+    // pairs (i, j), i < j, in row-major order of the upper triangle, strided over the block.  Vincenty's
+    // formula with the angle-difference identities on the precomputed sines and cosines; pairs closer than
+    // 1e-6 rad (where the identities lose digits) are recomputed from the angles themselves.
+    const double scale = kRad2Deg * dA * kDeg2Rad * cosmo.h;
+    int i = 0;
+    long long j = 1 + tid;
+    while (i < n - 1) {
+      while (j >= n && i < n - 1) {
+        j = j - n + (i + 2);
+        ++i;
+      }
+      if (i >= n - 1) break;
+      const double4 a = trig[s0 + i], b = trig[s0 + j];
+      const double sdlon = b.x * a.y - b.y * a.x, cdlon = b.y * a.y + b.x * a.x;
+      const double num1 = b.w * sdlon;
+      const double num2 = a.w * b.z - a.z * b.w * cdlon;
+      const double den = a.z * b.z + a.w * b.w * cdlon;
+      double sep = atan2(sqrt(num1 * num1 + num2 * num2), den);
+      if (sep < 1e-6)
+        sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
+                           __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
+      psum += 1.0 / (sep * scale);
+      j += kVirialThreads;
+    }
   }
   const double total_sep = Reduce(rtmp).Sum(psum);
   __syncthreads();
@@ -468,7 +490,12 @@ void CleanState::virial_core(fofb_handle* h, const fofb_params& p, int K, const 
   const double pc_m = 149597870700.0 * 648000.0 / kPi;
   const double msun_kg = 1.3271244e20 / 6.6743e-11;
   const double mass_unit = 1.0e6 * (1.0e6 * pc_m) / 6.6743e-11 / msun_kg;
-  FOFB_PROFILED(h, "k_virial_mass", k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status));
+  double4* trig = d_trig.alloc((size_t)std::max<long long>(M.rows, 1));
+  if (M.rows > 0) {
+    k_member_trig<<<grid_for(M.rows, 256), 256, 0, st>>>(M.rows, M, trig);
+    FOFB_LAUNCH_CHECK(h);
+  }
+  FOFB_PROFILED(h, "k_virial_mass", k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, trig, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status));
   int bad = 0;
   FOFB_CUDA(cudaMemcpyAsync(&bad, status, sizeof(int), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));

@@ -10,6 +10,7 @@ struct CleanState {
   DBuf<double> d_cen, d_vel, d_rad, d_dev, d_dA, d_props;
   DBuf<int> d_perm, d_bin_start, d_kept, d_out_index, d_status;
   DBuf<unsigned> d_mt;
+  DBuf<double4> d_trig;
   size_t mt_len = 0;
   // device-resident cores: results stay in d_out_off (K+1) / d_out_index; returns the kept total
   long long three_sigma_core(fofb_handle* h, const fofb_params& p, int K, const long long* d_off_in, long long total,

@@ -86,15 +86,20 @@ __global__ void k_kill_targets(View G, int n, int m, const double* skey, const i
 }
 
 // ---- centre cell list for the blocking test ----------------------------------------------------------------
-__global__ void k_cc_keys(int m, const double* ra, const double* dec, double ra0, double dec0, double inv_sra,
-                          double inv_sdec, int ncx, int ncy, unsigned* key, int* val) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
+__global__ void k_cc_keys(int m, const int* order, const double* ra, const double* dec, double ra0, double dec0,
+                          double inv_sra, double inv_sdec, int ncx, int ncy, unsigned* key) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int i = order[t];
   int cx = (int)floor((ra[i] - ra0) * inv_sra), cy = (int)floor((dec[i] - dec0) * inv_sdec);
   cx = min(max(cx, 0), ncx - 1);
   cy = min(max(cy, 0), ncy - 1);
-  key[i] = (unsigned)(cy * ncx + cx);
-  val[i] = i;
+  key[t] = (unsigned)(cy * ncx + cx);
+}
+
+__global__ void k_gather_d(int m, const int* idx, const double* src, double* dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m) dst[t] = src[idx[t]];
 }
 
 __global__ void k_cc_starts(int m, const unsigned* key, int ncell, int* start) {
@@ -109,13 +114,15 @@ struct CentreCells {
   double ra0, dec0, inv_sra, inv_sdec;
   int ncx, ncy;
   const int* start;
-  const int* idx;
+  const int* idx;     // centre index, cells sorted by centre redshift
+  const double* z;    // centre redshift in the same order
 };
 
 // ---- K9a: which active centres can be evaluated now ----------------------------------------------------------
-// Centre j (higher priority: j < i) can claim centre i as a member only if i lies in j's velocity
-// window and within j's virial search radius (members are a subset of virial_points, fof.py:180-228).
-// i is ready when no alive, undecided such j exists.
+// Centre j (higher priority: j < i) can claim the galaxy that switches centre i off only if that galaxy lies
+// in j's velocity window and within j's virial search radius (members are a subset of virial_points,
+// fof.py:180-228).  i is ready when no alive, undecided such j exists.  Cells are z-sorted, so only the
+// centres whose window can contain the galaxy are visited.
 __global__ void k_ready(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
                         const double* c_cos, const double* c_z, const double* c_R1, const unsigned char* alive,
                         const unsigned char* decided, const int* t_row, const double* ra_row, const double* dec_row,
@@ -127,6 +134,9 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
   const int g = t_row[i];
   if (g < 0) { ready_flag[t] = 1; return; }
   const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+  // |v(z; z_j)| <= vmax  =>  (z - beta)/(1 + beta) <= z_j <= (z + beta)/(1 - beta), beta = vmax/c (+ margin)
+  const double beta = vmax / kCkms;
+  const double zlo = (z - beta) / (1.0 + beta) - 1e-9, zhi = (z + beta) / (1.0 - beta) + 1e-9;
   const double reach = ra_reach(R1max, dec);
   int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
   int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
@@ -135,14 +145,19 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
   x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
   bool blocked = false;
   for (int yy = y0; yy <= y1 && !blocked; ++yy) {
-    const int s = cc.start[yy * cc.ncx + x0], e = cc.start[yy * cc.ncx + x1 + 1];
-    for (int k = s; k < e; ++k) {
-      const int j = cc.idx[k];
-      if (j >= i || !alive[j] || decided[j]) continue;
-      if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
-      BubbleTest bt;
-      bt.init(c_ra[j], c_dec[j], c_cos[j], c_R1[j]);
-      if (bt.inside(ra, dec, cs)) { blocked = true; break; }
+    for (int xx = x0; xx <= x1 && !blocked; ++xx) {
+      int lo = cc.start[yy * cc.ncx + xx];
+      const int e = cc.start[yy * cc.ncx + xx + 1];
+      int hi = e;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
+      for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
+        const int j = cc.idx[k];
+        if (j >= i || !alive[j] || decided[j]) continue;
+        if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+        BubbleTest bt;
+        bt.init(c_ra[j], c_dec[j], c_cos[j], c_R1[j]);
+        if (bt.inside(ra, dec, cs)) { blocked = true; break; }
+      }
     }
   }
   ready_flag[t] = blocked ? 0 : 1;
@@ -344,17 +359,21 @@ __device__ __forceinline__ bool hash_contains(const unsigned long long* tab, lon
 }
 
 // ---- K8b: hop 2 and the richness gate, one warp per centre (fof.py:208-246) ------------------------------------------
+// A row is admitted in the batch of the FIRST friend whose bubble contains it, iff none of its values occurs in
+// the member matrix as it stands before that batch; the value set only grows, so a row that fails once can never
+// be admitted later, and a row whose values already collide with the hop-1 members is out from the start.
 __global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, const long long* voff,
                        const unsigned long long* keys1, const unsigned long long* keys2, const long long* hoff,
                        const long long* hcap, unsigned long long* htab, View G, const double* ra_row,
                        const double* dec_row, const double* cos_row, const double* LLin, const double4* bbox2,
-                       fofb_params p, int* v2row, int* mrows, int* nm_list, unsigned char* admit_flag, int* nM,
+                       fofb_params p, int* v2row, int* mrows, int* nm_list, int* first_batch, int* nM,
                        int* pass, const int* kill_target, unsigned char* alive, unsigned char* decided) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nr) return;
   const int c = ready[w];
   const int n_v = nv[w];
+  const unsigned below = (1u << lane) - 1u;
   int n_members = 0;
   if (n_v >= p.min_virial) {
     const long long off = voff[w];
@@ -372,59 +391,81 @@ __global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, c
       unsigned long long* tab = htab + hoff[w];
       __syncwarp();
       for (int t = lane; t < n_f * G.cols; t += 32) hash_insert(tab, cap, G.at(v2row[off + t / G.cols], t % G.cols));
-      int n_nm = n_v - n_f;  // non-members, kept in V2 order
-      for (int t = lane; t < n_nm; t += 32) nm_list[off + t] = n_f + t;
+      __threadfence_block();
       __syncwarp();
-      const double LL = LLin[w];
-      const double4 b4 = bbox2[w];
-      const BBox b2{b4.x, b4.y, b4.z, b4.w};
-      for (int fi = 0; fi < n_f && n_nm > 0; ++fi) {
-        const int frow = v2row[off + fi];
-        const double fra = ra_row[frow], fdec = dec_row[frow];
-        const Box box = grid_box(b2, p.grid_cells, fra, fdec, LL);
-        BubbleTest bt;
-        bt.init(fra, fdec, cos_row[frow], LL);
-        // pass 1: admission of every remaining non-member against the member matrix before this batch
-        int any = 0;
-        for (int base = 0; base < n_nm; base += 32) {
-          const int t = base + lane;
-          bool adm = false;
-          if (t < n_nm) {
-            const int row = v2row[off + nm_list[off + t]];
-            const double pra = ra_row[row], pdec = dec_row[row];
-            if (box.contains(pra, pdec) && bt.inside(pra, pdec, cos_row[row])) {
-              adm = true;
-              for (int col = 0; col < G.cols && adm; ++col) adm = !hash_contains(tab, cap, G.at(row, col));
+      // candidates: non-members none of whose values occurs among the hop-1 members, kept in V2 order
+      int n_nm = 0;
+      for (int base = n_f; base < n_v; base += 32) {
+        const int t = base + lane;
+        bool novel = false;
+        if (t < n_v) {
+          const int row = v2row[off + t];
+          novel = true;
+          for (int col = 0; col < G.cols && novel; ++col) novel = !hash_contains(tab, cap, G.at(row, col));
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, novel);
+        if (novel) nm_list[off + n_nm + __popc(mk & below)] = t;
+        n_nm += __popc(mk);
+      }
+      __syncwarp();
+      if (n_nm > 0) {
+        const double LL = LLin[w];
+        const double4 b4 = bbox2[w];
+        const BBox b2{b4.x, b4.y, b4.z, b4.w};
+        // first friend (in order) whose bubble contains each candidate
+        for (int q = 0; q < n_nm; ++q) {
+          const int row = v2row[off + nm_list[off + q]];
+          const double pra = ra_row[row], pdec = dec_row[row], pcs = cos_row[row];
+          int first = 0x7fffffff;
+          for (int base = 0; base < n_f && first == 0x7fffffff; base += 32) {
+            const int fi = base + lane;
+            bool hit = false;
+            if (fi < n_f) {
+              const int frow = v2row[off + fi];
+              const double fra = ra_row[frow], fdec = dec_row[frow];
+              BubbleTest bt;
+              bt.init(fra, fdec, cos_row[frow], LL);
+              if (bt.inside(pra, pdec, pcs)) hit = grid_box(b2, p.grid_cells, fra, fdec, LL).contains(pra, pdec);
             }
-            admit_flag[off + t] = adm ? 1 : 0;
+            const unsigned mh = __ballot_sync(0xffffffffu, hit);
+            if (mh) first = base + __ffs(mh) - 1;
           }
-          any |= __any_sync(0xffffffffu, adm) ? 1 : 0;
+          if (lane == 0) first_batch[off + q] = first;
         }
-        if (!any) continue;
         __syncwarp();
-        // pass 2: append the admitted rows in order, insert their values, compact the non-member list
-        int kept = 0;
-        for (int base = 0; base < n_nm; base += 32) {
-          const int t = base + lane;
-          const bool in = t < n_nm;
-          const bool adm = in && admit_flag[off + t];
-          const int vpos = in ? nm_list[off + t] : 0;
-          const unsigned ma = __ballot_sync(0xffffffffu, adm), mk = __ballot_sync(0xffffffffu, in && !adm);
-          const unsigned below = (1u << lane) - 1u;
-          if (adm) {
-            const int row = v2row[off + vpos];
-            mrows[off + n_members + __popc(ma & below)] = row;
-            for (int col = 0; col < G.cols; ++col) hash_insert(tab, cap, G.at(row, col));
+        // batches in friend order; every candidate is decided in its first batch
+        for (;;) {
+          int fmin = 0x7fffffff;
+          for (int t = lane; t < n_nm; t += 32) fmin = min(fmin, first_batch[off + t]);
+          for (int o = 16; o; o >>= 1) fmin = min(fmin, __shfl_xor_sync(0xffffffffu, fmin, o));
+          if (fmin == 0x7fffffff) break;
+          // pass 1: admission against the member matrix before this batch
+          for (int base = 0; base < n_nm; base += 32) {
+            const int t = base + lane;
+            if (t < n_nm && first_batch[off + t] == fmin) {
+              const int row = v2row[off + nm_list[off + t]];
+              bool adm = true;
+              for (int col = 0; col < G.cols && adm; ++col) adm = !hash_contains(tab, cap, G.at(row, col));
+              first_batch[off + t] = adm ? -1 : 0x7fffffff;  // -1: admitted now; rejected rows are out for good
+            }
           }
           __syncwarp();
-          if (in && !adm) nm_list[off + kept + __popc(mk & below)] = vpos;  // kept + rank <= t: never ahead of reads
-          n_members += __popc(ma);
-          kept += __popc(mk);
+          // pass 2: append in order, then extend the value set
+          for (int base = 0; base < n_nm; base += 32) {
+            const int t = base + lane;
+            const bool adm = t < n_nm && first_batch[off + t] == -1;
+            const unsigned ma = __ballot_sync(0xffffffffu, adm);
+            if (adm) {
+              const int row = v2row[off + nm_list[off + t]];
+              mrows[off + n_members + __popc(ma & below)] = row;
+              for (int col = 0; col < G.cols; ++col) hash_insert(tab, cap, G.at(row, col));
+              first_batch[off + t] = 0x7fffffff;
+            }
+            n_members += __popc(ma);
+          }
+          __threadfence_block();
           __syncwarp();
         }
-        n_nm = kept;
-        __threadfence_block();
-        __syncwarp();
       }
     }
   }
@@ -436,6 +477,7 @@ __global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, c
   }
   if (ok) {  // tracker: members that are candidate centres never seed a cluster later (fof.py:238-246)
     const long long off = voff[w];
+    __syncwarp();
     for (int t = lane; t < n_members; t += 32) {
       const int tgt = kill_target[mrows[off + t]];
       if (tgt > c) alive[tgt] = 0;
@@ -614,22 +656,34 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
     cc_ncx = (int)floor(ext_ra / cc_sra) + 1;
     cc_ncy = (int)floor(ext_dec / cc_sdec) + 1;
     const int ncell = cc_ncx * cc_ncy;
+    // centres by redshift, then a stable sort by cell: every cell ends up z-sorted
+    double* zk_in = sort_keys_d.alloc(mm);
+    double* zk_out = sort_keys_d2.alloc(mm);
+    int* zi_in = sort_vals.alloc(mm);
+    int* zi_out = sort_vals2.alloc(mm);
+    FOFB_CUDA(cudaMemcpyAsync(zk_in, c_z.p, sizeof(double) * mm, cudaMemcpyDeviceToDevice, st));
+    k_iota_i32<<<grid_for(m, B), B, 0, st>>>(m, zi_in);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, zk_in, zk_out, zi_in, zi_out, m, 0, 64, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, zk_in, zk_out, zi_in, zi_out, m, 0, 64, st));
+    count_launch(h, 8);
     unsigned* ka = cc_key_a.alloc(mm);
     unsigned* kb = cc_key_b.alloc(mm);
-    int* va = cc_val_a.alloc(mm);
     int* vb = cc_idx.alloc(mm);
-    k_cc_keys<<<grid_for(m, B), B, 0, st>>>(m, c_ra.p, c_dec.p, cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx,
-                                            cc_ncy, ka, va);
+    k_cc_keys<<<grid_for(m, B), B, 0, st>>>(m, zi_out, c_ra.p, c_dec.p, cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx,
+                                            cc_ncy, ka);
     FOFB_LAUNCH_CHECK(h);
     int bits = 1;
     while ((1ll << bits) < ncell) ++bits;
-    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ka, kb, va, vb, m, 0, bits, st));
-    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, ka, kb, va, vb, m, 0, bits, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ka, kb, zi_out, vb, m, 0, bits, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, ka, kb, zi_out, vb, m, 0, bits, st));
     count_launch(h, 4);
     k_cc_starts<<<grid_for(m + 1, B), B, 0, st>>>(m, kb, ncell, cc_start.alloc((size_t)ncell + 1));
     FOFB_LAUNCH_CHECK(h);
+    k_gather_d<<<grid_for(m, B), B, 0, st>>>(m, vb, c_z.p, cc_z.alloc(mm));
+    FOFB_LAUNCH_CHECK(h);
   }
-  CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p};
+  CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p, cc_z.p};
   CellListView clbig = big.view();
 
   // ---- priority rounds ---------------------------------------------------------------------------
@@ -676,7 +730,7 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
       int* v2 = v2row.alloc(tv);
       int* mr = mrows.alloc(tv);
       int* nml = nm_list.alloc(tv);
-      unsigned char* adm = ismember.alloc(tv);
+      int* fbatch = first_batch.alloc(tv);
       double* LLp = LL.alloc(nr);
       double4* bb2 = bbox2.alloc(nr);
       unsigned long long* k1 = keys1.alloc(tv);
@@ -705,7 +759,7 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
         FOFB_CUDA(cudaMemsetAsync(ho, 0, sizeof(long long) * ((size_t)nr + 1), st));
       }
       FOFB_PROFILED(h, "k_hop2", k_hop2<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, k1s, k2s, ho, need, htab.p, G, cat.ra_row.p,
-                                      cat.dec_row.p, cos_row.p, LLp, bb2, p, v2, mr, nml, adm, nM_p, pass_p,
+                                      cat.dec_row.p, cos_row.p, LLp, bb2, p, v2, mr, nml, fbatch, nM_p, pass_p,
                                       kill_target.p, alive.p, decided.p));
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse

@@ -44,7 +44,8 @@ struct FofState {
   DBuf<int> active_a, active_b, ready, flags, counts, nv, nF, nM, cursor, pass;
   DBuf<long long> voff, hoff, hcap, moff;
   DBuf<unsigned long long> keys1, keys1b, keys2, keys2b, htab;
-  DBuf<int> v2row, mrows, nm_list;
+  DBuf<int> v2row, mrows, nm_list, first_batch;
+  DBuf<double> cc_z;
   DBuf<unsigned char> ismember;
   DBuf<double> LL;
   DBuf<double4> bbox1, bbox2;
@@ -66,6 +67,9 @@ struct FofState {
   // u: K x 2 x n_random samples of [0, 1) (per cluster the RA block, then the Dec block)
   void finish_unit(fofb_handle* h, const double* u, int mem);
   DBuf<double> unit_pts;
+  // draw the points on the device from numpy's legacy MT19937 state (624-word key + position), advanced in place
+  void finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host);
+  DBuf<unsigned> mt_key, mt_words;
 };
 
 }  // namespace fofb

@@ -570,6 +570,100 @@ __global__ void k_scale_points(long long total, int npts, const double* u, doubl
   dec[q] = __dadd_rn(dec_lo, __dmul_rn(dec_range, u[(2 * k + 1) * npts + i]));
 }
 
+// ---- numpy's legacy MT19937 on the device ------------------------------------------------------------------
+// center_overdensity (helper.py:196-202) consumes np.random's global MT19937 stream: 2 words per double,
+// (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.  One CTA advances the 624-word state block by block (three
+// dependent phases of 227 / 227 / 170 words) and writes the tempered words; a second kernel turns them into points.
+__device__ __forceinline__ unsigned mt_twist(unsigned u, unsigned v) {
+  const unsigned y = (u & 0x80000000u) | (v & 0x7fffffffu);
+  return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ unsigned mt_temper(unsigned y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+__global__ void __launch_bounds__(256) k_mt19937(unsigned* key, int pos, long long W, unsigned* out, int* pos_out) {
+  __shared__ unsigned buf[2][624];
+  const int tid = threadIdx.x;
+  for (int k = tid; k < 624; k += 256) buf[0][k] = key[k];
+  __syncthreads();
+  int cur = 0;
+  long long produced = 0;
+  int final_pos = pos;
+  {
+    const long long take = min((long long)(624 - pos), W);
+    for (int k = tid; k < take; k += 256) out[k] = mt_temper(buf[0][pos + k]);
+    produced = take > 0 ? take : 0;
+    final_pos = pos + (int)produced;
+  }
+  while (produced < W) {
+    unsigned* c = buf[cur];
+    unsigned* nx = buf[cur ^ 1];
+    if (tid < 227) nx[tid] = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
+    __syncthreads();
+    if (tid < 227) nx[227 + tid] = nx[tid] ^ mt_twist(c[227 + tid], c[228 + tid]);
+    __syncthreads();
+    if (tid < 170) {
+      const int k = 454 + tid;
+      nx[k] = nx[k - 227] ^ mt_twist(c[k], k == 623 ? nx[0] : c[k + 1]);
+    }
+    __syncthreads();
+    const long long take = min(624LL, W - produced);
+    for (int k = tid; k < take; k += 256) out[produced + k] = mt_temper(nx[k]);
+    produced += take;
+    final_pos = (int)take;
+    cur ^= 1;
+  }
+  __syncthreads();
+  for (int k = tid; k < 624; k += 256) key[k] = buf[cur][k];
+  if (tid == 0) *pos_out = final_pos;
+}
+
+__global__ void k_points_from_words(long long total, int npts, const unsigned* w, double ra_lo, double ra_range,
+                                    double dec_lo, double dec_range, double* ra, double* dec) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const long long k = q / npts, i = q % npts;
+  const long long ia = ((2 * k) * npts + i) * 2, id = ((2 * k + 1) * npts + i) * 2;
+  const double ua = ((double)(w[ia] >> 5) * 67108864.0 + (double)(w[ia + 1] >> 6)) / 9007199254740992.0;
+  const double ud = ((double)(w[id] >> 5) * 67108864.0 + (double)(w[id + 1] >> 6)) / 9007199254740992.0;
+  ra[q] = __dadd_rn(ra_lo, __dmul_rn(ra_range, ua));
+  dec[q] = __dadd_rn(dec_lo, __dmul_rn(dec_range, ud));
+}
+
+void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
+  if (!ran) throw Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
+  const int K = merged.K;
+  if (K == 0) {
+    finish(h, nullptr, nullptr, 1);
+    return;
+  }
+  FOFB_REQUIRE(key_host && pos_host && *pos_host >= 0 && *pos_host <= 624, "bad MT19937 state");
+  cudaStream_t st = h->stream;
+  const int npts = params.n_random;
+  const long long total = (long long)K * npts;
+  const long long W = total * 4;  // 2 coordinates x 2 words
+  unsigned* key = mt_key.alloc(624 + 2);
+  int* dpos = reinterpret_cast<int*>(key + 624);
+  FOFB_CUDA(cudaMemcpyAsync(key, key_host, sizeof(unsigned) * 624, cudaMemcpyHostToDevice, st));
+  unsigned* words = mt_words.alloc((size_t)W);
+  FOFB_PROFILED(h, "k_mt19937", k_mt19937<<<1, 256, 0, st>>>(key, *pos_host, W, words, dpos));
+  double* pts = unit_pts.alloc((size_t)total * 2);
+  const double ra_range = cat.gbox.ra_max - cat.gbox.ra_min, dec_range = cat.gbox.dec_max - cat.gbox.dec_min;
+  k_points_from_words<<<grid_for(total, 256), 256, 0, st>>>(total, npts, words, cat.gbox.ra_min, ra_range,
+                                                            cat.gbox.dec_min, dec_range, pts, pts + total);
+  FOFB_LAUNCH_CHECK(h);
+  FOFB_CUDA(cudaMemcpyAsync(key_host, key, sizeof(unsigned) * 624, cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaMemcpyAsync(pos_host, dpos, sizeof(int), cudaMemcpyDeviceToHost, st));
+  finish(h, pts, pts + total, 1);
+  FOFB_CUDA(cudaStreamSynchronize(st));
+}
+
 void FofState::finish_unit(fofb_handle* h, const double* u, int mem) {
   if (!ran) throw Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
   const int K = merged.K;

@@ -172,12 +172,13 @@ void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, doub
   began = true;
 }
 
-void Pipeline::finish(fofb_handle* h, const double* u, int mem) {
+void Pipeline::finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key, int* mt_pos) {
   cudaStream_t st = h->stream;
   const int B = 256;
   if (!began) throw Error(FOFB_ERR_STATE, "fofb_pipeline_finish called before fofb_pipeline_begin");
   const fofb_params& p = params;
-  fof.finish_unit(h, u, mem);
+  if (mt_key) fof.finish_mt(h, mt_key, mt_pos);
+  else fof.finish_unit(h, u, mem);
   K_out = 0;
   total_out = 0;
   finished = true;

@@ -22,7 +22,7 @@ struct Pipeline {
   DBuf<double> g_rows, c_rows, m_rows, m_rows2, centres, props, out_N, out_D;
   DBuf<long long> lens, out_off;
   void begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen);
-  void finish(fofb_handle* h, const double* u, int mem);
+  void finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key = nullptr, int* mt_pos = nullptr);
 };
 
 }  // namespace fofb

@@ -90,9 +90,8 @@ def FoF(galaxy_data, candidate_centers, richness, overdensity, max_velocity=2000
     h = _lib.get_handle(device)
     p = _lib_params(max_velocity=as_float(max_velocity, "km/s"), linking_length_factor=float(linking_length_factor),
                     virial_radius=as_float(virial_radius), richness=int(richness), overdensity=float(overdensity))
-    K, bbox = h.fof_run(g, c, p)
-    ra, dec = draw_overdensity_points(K, bbox, p.n_random)
-    h.fof_finish(ra, dec)
+    h.fof_run(g, c, p)
+    h.fof_finish_np_random()  # consumes np.random's MT19937 stream on the device, state written back
     return _clusters_from_csr(g, c, *h.fof_fetch(3))
 
 

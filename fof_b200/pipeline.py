@@ -68,7 +68,9 @@ def find_clusters(galaxy_data, max_velocity=None, linking_length_factor=None, vi
         overdensity=float(P.D if overdensity is None else overdensity))
     zmin = P.min_redshift if min_redshift is None else min_redshift
     zmax = P.max_redshift if max_redshift is None else max_redshift
-    K = h.pipeline_begin(g, p, zmin, zmax + 0.02, zmax)
-    u = np.random.random_sample((K, 2, p.n_random)) if uniforms is None else uniforms
-    Kf, total = h.pipeline_finish(u)
+    h.pipeline_begin(g, p, zmin, zmax + 0.02, zmax)
+    if uniforms is None:
+        Kf, total = h.pipeline_finish_np_random()
+    else:
+        Kf, total = h.pipeline_finish(uniforms)
     return Catalogue(g, *h.pipeline_fetch(Kf, total))

@@ -130,6 +130,11 @@ int fofb_candidate_order(fofb_handle* h, int32_t* rows_out, int32_t rows_mem, in
 int fofb_fof_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, const fofb_matrix* centres,
                  int64_t* n_clusters, double* bbox);
 int fofb_fof_finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int32_t mem, int64_t* n_final);
+/* Same as fofb_fof_finish, but the points are drawn ON THE DEVICE from numpy's legacy MT19937 generator: mt_key[624]
+ * and *mt_pos are the 'key' and 'pos' entries of np.random.get_state(); they are advanced in place by exactly the
+ * 4 * n_clusters * n_random words the reference's np.random.uniform calls would consume (helper.py:197-202), so
+ * np.random.set_state() with the returned values leaves the caller's generator where the reference would. */
+int fofb_fof_finish_mt(fofb_handle* h, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final);
 int fofb_fof_sizes(fofb_handle* h, int32_t which, int64_t* n_clusters, int64_t* n_members);
 int fofb_fof_fetch(fofb_handle* h, int32_t which, int64_t* offsets, int32_t* members, int32_t* centre, double* N,
                    double* D);
@@ -171,6 +176,7 @@ int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out);
 int fofb_pipeline_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double zmin, double zmax_gal,
                         double zmax_cen, int64_t* n_clusters);
 int fofb_pipeline_finish(fofb_handle* h, const double* u, int32_t mem, int64_t* n_final, int64_t* n_members);
+int fofb_pipeline_finish_mt(fofb_handle* h, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final, int64_t* n_members);
 int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
                         double* props);
 /* sizes seen by the last pipeline run: galaxies after the z cut, candidate centres, stage-1 candidate clusters,

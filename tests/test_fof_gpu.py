@@ -70,3 +70,22 @@ def test_fof_stages_match_oracle(lib, handle, n, seed, kind, b, rich, D, density
         assert np.array_equal(g[mem[off[k]:off[k + 1]]], cl.galaxies)
         assert N[k] == cl.N
         assert Dv[k] == cl.D, (Dv[k], cl.D)
+
+
+def test_device_mt19937_leaves_np_random_where_the_reference_would(lib, handle):
+    """FoF() draws the overdensity points on the device from np.random's MT19937 state; afterwards the
+    global generator must be exactly where helper.py:197-202's 2 x 300 uniforms per cluster leave it."""
+    from fof_b200 import fof
+    g, c = _inputs(6000, 2, "cosmos", 50000.0)
+    for seed in (5, 6):
+        np.random.seed(seed)
+        np.random.random_sample(seed * 100 + 17)  # start from an arbitrary position inside a state block
+        state0 = np.random.get_state()
+        clusters = fof.FoF(g, c, richness=12, overdensity=-1e9, linking_length_factor=0.2)
+        after = np.random.random_sample(3)
+        np.random.set_state(state0)
+        K = len(clusters)  # overdensity=-1e9 keeps every cluster with N >= 8; draws happen for all stage-4 inputs
+        K_stage4, _ = handle.fof_run(g, c, lib.default_params(richness=12, overdensity=-1e9))
+        ra, dec = fof.draw_overdensity_points(K_stage4, (g[:, 0].min(), g[:, 0].max(), g[:, 1].min(), g[:, 1].max()))
+        assert np.array_equal(after, np.random.random_sample(3))
+        assert K <= K_stage4
