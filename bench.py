@@ -235,8 +235,9 @@ def main():
     stats = {}
 
     def step(resident):
-        K = h.pipeline_begin(dev if resident else host_np, p, *ZCUT)
-        Kf, total = h.pipeline_finish_np_random()  # overdensity points: np.random's MT19937 stream, advanced on the device
+        # one C-ABI call; the overdensity points come from np.random's MT19937 state, advanced on the device
+        Kf, total = h.pipeline_run_np_random(dev if resident else host_np, p, *ZCUT)
+        K = h.pipeline_stats()["stage4_clusters"]
         ms, launches = h.last_timing()
         out = None
         if not resident:

@@ -79,6 +79,7 @@ def load():
         "fofb_fof_finish": (C.c_int, [vp, vp, vp, i32, P(i64)]),
         "fofb_fof_finish_mt": (C.c_int, [vp, vp, P(i32), P(i64)]),
         "fofb_pipeline_finish_mt": (C.c_int, [vp, vp, P(i32), P(i64), P(i64)]),
+        "fofb_pipeline_run": (C.c_int, [vp, P(Params), P(Matrix), dbl, dbl, dbl, vp, P(i32), P(i64), P(i64)]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
@@ -231,6 +232,17 @@ class Handle:
         np.random.set_state(("MT19937", key, pos.value, has_gauss, cached))
         return k.value, t.value
 
+    def pipeline_run_np_random(self, galaxies, params, zmin, zmax_gal, zmax_cen):
+        """The whole path in one C call; np.random's MT19937 state is consumed on the device and written back."""
+        m, keep = matrix_of(galaxies)
+        key, pos, has_gauss, cached = self._numpy_mt_state()
+        k, t = C.c_int64(), C.c_int64()
+        self.check(self.lib.fofb_pipeline_run(self.h, C.byref(params), C.byref(m), zmin, zmax_gal, zmax_cen,
+                                              key.ctypes.data, C.byref(pos), C.byref(k), C.byref(t)))
+        np.random.set_state(("MT19937", key, pos.value, has_gauss, cached))
+        del keep
+        return k.value, t.value
+
     def fof_fetch(self, which=3):
         """(offsets int64[K+1], members int32[total], centre int32[K], N float64[K], D float64[K])."""
         k, t = C.c_int64(), C.c_int64()
@@ -301,10 +313,10 @@ class Handle:
         return off, rows, cen, N, D, props
 
     def pipeline_stats(self):
-        s = np.zeros(6, dtype=np.int64)
+        s = np.zeros(7, dtype=np.int64)
         self.lib.fofb_pipeline_stats(self.h, s.ctypes.data)
         return dict(zip(("galaxies_after_zcut", "candidate_centres", "stage1_clusters", "stage1_members",
-                         "priority_rounds", "centres_evaluated"), s.tolist()))
+                         "priority_rounds", "centres_evaluated", "stage4_clusters"), s.tolist()))
 
     def fof_stats(self):
         r, e = C.c_int64(), C.c_int64()

@@ -535,6 +535,25 @@ int fofb_pipeline_finish_mt(fofb_handle* h, uint32_t* mt_key, int32_t* mt_pos, i
   FOFB_CATCH(h)
 }
 
+int fofb_pipeline_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double zmin, double zmax_gal,
+                      double zmax_cen, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final, int64_t* n_members) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(galaxies && mt_key && mt_pos, "galaxies / MT19937 state is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->pipe) h->pipe = new Pipeline();
+  Timed timer(h);
+  const View raw = to_device(h, *galaxies, h->upload);
+  h->pipe->begin(h, *p, raw, zmin, zmax_gal, zmax_cen, mt_key, *mt_pos);
+  h->pipe->finish(h, nullptr, 0, mt_key, mt_pos);
+  timer.stop();
+  if (n_final) *n_final = h->pipe->K_out;
+  if (n_members) *n_members = h->pipe->total_out;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
 int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
                         double* props) {
   if (!h) return FOFB_ERR_INVALID;
@@ -563,7 +582,7 @@ int fofb_pipeline_stats(fofb_handle* h, int64_t* s) {
   if (!h || !h->pipe || !s) return FOFB_ERR_STATE;
   Pipeline& P = *h->pipe;
   s[0] = P.n_g; s[1] = P.m_c; s[2] = P.fof.candidates.K; s[3] = P.fof.candidates.total;
-  s[4] = P.fof.rounds; s[5] = P.fof.evaluated;
+  s[4] = P.fof.rounds; s[5] = P.fof.evaluated; s[6] = P.fof.merged.K;
   return FOFB_OK;
 }
 

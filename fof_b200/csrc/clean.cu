@@ -429,12 +429,27 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
     }
     int rank, agg;
     Scan(stmp).ExclusiveSum(ok, rank, agg);
+    // accepted ordinals are consecutive across the block, so a warp touches one or two resamples: reduce per
+    // resample inside the warp and issue one shared-memory atomic per (warp, resample)
+    int rs = -1;
+    double v2 = 0.0;
     if (ok) {
       const long long ord = taken + rank;
       if (ord < want) {
+        rs = (int)(ord / (n - 1));
         const double v = redshift_to_velocity(M.at(s0 + val, 2), zbar);
-        atomicAdd(&boot[(int)(ord / (n - 1))], v * v);
+        v2 = v * v;
       }
+    }
+    unsigned remaining = __ballot_sync(0xffffffffu, rs >= 0);
+    while (remaining) {
+      const int leader = __ffs(remaining) - 1;
+      const int key = __shfl_sync(0xffffffffu, rs, leader);
+      const unsigned grp = __ballot_sync(0xffffffffu, rs == key);
+      double part = rs == key ? v2 : 0.0;
+      for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if ((threadIdx.x & 31) == leader) atomicAdd(&boot[key], part);
+      remaining &= ~grp;
     }
     __syncthreads();
     if (tid == 0) s_taken = taken + agg;

@@ -70,6 +70,14 @@ struct FofState {
   // draw the points on the device from numpy's legacy MT19937 state (624-word key + position), advanced in place
   void finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host);
   DBuf<unsigned> mt_key, mt_words;
+  void mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec);
+  cudaStream_t rng_stream = nullptr;
+  cudaEvent_t rng_done = nullptr;
+  bool mt_prefetched = false;
+  int mt_pos0 = 0, params_n_random_hint = 300;
+  long long mt_head = 0, mt_blocks = 0;
+  unsigned mt_key_host[624];
+  int last_K = 0;
 };
 
 }  // namespace fofb

@@ -3,6 +3,8 @@
 // (kernels K10, K11 of DESIGN.md).
 #include <cub/cub.cuh>
 
+#include <cstring>
+
 #include "fof_stage.cuh"
 
 namespace fofb {
@@ -587,21 +589,19 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y) {
   return y;
 }
 
-__global__ void __launch_bounds__(256) k_mt19937(unsigned* key, int pos, long long W, unsigned* out, int* pos_out) {
+// Generates `nblocks` new state blocks after `key` (624 raw words) and writes their tempered words to
+// out[0 .. 624*nblocks); when first == 1 the unread tail key[pos .. 624) of the current block is tempered into
+// head[0 .. 624-pos) first.  The final raw state is written back to `key`.
+__global__ void __launch_bounds__(256) k_mt19937(unsigned* key, int pos, int first, unsigned* head, long long nblocks,
+                                                 unsigned* out) {
   __shared__ unsigned buf[2][624];
   const int tid = threadIdx.x;
   for (int k = tid; k < 624; k += 256) buf[0][k] = key[k];
   __syncthreads();
+  if (first)
+    for (int k = pos + tid; k < 624; k += 256) head[k - pos] = mt_temper(buf[0][k]);
   int cur = 0;
-  long long produced = 0;
-  int final_pos = pos;
-  {
-    const long long take = min((long long)(624 - pos), W);
-    for (int k = tid; k < take; k += 256) out[k] = mt_temper(buf[0][pos + k]);
-    produced = take > 0 ? take : 0;
-    final_pos = pos + (int)produced;
-  }
-  while (produced < W) {
+  for (long long b = 0; b < nblocks; ++b) {
     unsigned* c = buf[cur];
     unsigned* nx = buf[cur ^ 1];
     if (tid < 227) nx[tid] = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
@@ -613,33 +613,67 @@ __global__ void __launch_bounds__(256) k_mt19937(unsigned* key, int pos, long lo
       nx[k] = nx[k - 227] ^ mt_twist(c[k], k == 623 ? nx[0] : c[k + 1]);
     }
     __syncthreads();
-    const long long take = min(624LL, W - produced);
-    for (int k = tid; k < take; k += 256) out[produced + k] = mt_temper(nx[k]);
-    produced += take;
-    final_pos = (int)take;
+    unsigned* o = out + b * 624;
+    for (int k = tid; k < 624; k += 256) o[k] = mt_temper(nx[k]);
     cur ^= 1;
   }
   __syncthreads();
   for (int k = tid; k < 624; k += 256) key[k] = buf[cur][k];
-  if (tid == 0) *pos_out = final_pos;
 }
 
-__global__ void k_points_from_words(long long total, int npts, const unsigned* w, double ra_lo, double ra_range,
-                                    double dec_lo, double dec_range, double* ra, double* dec) {
+// raw state block from its tempered words (the tempering transform is a bijection)
+__global__ void k_mt_untemper(const unsigned* words, unsigned* key) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= 624) return;
+  unsigned y = words[k];
+  y ^= y >> 18;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= ((y << 7) & 0x9d2c5680u) ^ ((y << 14) & 0x94284000u) ^ ((y << 21) & 0x14200000u) ^ ((y << 28) & 0x10000000u);
+  y ^= (y >> 11) ^ (y >> 22);
+  key[k] = y;
+}
+
+__global__ void k_points_from_words(long long total, int npts, const unsigned* w, long long head, double ra_lo,
+                                    double ra_range, double dec_lo, double dec_range, double* ra, double* dec) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= total) return;
   const long long k = q / npts, i = q % npts;
   const long long ia = ((2 * k) * npts + i) * 2, id = ((2 * k + 1) * npts + i) * 2;
-  const double ua = ((double)(w[ia] >> 5) * 67108864.0 + (double)(w[ia + 1] >> 6)) / 9007199254740992.0;
-  const double ud = ((double)(w[id] >> 5) * 67108864.0 + (double)(w[id + 1] >> 6)) / 9007199254740992.0;
+  auto word = [&](long long t) -> unsigned { return t < head ? w[t] : w[624 + (t - head)]; };
+  const double ua = ((double)(word(ia) >> 5) * 67108864.0 + (double)(word(ia + 1) >> 6)) / 9007199254740992.0;
+  const double ud = ((double)(word(id) >> 5) * 67108864.0 + (double)(word(id + 1) >> 6)) / 9007199254740992.0;
   ra[q] = __dadd_rn(ra_lo, __dmul_rn(ra_range, ua));
   dec[q] = __dadd_rn(dec_lo, __dmul_rn(dec_range, ud));
 }
 
+// Start generating the stream on a side stream while stages 0-3 run: enough words for k_spec clusters.
+void FofState::mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec) {
+  FOFB_REQUIRE(key_host && pos >= 0 && pos <= 624, "bad MT19937 state");
+  if (!rng_stream) {
+    FOFB_CUDA(cudaStreamCreateWithFlags(&rng_stream, cudaStreamNonBlocking));
+    FOFB_CUDA(cudaEventCreateWithFlags(&rng_done, cudaEventDisableTiming));
+  }
+  mt_pos0 = pos;
+  mt_head = 624 - pos;
+  const long long W = std::max<long long>(k_spec, 1) * params_n_random_hint * 4;
+  mt_blocks = std::max<long long>((W - mt_head + 623) / 624, 1);
+  unsigned* key = mt_key.alloc(624 * 2);
+  unsigned* words = mt_words.alloc((size_t)(624 + mt_blocks * 624));
+  std::memcpy(mt_key_host, key_host, sizeof(unsigned) * 624);
+  FOFB_CUDA(cudaMemcpyAsync(key, mt_key_host, sizeof(unsigned) * 624, cudaMemcpyHostToDevice, rng_stream));
+  k_mt19937<<<1, 256, 0, rng_stream>>>(key, pos, 1, words, mt_blocks, words + 624);
+  count_launch(h);
+  FOFB_CUDA(cudaGetLastError());
+  FOFB_CUDA(cudaEventRecord(rng_done, rng_stream));
+  mt_prefetched = true;
+}
+
+// word t of the consumed stream lives at: t < head ? words[t] : words[624 + (t - head)]
 void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
   if (!ran) throw Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
   const int K = merged.K;
   if (K == 0) {
+    mt_prefetched = false;
     finish(h, nullptr, nullptr, 1);
     return;
   }
@@ -648,18 +682,41 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
   const int npts = params.n_random;
   const long long total = (long long)K * npts;
   const long long W = total * 4;  // 2 coordinates x 2 words
-  unsigned* key = mt_key.alloc(624 + 2);
-  int* dpos = reinterpret_cast<int*>(key + 624);
-  FOFB_CUDA(cudaMemcpyAsync(key, key_host, sizeof(unsigned) * 624, cudaMemcpyHostToDevice, st));
-  unsigned* words = mt_words.alloc((size_t)W);
-  FOFB_PROFILED(h, "k_mt19937", k_mt19937<<<1, 256, 0, st>>>(key, *pos_host, W, words, dpos));
+  if (!mt_prefetched || mt_pos0 != *pos_host || std::memcmp(mt_key_host, key_host, sizeof(unsigned) * 624) != 0) {
+    params_n_random_hint = npts;
+    mt_prefetch(h, key_host, *pos_host, K);
+  }
+  FOFB_CUDA(cudaStreamWaitEvent(st, rng_done, 0));
+  const long long need_blocks = W > mt_head ? (W - mt_head + 623) / 624 : 0;
+  if (need_blocks > mt_blocks) {  // the speculation fell short: continue from the last generated state
+    const long long extra = need_blocks - mt_blocks;
+    DBuf<unsigned> bigger;
+    bigger.alloc((size_t)(624 + need_blocks * 624));
+    FOFB_CUDA(cudaMemcpyAsync(bigger.p, mt_words.p, sizeof(unsigned) * (size_t)(624 + mt_blocks * 624), cudaMemcpyDeviceToDevice, st));
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    std::swap(bigger.p, mt_words.p);
+    std::swap(bigger.cap, mt_words.cap);
+    FOFB_PROFILED(h, "k_mt19937", k_mt19937<<<1, 256, 0, st>>>(mt_key.p, 624, 0, nullptr, extra, mt_words.p + 624 + mt_blocks * 624));
+    mt_blocks = need_blocks;
+  }
   double* pts = unit_pts.alloc((size_t)total * 2);
   const double ra_range = cat.gbox.ra_max - cat.gbox.ra_min, dec_range = cat.gbox.dec_max - cat.gbox.dec_min;
-  k_points_from_words<<<grid_for(total, 256), 256, 0, st>>>(total, npts, words, cat.gbox.ra_min, ra_range,
+  k_points_from_words<<<grid_for(total, 256), 256, 0, st>>>(total, npts, mt_words.p, mt_head, cat.gbox.ra_min, ra_range,
                                                             cat.gbox.dec_min, dec_range, pts, pts + total);
   FOFB_LAUNCH_CHECK(h);
-  FOFB_CUDA(cudaMemcpyAsync(key_host, key, sizeof(unsigned) * 624, cudaMemcpyDeviceToHost, st));
-  FOFB_CUDA(cudaMemcpyAsync(pos_host, dpos, sizeof(int), cudaMemcpyDeviceToHost, st));
+  // the generator state after exactly W words
+  if (W <= mt_head) {
+    *pos_host += (int)W;
+  } else {
+    const long long rem = W - mt_head;
+    const long long last = (rem - 1) / 624;  // index of the last block touched
+    unsigned* key_out = mt_key.p + 624;
+    k_mt_untemper<<<3, 256, 0, st>>>(mt_words.p + 624 + last * 624, key_out);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_CUDA(cudaMemcpyAsync(key_host, key_out, sizeof(unsigned) * 624, cudaMemcpyDeviceToHost, st));
+    *pos_host = (int)(rem - last * 624);
+  }
+  mt_prefetched = false;
   finish(h, pts, pts + total, 1);
   FOFB_CUDA(cudaStreamSynchronize(st));
 }

@@ -122,11 +122,17 @@ __global__ void k_max_len(int K, const long long* off, int* out) {
   if (k < K) atomicMax(out, (int)(off[k + 1] - off[k]));
 }
 
-void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen) {
+void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen,
+                     const unsigned* mt_key, int mt_pos) {
   cudaStream_t st = h->stream;
   const int B = 256;
   began = finished = false;
   params = p;
+  if (mt_key) {  // overlap the serial MT19937 stream with stages 0-3
+    fof.params_n_random_hint = p.n_random;
+    const long long k_spec = fof.last_K > 0 ? (long long)(fof.last_K * 1.25) + 256 : raw.rows / 150 + 1024;
+    fof.mt_prefetch(h, mt_key, mt_pos, k_spec);
+  }
   FOFB_REQUIRE(raw.cols == 7, "the pipeline expects the 7 input columns ra, dec, z, z_lower, z_upper, RMag, ID");
   cat.build(h, raw);
   s0.run(h, p, cat, cells);
@@ -169,6 +175,7 @@ void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, doub
   Gv.data = G; Gv.rows = n_g; Gv.cols = ocols; Gv.rs = ocols; Gv.cs = 1;
   Cv.data = C; Cv.rows = m_c; Cv.cols = ocols; Cv.rs = ocols; Cv.cs = 1;
   fof.run(h, p, Gv, Cv);
+  fof.last_K = fof.merged.K;
   began = true;
 }
 

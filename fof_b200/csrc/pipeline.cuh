@@ -21,7 +21,8 @@ struct Pipeline {
   DBuf<int> flags, iotas, counter, g_src, c_src, selected, out_grow, out_rows, out_centre;
   DBuf<double> g_rows, c_rows, m_rows, m_rows2, centres, props, out_N, out_D;
   DBuf<long long> lens, out_off;
-  void begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen);
+  void begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen,
+             const unsigned* mt_key = nullptr, int mt_pos = 0);
   void finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key = nullptr, int* mt_pos = nullptr);
 };
 

@@ -68,9 +68,9 @@ def find_clusters(galaxy_data, max_velocity=None, linking_length_factor=None, vi
         overdensity=float(P.D if overdensity is None else overdensity))
     zmin = P.min_redshift if min_redshift is None else min_redshift
     zmax = P.max_redshift if max_redshift is None else max_redshift
-    h.pipeline_begin(g, p, zmin, zmax + 0.02, zmax)
     if uniforms is None:
-        Kf, total = h.pipeline_finish_np_random()
+        Kf, total = h.pipeline_run_np_random(g, p, zmin, zmax + 0.02, zmax)
     else:
+        h.pipeline_begin(g, p, zmin, zmax + 0.02, zmax)
         Kf, total = h.pipeline_finish(uniforms)
     return Catalogue(g, *h.pipeline_fetch(Kf, total))

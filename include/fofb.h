@@ -177,11 +177,14 @@ int fofb_pipeline_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix*
                         double zmax_cen, int64_t* n_clusters);
 int fofb_pipeline_finish(fofb_handle* h, const double* u, int32_t mem, int64_t* n_final, int64_t* n_members);
 int fofb_pipeline_finish_mt(fofb_handle* h, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final, int64_t* n_members);
+/* begin + finish_mt in one call; the MT19937 stream is generated on a side stream while stages 0-3 run */
+int fofb_pipeline_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double zmin, double zmax_gal,
+                      double zmax_cen, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final, int64_t* n_members);
 int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
                         double* props);
 /* sizes seen by the last pipeline run: galaxies after the z cut, candidate centres, stage-1 candidate clusters,
- * total stage-1 members, priority rounds, centres evaluated */
-int fofb_pipeline_stats(fofb_handle* h, int64_t* stats6);
+ * total stage-1 members, priority rounds, centres evaluated, clusters entering stage 4 */
+int fofb_pipeline_stats(fofb_handle* h, int64_t* stats7);
 
 #ifdef __cplusplus
 }
