@@ -22,7 +22,7 @@ static T d2h_scalar(fofb_handle* h, const T* dptr) {
 // ---- per-centre scalars (fof.py:158-175, 277-279; helper.py:182) -------------------------------------
 __global__ void k_centre_prep(View Cn, int m, CatalogView cat, Cosmo cosmo, double vmax, double virial_radius,
                               double count_radius, double* c_ra, double* c_dec, double* c_cos, double* c_z,
-                              double* c_R1, double* c_thvir, double* c_th05, double* c_mag, double* c_N,
+                              double* c_R1, double* c_T1, double* c_thvir, double* c_th05, double* c_mag, double* c_N,
                               double* c_id, int* c_wlo, int* c_whi, unsigned char* alive, unsigned char* decided) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -38,7 +38,12 @@ __global__ void k_centre_prep(View Cn, int m, CatalogView cat, Cosmo cosmo, doub
   // fof.py:165-175: angle -> comoving transverse length -> angle again (= theta_vir * (1 + z), Q4)
   const double ang = thvir * kDeg2Rad;
   const double max_dist_mpc = ang * cosmo_transverse_distance(cosmo, z);
-  c_R1[i] = cosmo_proper_mpc_to_deg(cosmo, max_dist_mpc, z);
+  const double R1 = cosmo_proper_mpc_to_deg(cosmo, max_dist_mpc, z);
+  c_R1[i] = R1;
+  {
+    const double sh = sin(0.5 * R1 * kDeg2Rad);
+    c_T1[i] = sh * sh;
+  }
   c_thvir[i] = thvir;
   c_th05[i] = cosmo_linear_to_angular_dist(cosmo, count_radius, z);
   int lo, hi;
@@ -124,8 +129,8 @@ struct CentreCells {
 // fof.py:180-228).  i is ready when no alive, undecided such j exists.  Cells are z-sorted, so only the
 // centres whose window can contain the galaxy are visited.
 __global__ void k_ready(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
-                        const double* c_cos, const double* c_z, const double* c_R1, const unsigned char* alive,
-                        const unsigned char* decided, const int* t_row, const double* ra_row, const double* dec_row,
+                        const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
+                        const unsigned char* alive, const unsigned char* decided, const int* t_row, const double* ra_row, const double* dec_row,
                         const double* cos_row, const double* z_row, double vmax, double R1max, int* ready_flag) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= na) return;
@@ -155,7 +160,7 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
         if (j >= i || !alive[j] || decided[j]) continue;
         if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
         BubbleTest bt;
-        bt.init(c_ra[j], c_dec[j], c_cos[j], c_R1[j]);
+        bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
         if (bt.inside(ra, dec, cs)) { blocked = true; break; }
       }
     }
@@ -358,16 +363,72 @@ __device__ __forceinline__ bool hash_contains(const unsigned long long* tab, lon
   }
 }
 
-// ---- K8b: hop 2 and the richness gate, one warp per centre (fof.py:208-246) ------------------------------------------
+// ---- K8b: hop 2 and the richness gate (fof.py:208-246) -------------------------------------------------------
 // A row is admitted in the batch of the FIRST friend whose bubble contains it, iff none of its values occurs in
 // the member matrix as it stands before that batch; the value set only grows, so a row that fails once can never
 // be admitted later, and a row whose values already collide with the hop-1 members is out from the start.
-__global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, const long long* voff,
-                       const unsigned long long* keys1, const unsigned long long* keys2, const long long* hoff,
-                       const long long* hcap, unsigned long long* htab, View G, const double* ra_row,
-                       const double* dec_row, const double* cos_row, const double* LLin, const double4* bbox2,
-                       fofb_params p, int* v2row, int* mrows, int* nm_list, int* first_batch, int* nM,
-                       int* pass, const int* kill_target, unsigned char* alive, unsigned char* decided) {
+// Four launches: (a) V2 order and friend rows, warp/centre; (b) hop-1 member values into the per-centre hash set,
+// thread/V2 entry; (c) novelty of every non-member against that set, thread/V2 entry; (d) the few surviving
+// candidates are decided batch by batch, warp/centre.
+__global__ void k_hop2_setup(int nr, const int* nv, const int* nF, const long long* voff, const unsigned long long* keys1,
+                             const unsigned long long* keys2, const double* ra_row, const double* dec_row,
+                             const double* cos_row, int min_virial, int* v2row, int* owner, double* v2ra, double* v2dec,
+                             double* v2cos, int* mrows) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nr) return;
+  const int n_v = nv[w];
+  if (n_v < min_virial) return;
+  const long long off = voff[w];
+  const int n_f = nF[w];
+  // V2 order: friends first (in f_gsp's return order), then the rest in f_gsp cell order
+  for (int t = lane; t < n_v; t += 32) {
+    const int k = (int)(unsigned)(keys2[off + t] & 0xffffffffull);
+    const int row = (int)(unsigned)(keys1[off + k] & 0xffffffffull);
+    v2row[off + t] = row;
+    owner[off + t] = w;
+    v2ra[off + t] = ra_row[row];
+    v2dec[off + t] = dec_row[row];
+    v2cos[off + t] = cos_row[row];
+    if (t < n_f) mrows[off + t] = row;
+  }
+}
+
+__global__ void k_hop2_insert(long long total, const int* owner, const long long* voff, const int* nF, const long long* hoff,
+                              const long long* hcap, unsigned long long* htab, View G, const int* v2row) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int w = owner[g];
+  const long long cap = hcap[w];
+  if (cap == 0 || g - voff[w] >= nF[w]) return;
+  unsigned long long* tab = htab + hoff[w];
+  const int row = v2row[g];
+  for (int col = 0; col < G.cols; ++col) hash_insert(tab, cap, G.at(row, col));
+}
+
+__global__ void k_hop2_novel(long long total, const int* owner, const long long* voff, const int* nF, const long long* hoff,
+                             const long long* hcap, const unsigned long long* htab, View G, const int* v2row,
+                             unsigned char* novel) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int w = owner[g];
+  const long long cap = hcap[w];
+  unsigned char nov = 0;
+  if (cap > 0 && g - voff[w] >= nF[w]) {
+    const unsigned long long* tab = htab + hoff[w];
+    const int row = v2row[g];
+    bool ok = true;  // columns from the last (N, then ID: the ones that collide in practice) to the first
+    for (int col = G.cols - 1; col >= 0 && ok; --col) ok = !hash_contains(tab, cap, G.at(row, col));
+    nov = ok ? 1 : 0;
+  }
+  novel[g] = nov;
+}
+
+__global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, const long long* voff, const long long* hoff,
+                       const long long* hcap, unsigned long long* htab, View G, const double* v2ra, const double* v2dec,
+                       const double* v2cos, const unsigned char* novel, const double* LLin, const double4* bbox2,
+                       fofb_params p, const int* v2row, int* mrows, int* nm_list, int* first_batch, int* nM, int* pass,
+                       const int* kill_target, unsigned char* alive, unsigned char* decided) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nr) return;
@@ -378,33 +439,17 @@ __global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, c
   if (n_v >= p.min_virial) {
     const long long off = voff[w];
     const int n_f = nF[w];
-    // V2 order: friends first (in f_gsp's return order), then the rest in f_gsp cell order
-    for (int t = lane; t < n_v; t += 32) {
-      const int k = (int)(unsigned)(keys2[off + t] & 0xffffffffull);
-      const int row = (int)(unsigned)(keys1[off + k] & 0xffffffffull);
-      v2row[off + t] = row;
-      if (t < n_f) mrows[off + t] = row;
-    }
     n_members = n_f;
     const long long cap = hcap[w];
     if (cap > 0) {
       unsigned long long* tab = htab + hoff[w];
-      __syncwarp();
-      for (int t = lane; t < n_f * G.cols; t += 32) hash_insert(tab, cap, G.at(v2row[off + t / G.cols], t % G.cols));
-      __threadfence_block();
-      __syncwarp();
-      // candidates: non-members none of whose values occurs among the hop-1 members, kept in V2 order
+      // candidates: the novel non-members, kept in V2 order
       int n_nm = 0;
       for (int base = n_f; base < n_v; base += 32) {
         const int t = base + lane;
-        bool novel = false;
-        if (t < n_v) {
-          const int row = v2row[off + t];
-          novel = true;
-          for (int col = 0; col < G.cols && novel; ++col) novel = !hash_contains(tab, cap, G.at(row, col));
-        }
-        const unsigned mk = __ballot_sync(0xffffffffu, novel);
-        if (novel) nm_list[off + n_nm + __popc(mk & below)] = t;
+        const bool nov = t < n_v && novel[off + t];
+        const unsigned mk = __ballot_sync(0xffffffffu, nov);
+        if (nov) nm_list[off + n_nm + __popc(mk & below)] = t;
         n_nm += __popc(mk);
       }
       __syncwarp();
@@ -412,19 +457,20 @@ __global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, c
         const double LL = LLin[w];
         const double4 b4 = bbox2[w];
         const BBox b2{b4.x, b4.y, b4.z, b4.w};
+        const double sh = sin(0.5 * LL * kDeg2Rad);
+        const double T = sh * sh;
         // first friend (in order) whose bubble contains each candidate
         for (int q = 0; q < n_nm; ++q) {
-          const int row = v2row[off + nm_list[off + q]];
-          const double pra = ra_row[row], pdec = dec_row[row], pcs = cos_row[row];
+          const int vp = nm_list[off + q];
+          const double pra = v2ra[off + vp], pdec = v2dec[off + vp], pcs = v2cos[off + vp];
           int first = 0x7fffffff;
           for (int base = 0; base < n_f && first == 0x7fffffff; base += 32) {
             const int fi = base + lane;
             bool hit = false;
             if (fi < n_f) {
-              const int frow = v2row[off + fi];
-              const double fra = ra_row[frow], fdec = dec_row[frow];
+              const double fra = v2ra[off + fi], fdec = v2dec[off + fi];
               BubbleTest bt;
-              bt.init(fra, fdec, cos_row[frow], LL);
+              bt.init_T(fra, fdec, v2cos[off + fi], LL, T);
               if (bt.inside(pra, pdec, pcs)) hit = grid_box(b2, p.grid_cells, fra, fdec, LL).contains(pra, pdec);
             }
             const unsigned mh = __ballot_sync(0xffffffffu, hit);
@@ -445,7 +491,7 @@ __global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, c
             if (t < n_nm && first_batch[off + t] == fmin) {
               const int row = v2row[off + nm_list[off + t]];
               bool adm = true;
-              for (int col = 0; col < G.cols && adm; ++col) adm = !hash_contains(tab, cap, G.at(row, col));
+              for (int col = G.cols - 1; col >= 0 && adm; --col) adm = !hash_contains(tab, cap, G.at(row, col));
               first_batch[off + t] = adm ? -1 : 0x7fffffff;  // -1: admitted now; rejected rows are out for good
             }
           }
@@ -595,7 +641,7 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
   const size_t mm = (size_t)m;
   FOFB_PROFILED(h, "k_centre_prep", k_centre_prep<<<grid_for(m, B), B, 0, st>>>(Cn, m, cv, cosmo, p.max_velocity, p.virial_radius, p.count_radius,
                                               c_ra.alloc(mm), c_dec.alloc(mm), c_cos.alloc(mm), c_z.alloc(mm),
-                                              c_R1.alloc(mm), c_thvir.alloc(mm), c_th05.alloc(mm), c_mag.alloc(mm),
+                                              c_R1.alloc(mm), c_T1.alloc(mm), c_thvir.alloc(mm), c_th05.alloc(mm), c_mag.alloc(mm),
                                               c_N.alloc(mm), c_id.alloc(mm), c_wlo.alloc(mm), c_whi.alloc(mm),
                                               alive.alloc(mm), decided.alloc(mm)));
   size_t bytes = 0;
@@ -689,8 +735,8 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
   // ---- priority rounds ---------------------------------------------------------------------------
   int* act = active_a.alloc(mm);
   int* act_next = active_b.alloc(mm);
-  k_iota_i32<<<grid_for(m, B), B, 0, st>>>(m, act);
-  FOFB_LAUNCH_CHECK(h);
+  // the active list walks the centre cell list, so a warp's 32 centres share cells and redshift neighbourhoods
+  FOFB_CUDA(cudaMemcpyAsync(act, cc_idx.p, sizeof(int) * mm, cudaMemcpyDeviceToDevice, st));
   int na = m;
   int* d_count = reinterpret_cast<int*>(scal_p + 8);
   pool_centre.alloc(mm);
@@ -699,7 +745,7 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
   while (na > 0) {
     ++rounds;
     int* fl = flags.alloc((size_t)na);
-    FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, alive.p, decided.p,
+    FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
                                                t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
                                                p.max_velocity, R1max, fl));
     int* rdy = ready.alloc((size_t)na);
@@ -758,9 +804,23 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
         FOFB_CUDA(cudaMemsetAsync(nF_p, 0, sizeof(int) * nr, st));
         FOFB_CUDA(cudaMemsetAsync(ho, 0, sizeof(long long) * ((size_t)nr + 1), st));
       }
-      FOFB_PROFILED(h, "k_hop2", k_hop2<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, k1s, k2s, ho, need, htab.p, G, cat.ra_row.p,
-                                      cat.dec_row.p, cos_row.p, LLp, bb2, p, v2, mr, nml, fbatch, nM_p, pass_p,
-                                      kill_target.p, alive.p, decided.p));
+      if (total_v > 0) {
+        int* own = owner.alloc(tv);
+        double* v2a = v2ra.alloc(tv);
+        double* v2d = v2dec.alloc(tv);
+        double* v2c = v2cos.alloc(tv);
+        unsigned char* nov = ismember.alloc(tv);
+        k_hop2_setup<<<wblocks, 128, 0, st>>>(nr, nv_p, nF_p, vo, k1s, k2s, cat.ra_row.p, cat.dec_row.p, cos_row.p, p.min_virial,
+                                              v2, own, v2a, v2d, v2c, mr);
+        FOFB_LAUNCH_CHECK(h);
+        if (total_h > 0) {
+          FOFB_PROFILED(h, "k_hop2_insert", k_hop2_insert<<<grid_for(total_v, B), B, 0, st>>>(total_v, own, vo, nF_p, ho, need, htab.p, G, v2));
+          FOFB_PROFILED(h, "k_hop2_novel", k_hop2_novel<<<grid_for(total_v, B), B, 0, st>>>(total_v, own, vo, nF_p, ho, need, htab.p, G, v2, nov));
+        }
+      }
+      FOFB_PROFILED(h, "k_hop2", k_hop2<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p,
+                                      ismember.p, LLp, bb2, p, v2, mr, nml, fbatch, nM_p, pass_p, kill_target.p, alive.p,
+                                      decided.p));
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse
       long long* dst = ho;    // reuse

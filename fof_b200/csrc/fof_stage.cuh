@@ -25,7 +25,7 @@ struct FofState {
   fofb_params params{};
 
   // per-centre (index = priority)
-  DBuf<double> c_ra, c_dec, c_cos, c_z, c_R1, c_thvir, c_th05, c_mag, c_N, c_id;
+  DBuf<double> c_ra, c_dec, c_cos, c_z, c_R1, c_T1, c_thvir, c_th05, c_mag, c_N, c_id;
   DBuf<int> c_wlo, c_whi;
   DBuf<unsigned char> alive, decided;
   DBuf<int> t_row, t_count;  // per centre: the galaxy row whose membership switches it off (-1: none)
@@ -45,7 +45,8 @@ struct FofState {
   DBuf<long long> voff, hoff, hcap, moff;
   DBuf<unsigned long long> keys1, keys1b, keys2, keys2b, htab;
   DBuf<int> v2row, mrows, nm_list, first_batch;
-  DBuf<double> cc_z;
+  DBuf<double> cc_z, v2ra, v2dec, v2cos;
+  DBuf<int> owner;
   DBuf<unsigned char> ismember;
   DBuf<double> LL;
   DBuf<double4> bbox1, bbox2;

@@ -40,9 +40,12 @@ __device__ __forceinline__ double sin_small(double x) {
 struct BubbleTest {
   double ra, dec, cosdec, r_deg, T_lo, T_hi;
   __device__ __forceinline__ void init(double ra_, double dec_, double cosdec_, double r) {
-    ra = ra_; dec = dec_; cosdec = cosdec_; r_deg = r;
     const double s = sin(0.5 * r * kDeg2Rad);
-    const double T = s * s;
+    init_T(ra_, dec_, cosdec_, r, s * s);
+  }
+  // with T = sin^2(r/2) precomputed (r in degrees)
+  __device__ __forceinline__ void init_T(double ra_, double dec_, double cosdec_, double r, double T) {
+    ra = ra_; dec = dec_; cosdec = cosdec_; r_deg = r;
     T_lo = T * (1.0 - 1e-9);
     T_hi = T * (1.0 + 1e-9);
   }

@@ -492,12 +492,22 @@ __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, c
   }
 }
 
-// one thread per (cluster, random point): galaxies of the centre's velocity window within theta_0.5
-__global__ void k_od_count(long long total, int npts, const int* centre, CellListView cl, const int* c_wlo,
-                           const int* c_whi, const double* c_th05, const double4* bbox, const int* all_oof,
-                           const double* rra, const double* rdec, int grid_cells, int* counts) {
+// cell of every query point, so that the queries can be processed in cell order (neighbouring threads then
+// touch the same cells: the 300 points of one cluster are scattered over the whole footprint)
+__global__ void k_od_keys(long long total, CellListView cl, const double* rra, const double* rdec, unsigned* key, int* val) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= total) return;
+  key[q] = (unsigned)(cl.cy_of(rdec[q]) * cl.ncx + cl.cx_of(rra[q]));
+  val[q] = (int)q;
+}
+
+// one thread per (cluster, random point): galaxies of the centre's velocity window within theta_0.5
+__global__ void k_od_count(long long total, int npts, const int* order, const int* centre, CellListView cl, const int* c_wlo,
+                           const int* c_whi, const double* c_th05, const double4* bbox, const int* all_oof,
+                           const double* rra, const double* rdec, int grid_cells, int* counts) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long long q = order[t];
   const int k = (int)(q / npts);
   int cnt = 0;
   if (!all_oof[k]) {
@@ -780,7 +790,23 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, bb, oof);
   FOFB_LAUNCH_CHECK(h);
   int* counts = sc.ev_a.alloc((size_t)total);
-  FOFB_PROFILED(h, "k_od_count", k_od_count<<<grid_for(total, 128), 128, 0, st>>>(total, npts, merged.centre.p, small.view(), c_wlo.p, c_whi.p, c_th05.p, bb,
+  FOFB_REQUIRE(total < (1ll << 31), "too many overdensity sample points");
+  const CellListView scl = small.view();
+  unsigned* qk = reinterpret_cast<unsigned*>(sc.ev_c.alloc((size_t)total));
+  unsigned* qk2 = reinterpret_cast<unsigned*>(sc.ev_loser.alloc((size_t)total));
+  int* qv = sc.kidx.alloc((size_t)total);
+  int* qv2 = sc.kidx_sorted.alloc((size_t)total);
+  k_od_keys<<<grid_for(total, 256), 256, 0, st>>>(total, scl, rra, rdec, qk, qv);
+  FOFB_LAUNCH_CHECK(h);
+  {
+    int bits = 1;
+    while ((1ll << bits) < (long long)scl.ncx * scl.ncy) ++bits;
+    size_t bytes = 0;
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, qk, qk2, qv, qv2, (int)total, 0, bits, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, qk, qk2, qv, qv2, (int)total, 0, bits, st));
+    count_launch(h, 4);
+  }
+  FOFB_PROFILED(h, "k_od_count", k_od_count<<<grid_for(total, 128), 128, 0, st>>>(total, npts, qv2, merged.centre.p, scl, c_wlo.p, c_whi.p, c_th05.p, bb,
                                                    oof, rra, rdec, p.grid_cells, counts));
   int* keep = sc.state.alloc(K);
   k_od_finish<<<wblocks, 128, 0, st>>>(K, npts, counts, N_own, merged.off.p, p.overdensity, p.min_count, p.richness, D, keep);
