@@ -168,6 +168,52 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
   ready_flag[t] = blocked ? 0 : 1;
 }
 
+// Same test with one warp per centre and one lane per neighbour cell: used for the late, small rounds, where the
+// serial chain of dependent loads of a single thread is what the round waits for.
+__global__ void k_ready_warp(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
+                             const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
+                             const unsigned char* alive, const unsigned char* decided, const int* t_row,
+                             const double* ra_row, const double* dec_row, const double* cos_row, const double* z_row,
+                             double vmax, double R1max, int* ready_flag) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= na) return;
+  const int i = active[t];
+  const int g = t_row[i];
+  if (g < 0) {
+    if (lane == 0) ready_flag[t] = 1;
+    return;
+  }
+  const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+  const double beta = vmax / kCkms;
+  const double zlo = (z - beta) / (1.0 + beta) - 1e-9, zhi = (z + beta) / (1.0 - beta) + 1e-9;
+  const double reach = ra_reach(R1max, dec);
+  int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
+  int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
+      y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
+  x0 = max(x0, 0); y0 = max(y0, 0);
+  x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
+  const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
+  bool blocked = false;
+  for (int cidx = lane; cidx < ncells && !blocked; cidx += 32) {
+    const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
+    int lo = cc.start[yy * cc.ncx + xx];
+    const int e = cc.start[yy * cc.ncx + xx + 1];
+    int hi = e;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
+    for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
+      const int j = cc.idx[k];
+      if (j >= i || !alive[j] || decided[j]) continue;
+      if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+      BubbleTest bt;
+      bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
+      if (bt.inside(ra, dec, cs)) { blocked = true; break; }
+    }
+  }
+  blocked = __any_sync(0xffffffffu, blocked);
+  if (lane == 0) ready_flag[t] = blocked ? 0 : 1;
+}
+
 __global__ void k_still_active(int na, const int* active, const unsigned char* alive, const unsigned char* decided,
                                int* flag) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,6 +409,32 @@ __device__ __forceinline__ bool hash_contains(const unsigned long long* tab, lon
   }
 }
 
+// Single-owner variants for phase (d): only one CTA touches the table, so ordinary cached loads/stores with
+// block barriers in between are coherent (same SM, same L1) and avoid an L2 round trip per probe.
+__device__ __forceinline__ void hash_insert_owner(unsigned long long* tab, long long cap, double v) {
+  unsigned long long b;
+  if (!value_bits(v, &b)) return;
+  long long s = (long long)(hash_mix(b) & (unsigned long long)(cap - 1));
+  for (;;) {
+    const unsigned long long cur = tab[s];
+    if (cur == b) return;
+    if (cur == kHashEmpty) { tab[s] = b; return; }
+    s = (s + 1) & (cap - 1);
+  }
+}
+
+__device__ __forceinline__ bool hash_contains_owner(const unsigned long long* tab, long long cap, double v) {
+  unsigned long long b;
+  if (!value_bits(v, &b)) return false;
+  long long s = (long long)(hash_mix(b) & (unsigned long long)(cap - 1));
+  for (;;) {
+    const unsigned long long cur = tab[s];
+    if (cur == b) return true;
+    if (cur == kHashEmpty) return false;
+    s = (s + 1) & (cap - 1);
+  }
+}
+
 // ---- K8b: hop 2 and the richness gate (fof.py:208-246) -------------------------------------------------------
 // A row is admitted in the batch of the FIRST friend whose bubble contains it, iff none of its values occurs in
 // the member matrix as it stands before that batch; the value set only grows, so a row that fails once can never
@@ -424,17 +496,22 @@ __global__ void k_hop2_novel(long long total, const int* owner, const long long*
   novel[g] = nov;
 }
 
-__global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, const long long* voff, const long long* hoff,
-                       const long long* hcap, unsigned long long* htab, View G, const double* v2ra, const double* v2dec,
-                       const double* v2cos, const unsigned char* novel, const double* LLin, const double4* bbox2,
-                       fofb_params p, const int* v2row, int* mrows, int* nm_list, int* first_batch, int* nM, int* pass,
-                       const int* kill_target, unsigned char* alive, unsigned char* decided) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+constexpr int kHop2Threads = 256;
+
+// (d) one CTA per centre: the surviving candidates are decided batch by batch.
+__global__ void __launch_bounds__(kHop2Threads) k_hop2(
+    int nr, const int* ready, const int* nv, const int* nF, const long long* voff, const long long* hoff,
+    const long long* hcap, unsigned long long* htab, View G, const double* v2ra, const double* v2dec, const double* v2cos,
+    const unsigned char* novel, const double* LLin, const double4* bbox2, fofb_params p, const int* v2row, int* mrows,
+    int* nm_list, int* first_batch, int* nm_sorted, int* nM, int* pass, const int* kill_target, unsigned char* alive,
+    unsigned char* decided, unsigned long long* dbg) {
+  const int w = blockIdx.x;
   if (w >= nr) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kHop2Threads / 32;
   const int c = ready[w];
   const int n_v = nv[w];
-  const unsigned below = (1u << lane) - 1u;
+  __shared__ int s_nnm, s_members, s_warp_cnt[kWarps];
   int n_members = 0;
   if (n_v >= p.min_virial) {
     const long long off = voff[w];
@@ -443,88 +520,115 @@ __global__ void k_hop2(int nr, const int* ready, const int* nv, const int* nF, c
     const long long cap = hcap[w];
     if (cap > 0) {
       unsigned long long* tab = htab + hoff[w];
-      // candidates: the novel non-members, kept in V2 order
+      // candidates: the novel non-members, kept in V2 order (block-wide ordered compaction)
       int n_nm = 0;
-      for (int base = n_f; base < n_v; base += 32) {
-        const int t = base + lane;
+      for (int base = n_f; base < n_v; base += kHop2Threads) {
+        const int t = base + tid;
         const bool nov = t < n_v && novel[off + t];
         const unsigned mk = __ballot_sync(0xffffffffu, nov);
-        if (nov) nm_list[off + n_nm + __popc(mk & below)] = t;
-        n_nm += __popc(mk);
+        if (lane == 0) s_warp_cnt[warp] = __popc(mk);
+        __syncthreads();
+        int before = 0, all = 0;
+        for (int k = 0; k < kWarps; ++k) {
+          before += k < warp ? s_warp_cnt[k] : 0;
+          all += s_warp_cnt[k];
+        }
+        if (nov) nm_list[off + n_nm + before + __popc(mk & ((1u << lane) - 1u))] = t;
+        n_nm += all;
+        __syncthreads();
       }
-      __syncwarp();
+      if (dbg && tid == 0) { atomicMax(dbg, (unsigned long long)n_v); atomicMax(dbg + 1, (unsigned long long)n_nm); atomicAdd(dbg + 2, (unsigned long long)n_nm); atomicAdd(dbg + 3, 1ull); atomicMax(dbg + 4, (unsigned long long)n_f); }
       if (n_nm > 0) {
         const double LL = LLin[w];
         const double4 b4 = bbox2[w];
         const BBox b2{b4.x, b4.y, b4.z, b4.w};
         const double sh = sin(0.5 * LL * kDeg2Rad);
         const double T = sh * sh;
-        // first friend (in order) whose bubble contains each candidate
-        for (int q = 0; q < n_nm; ++q) {
-          const int vp = nm_list[off + q];
-          const double pra = v2ra[off + vp], pdec = v2dec[off + vp], pcs = v2cos[off + vp];
-          int first = 0x7fffffff;
-          for (int base = 0; base < n_f && first == 0x7fffffff; base += 32) {
-            const int fi = base + lane;
-            bool hit = false;
-            if (fi < n_f) {
-              const double fra = v2ra[off + fi], fdec = v2dec[off + fi];
-              BubbleTest bt;
-              bt.init_T(fra, fdec, v2cos[off + fi], LL, T);
-              if (bt.inside(pra, pdec, pcs)) hit = grid_box(b2, p.grid_cells, fra, fdec, LL).contains(pra, pdec);
-            }
+        // first friend (in order) whose bubble contains each candidate.  Friends sit in the lanes, 32 per warp
+        // step; the candidates stream past them; atomicMin merges the warps' findings.
+        for (int q = tid; q < n_nm; q += kHop2Threads) first_batch[off + q] = 0x7fffffff;
+        __syncthreads();
+        for (int base = warp * 32; base < n_f; base += kHop2Threads) {
+          const int fi = base + lane;
+          const bool have = fi < n_f;
+          const double fra = have ? v2ra[off + fi] : 0.0, fdec = have ? v2dec[off + fi] : 0.0;
+          BubbleTest bt;
+          bt.init_T(fra, fdec, have ? v2cos[off + fi] : 1.0, LL, T);
+          const Box fbox = grid_box(b2, p.grid_cells, fra, fdec, LL);  // the friend's cell box: once per friend
+          for (int q = 0; q < n_nm; ++q) {
+            if (*(volatile int*)(first_batch + off + q) <= base) continue;  // an earlier friend already has it
+            const int vp = nm_list[off + q];
+            const double pra = v2ra[off + vp], pdec = v2dec[off + vp];
+            const bool hit = have && fbox.contains(pra, pdec) && bt.inside(pra, pdec, v2cos[off + vp]);
             const unsigned mh = __ballot_sync(0xffffffffu, hit);
-            if (mh) first = base + __ffs(mh) - 1;
+            if (mh && lane == 0) atomicMin(first_batch + off + q, base + __ffs(mh) - 1);
           }
-          if (lane == 0) first_batch[off + q] = first;
         }
-        __syncwarp();
-        // batches in friend order; every candidate is decided in its first batch
-        for (;;) {
-          int fmin = 0x7fffffff;
-          for (int t = lane; t < n_nm; t += 32) fmin = min(fmin, first_batch[off + t]);
-          for (int o = 16; o; o >>= 1) fmin = min(fmin, __shfl_xor_sync(0xffffffffu, fmin, o));
-          if (fmin == 0x7fffffff) break;
-          // pass 1: admission against the member matrix before this batch
-          for (int base = 0; base < n_nm; base += 32) {
-            const int t = base + lane;
-            if (t < n_nm && first_batch[off + t] == fmin) {
-              const int row = v2row[off + nm_list[off + t]];
-              bool adm = true;
-              for (int col = G.cols - 1; col >= 0 && adm; --col) adm = !hash_contains(tab, cap, G.at(row, col));
-              first_batch[off + t] = adm ? -1 : 0x7fffffff;  // -1: admitted now; rejected rows are out for good
-            }
+        __syncthreads();
+        // candidates ordered by (first batch, V2 position): rank by all-pairs counting
+        for (int q = tid; q < n_nm; q += kHop2Threads) {
+          const int fq = first_batch[off + q];
+          int rank = 0;
+          for (int r = 0; r < n_nm; ++r) {
+            const int fr = first_batch[off + r];
+            rank += (fr < fq || (fr == fq && r < q)) ? 1 : 0;
           }
-          __syncwarp();
-          // pass 2: append in order, then extend the value set
-          for (int base = 0; base < n_nm; base += 32) {
-            const int t = base + lane;
-            const bool adm = t < n_nm && first_batch[off + t] == -1;
-            const unsigned ma = __ballot_sync(0xffffffffu, adm);
-            if (adm) {
-              const int row = v2row[off + nm_list[off + t]];
-              mrows[off + n_members + __popc(ma & below)] = row;
-              for (int col = 0; col < G.cols; ++col) hash_insert(tab, cap, G.at(row, col));
-              first_batch[off + t] = 0x7fffffff;
-            }
-            n_members += __popc(ma);
+          nm_sorted[off + rank] = q;
+        }
+        __syncthreads();
+        // one pass over the batches in friend order; every candidate is decided in its first batch, against the
+        // member matrix as it stood before that batch.
+        const int cols = G.cols;
+        int s0 = 0;
+        while (s0 < n_nm) {
+          const int fb = first_batch[off + nm_sorted[off + s0]];
+          if (fb == 0x7fffffff) break;  // no friend's bubble contains the remaining rows
+          int s1 = s0 + 1;
+          while (s1 < n_nm && first_batch[off + nm_sorted[off + s1]] == fb) ++s1;
+          __syncthreads();
+          // pass 1: every row of the batch against the value set as it stands BEFORE the batch (a warp per row)
+          for (int j = s0 + warp; j < s1; j += kWarps) {
+            const int q = nm_sorted[off + j];
+            const int row = v2row[off + nm_list[off + q]];
+            bool found = false;
+            for (int col = lane; col < cols && !found; col += 32) found = hash_contains_owner(tab, cap, G.at(row, col));
+            const bool adm = !__any_sync(0xffffffffu, found);
+            if (lane == 0 && adm) first_batch[off + q] = -1;
           }
-          __threadfence_block();
-          __syncwarp();
+          __syncthreads();
+          // pass 2: append the admitted rows in order and extend the value set (warp 0)
+          if (warp == 0) {
+            int nm = n_members;
+            for (int j = s0; j < s1; ++j) {
+              const int q = nm_sorted[off + j];
+              if (first_batch[off + q] != -1) continue;
+              const int row = v2row[off + nm_list[off + q]];
+              if (lane == 0) {  // one thread inserts: plain stores, no two writers
+                mrows[off + nm] = row;
+                for (int col = 0; col < cols; ++col) hash_insert_owner(tab, cap, G.at(row, col));
+              }
+              ++nm;
+            }
+            if (lane == 0) s_members = nm;
+            __threadfence_block();
+          }
+          __syncthreads();
+          n_members = s_members;
+          s0 = s1;
         }
       }
     }
   }
   const bool ok = n_members >= p.richness;
-  if (lane == 0) {
+  if (tid == 0) {
     nM[w] = n_members;
     pass[w] = ok ? 1 : 0;
     decided[c] = 1;
   }
   if (ok) {  // tracker: members that are candidate centres never seed a cluster later (fof.py:238-246)
     const long long off = voff[w];
-    __syncwarp();
-    for (int t = lane; t < n_members; t += 32) {
+    __syncthreads();
+    for (int t = tid; t < n_members; t += kHop2Threads) {
       const int tgt = kill_target[mrows[off + t]];
       if (tgt > c) alive[tgt] = 0;
     }
@@ -739,15 +843,22 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
   FOFB_CUDA(cudaMemcpyAsync(act, cc_idx.p, sizeof(int) * mm, cudaMemcpyDeviceToDevice, st));
   int na = m;
   int* d_count = reinterpret_cast<int*>(scal_p + 8);
+  FOFB_CUDA(cudaMemsetAsync(dbg_buf.alloc(8), 0, 64, st));
   pool_centre.alloc(mm);
   pool_off.alloc(mm);
   pool_len.alloc(mm);
   while (na > 0) {
     ++rounds;
     int* fl = flags.alloc((size_t)na);
-    FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
+    if (na > 8192) {
+      FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
                                                t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
                                                p.max_velocity, R1max, fl));
+    } else {
+      FOFB_PROFILED(h, "k_ready", k_ready_warp<<<grid_for((int64_t)na * 32, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
+                                               t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
+                                               p.max_velocity, R1max, fl));
+    }
     int* rdy = ready.alloc((size_t)na);
     const int nr_all = select_flagged(h, act, fl, rdy, na, d_count);
     if (nr_all == 0) throw Error(FOFB_ERR_INTERNAL, "priority rounds made no progress");
@@ -818,9 +929,10 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
           FOFB_PROFILED(h, "k_hop2_novel", k_hop2_novel<<<grid_for(total_v, B), B, 0, st>>>(total_v, own, vo, nF_p, ho, need, htab.p, G, v2, nov));
         }
       }
-      FOFB_PROFILED(h, "k_hop2", k_hop2<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p,
-                                      ismember.p, LLp, bb2, p, v2, mr, nml, fbatch, nM_p, pass_p, kill_target.p, alive.p,
-                                      decided.p));
+      FOFB_PROFILED(h, "k_hop2", k_hop2<<<nr, kHop2Threads, 0, st>>>(nr, rb, nv_p, nF_p, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p,
+                                      ismember.p, LLp, bb2, p, v2, mr, nml, fbatch, nm_sorted.alloc(tv), nM_p, pass_p, kill_target.p, alive.p,
+                                      decided.p, dbg_buf.p));
+      if (getenv("FOFB_DEBUG")) { unsigned long long d[8]; FOFB_CUDA(cudaMemcpy(d, dbg_buf.p, sizeof(d), cudaMemcpyDeviceToHost)); fprintf(stderr, "[hop2] round %d nr=%d total_v=%lld max_nv=%llu max_nnm=%llu sum_nnm=%llu centres_with_table=%llu max_nf=%llu\n", rounds, nr, total_v, d[0], d[1], d[2], d[3], d[4]); FOFB_CUDA(cudaMemset(dbg_buf.p, 0, sizeof(d))); }
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse
       long long* dst = ho;    // reuse
