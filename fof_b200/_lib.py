@@ -80,6 +80,7 @@ def load():
         "fofb_fof_finish_mt": (C.c_int, [vp, vp, P(i32), P(i64)]),
         "fofb_pipeline_finish_mt": (C.c_int, [vp, vp, P(i32), P(i64), P(i64)]),
         "fofb_pipeline_run": (C.c_int, [vp, P(Params), P(Matrix), dbl, dbl, dbl, vp, P(i32), P(i64), P(i64)]),
+        "fofb_transitive_labels": (C.c_int, [vp, P(Params), P(Matrix), dbl, vp, i32, P(i64), P(i64)]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
@@ -317,6 +318,16 @@ class Handle:
         self.lib.fofb_pipeline_stats(self.h, s.ctypes.data)
         return dict(zip(("galaxies_after_zcut", "candidate_centres", "stage1_clusters", "stage1_members",
                          "priority_rounds", "centres_evaluated", "stage4_clusters"), s.tolist()))
+
+    def transitive_labels(self, galaxies, params, linking_length_mpc_h):
+        """(labels int32[n] = smallest row of each row's component, number of groups, number of links)."""
+        m, keep = matrix_of(galaxies)
+        lab = np.empty(m.rows, dtype=np.int32)
+        g, l = C.c_int64(), C.c_int64()
+        self.check(self.lib.fofb_transitive_labels(self.h, C.byref(params), C.byref(m), float(linking_length_mpc_h),
+                                                   lab.ctypes.data, 0, C.byref(g), C.byref(l)))
+        del keep
+        return lab, g.value, l.value
 
     def fof_stats(self):
         r, e = C.c_int64(), C.c_int64()

@@ -7,6 +7,7 @@
 #include "fof_stage.cuh"
 #include "clean.cuh"
 #include "pipeline.cuh"
+#include "transitive.cuh"
 
 namespace fofb {
 
@@ -175,6 +176,8 @@ void fofb_destroy(fofb_handle* h) {
   h->clean = nullptr;
   delete h->pipe;
   h->pipe = nullptr;
+  delete h->trans;
+  h->trans = nullptr;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -584,6 +587,27 @@ int fofb_pipeline_stats(fofb_handle* h, int64_t* s) {
   s[0] = P.n_g; s[1] = P.m_c; s[2] = P.fof.candidates.K; s[3] = P.fof.candidates.total;
   s[4] = P.fof.rounds; s[5] = P.fof.evaluated; s[6] = P.fof.merged.K;
   return FOFB_OK;
+}
+
+// ---- transitive mode (not a reference code path) ------------------------------------------------------------
+int fofb_transitive_labels(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double linking_length_mpc_h,
+                           int32_t* labels, int32_t labels_mem, int64_t* n_groups, int64_t* n_links) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(galaxies && labels, "galaxies / labels is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->trans) h->trans = new Transitive();
+  Timed timer(h);
+  const View v = to_device(h, *galaxies, h->upload);
+  h->trans->run(h, *p, v, linking_length_mpc_h);
+  FOFB_CUDA(cudaMemcpyAsync(labels, h->trans->label.p, sizeof(int32_t) * h->trans->n_rows,
+                            labels_mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  timer.stop();
+  if (n_groups) *n_groups = h->trans->n_groups;
+  if (n_links) *n_links = h->trans->n_links;
+  return FOFB_OK;
+  FOFB_CATCH(h)
 }
 
 }  // extern "C"

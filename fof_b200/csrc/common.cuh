@@ -94,6 +94,7 @@ struct Catalog;    // catalog.cu
 struct FofState;   // fof_stage.cu
 struct CleanState; // clean.cu
 struct Pipeline;   // pipeline.cu
+struct Transitive; // transitive.cu
 
 }  // namespace fofb
 
@@ -135,6 +136,7 @@ struct fofb_handle {
   fofb::FofState* fof = nullptr;
   fofb::CleanState* clean = nullptr;
   fofb::Pipeline* pipe = nullptr;
+  fofb::Transitive* trans = nullptr;
   fofb::DBuf<unsigned char> cub_tmp;
   fofb::DBuf<double> upload;      // staging for host matrices
   fofb::DBuf<double> upload2;

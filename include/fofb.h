@@ -186,6 +186,16 @@ int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, 
  * total stage-1 members, priority rounds, centres evaluated, clusters entering stage 4 */
 int fofb_pipeline_stats(fofb_handle* h, int64_t* stats7);
 
+/* ---- transitive friends-of-friends (connected components) ------------------------------------------------------
+ * NOT a reference code path (kencx/FoF never computes connected components): the lock-free
+ * union-find mode named in BASELINE.json.  Galaxies i, j are friends iff each lies in the other's velocity window
+ * (analysis/methods.py:68-87 with p->max_velocity) and their haversine separation is within the angle of the
+ * transverse linking length [h^-1 Mpc proper] at both redshifts (analysis/methods.py:12-32).  labels[i] = smallest
+ * row index of the component of row i.  Oracle: oracle/transitive_oracle.py (scipy connected components).
+ */
+int fofb_transitive_labels(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double linking_length_mpc_h,
+                           int32_t* labels, int32_t labels_mem, int64_t* n_groups, int64_t* n_links);
+
 #ifdef __cplusplus
 }
 #endif

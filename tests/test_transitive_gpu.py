@@ -1,0 +1,39 @@
+"""Union-find transitive mode against scipy connected components on the identical predicate (SURVEY.md test 7)."""
+import numpy as np
+import pytest
+
+from fof_b200.mock import make_catalog
+from oracle import transitive_oracle as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,seed,kind,ll", [(5000, 1, "cosmos", 0.5), (50000, 2, "cosmos", 0.3), (50000, 3, "wide", 2.0),
+                                             (200000, 4, "cosmos", 0.4), (24000, 5, "dense", 0.6)])
+def test_labels_equal_connected_components(lib, n, seed, kind, ll):
+    from fof_b200 import transitive
+    arr = make_catalog(n, seed=seed, kind=kind, as_frame=False)
+    want, n_links = T.labels(arr, ll)
+    got, n_groups, links = transitive.friends_of_friends(arr, linking_length=ll)
+    assert np.array_equal(got, want)
+    assert links == n_links
+    assert n_groups == len(np.unique(want))
+    # canonical form: the label is the smallest member, and every root labels itself
+    assert (got <= np.arange(n)).all() and (got[got] == got).all()
+
+
+def test_percolating_blobs_deep_chains(lib):
+    """configs[4]: a few giant percolating groups -- deep union-find chains."""
+    from fof_b200 import transitive
+    arr = make_catalog(20000, seed=9, kind="dense", n_blobs=6, as_frame=False)
+    got, n_groups, links = transitive.friends_of_friends(arr, linking_length=1.0)
+    uniq, counts = np.unique(got, return_counts=True)
+    assert counts.max() > 1500  # the blobs percolate
+    want, _ = T.labels(arr, 1.0)
+    assert np.array_equal(got, want)
+    # the same at a size the oracle cannot reach: size-independent invariants only
+    big = make_catalog(2000000, seed=10, kind="dense", n_blobs=12, as_frame=False)
+    lab, n_groups, links = transitive.friends_of_friends(big, linking_length=1.0)
+    assert (lab <= np.arange(len(big))).all() and (lab[lab] == lab).all()
+    assert n_groups == len(np.unique(lab))
+    assert np.unique(lab, return_counts=True)[1].max() > 50000
