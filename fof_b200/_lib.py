@@ -81,6 +81,16 @@ def load():
         "fofb_pipeline_finish_mt": (C.c_int, [vp, vp, P(i32), P(i64), P(i64)]),
         "fofb_pipeline_run": (C.c_int, [vp, P(Params), P(Matrix), dbl, dbl, dbl, vp, P(i32), P(i64), P(i64)]),
         "fofb_transitive_labels": (C.c_int, [vp, P(Params), P(Matrix), dbl, vp, i32, P(i64), P(i64)]),
+        "fofb_dist_begin": (C.c_int, [vp, P(Params), P(Matrix), vp, vp, vp, P(i64), P(i64)]),
+        "fofb_dist_local_inputs": (C.c_int, [vp, vp, vp, vp, vp]),
+        "fofb_dist_prepare": (C.c_int, [vp, vp, i64, vp, vp]),
+        "fofb_dist_round_evaluate": (C.c_int, [vp]),
+        "fofb_dist_state": (C.c_int, [vp, vp, vp, i32]),
+        "fofb_dist_round_advance": (C.c_int, [vp, P(i64)]),
+        "fofb_dist_finalize": (C.c_int, [vp, P(i64), P(i64)]),
+        "fofb_dist_local_clusters": (C.c_int, [vp, vp, vp, vp]),
+        "fofb_dist_overlap": (C.c_int, [vp, i64, vp, vp, vp, vp]),
+        "fofb_dist_set_merged": (C.c_int, [vp, vp, vp, i64, vp]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
@@ -232,6 +242,14 @@ class Handle:
         self.check(self.lib.fofb_pipeline_finish_mt(self.h, key.ctypes.data, C.byref(pos), C.byref(k), C.byref(t)))
         np.random.set_state(("MT19937", key, pos.value, has_gauss, cached))
         return k.value, t.value
+
+    def pipeline_finish_mt(self, key, pos):
+        """Like pipeline_finish_np_random with an explicit MT19937 state; returns (K, total, key, pos)."""
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        cpos = C.c_int32(int(pos))
+        k, t = C.c_int64(), C.c_int64()
+        self.check(self.lib.fofb_pipeline_finish_mt(self.h, key.ctypes.data, C.byref(cpos), C.byref(k), C.byref(t)))
+        return k.value, t.value, key, cpos.value
 
     def pipeline_run_np_random(self, galaxies, params, zmin, zmax_gal, zmax_cen):
         """The whole path in one C call; np.random's MT19937 state is consumed on the device and written back."""

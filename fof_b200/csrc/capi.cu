@@ -10,6 +10,12 @@
 #include "transitive.cuh"
 
 namespace fofb {
+void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total,
+                          const double* ids, int* keep_out);
+void fof_set_merged(fofb_handle* h, FofState& S, const int* keep_local);
+}
+
+namespace fofb {
 
 struct Stage0Holder {
   Catalog cat;
@@ -587,6 +593,214 @@ int fofb_pipeline_stats(fofb_handle* h, int64_t* s) {
   s[0] = P.n_g; s[1] = P.m_c; s[2] = P.fof.candidates.K; s[3] = P.fof.candidates.total;
   s[4] = P.fof.rounds; s[5] = P.fof.evaluated; s[6] = P.fof.merged.K;
   return FOFB_OK;
+}
+
+// ---- redshift-slab decomposition: the steps a multi-process driver interleaves with its collectives ------------
+static Pipeline& dist_pipe(fofb_handle* h) {
+  if (!h->pipe) throw fofb::Error(FOFB_ERR_STATE, "no distributed run in progress: call fofb_dist_begin first");
+  return *h->pipe;
+}
+
+int fofb_dist_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, const double* zcut3,
+                    const double* z_valid2, const double* z_own2, int64_t* n_fof_rows, int64_t* n_local_centres) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(galaxies && zcut3 && z_valid2 && z_own2, "fofb_dist_begin: null argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->pipe) h->pipe = new Pipeline();
+  Timed timer(h);
+  const View raw = to_device(h, *galaxies, h->upload);
+  h->pipe->begin_dist(h, *p, raw, zcut3[0], zcut3[1], zcut3[2], z_valid2[0], z_valid2[1], z_own2[0], z_own2[1]);
+  timer.stop();
+  if (n_fof_rows) *n_fof_rows = h->pipe->n_g;
+  if (n_local_centres) *n_local_centres = h->pipe->m_c;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_local_inputs(fofb_handle* h, double* centre_rows, int32_t* centre_src_row, int32_t* fof_src_row, double* bbox4) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  if (centre_rows && P.m_c) FOFB_CUDA(cudaMemcpyAsync(centre_rows, P.c_rows.p, sizeof(double) * 8 * P.m_c, cudaMemcpyDeviceToHost, st));
+  if (centre_src_row && P.m_c) FOFB_CUDA(cudaMemcpyAsync(centre_src_row, P.c_src.p, sizeof(int32_t) * P.m_c, cudaMemcpyDeviceToHost, st));
+  if (fof_src_row && P.n_g) FOFB_CUDA(cudaMemcpyAsync(fof_src_row, P.g_src.p, sizeof(int32_t) * P.n_g, cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  (void)bbox4;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_prepare(fofb_handle* h, const double* centres, int64_t n_centres, const uint8_t* owned, double* local_bbox4) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(centres && owned && n_centres >= 0 && n_centres < (1ll << 31), "fofb_dist_prepare: bad argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  Timed timer(h);
+  const size_t m = (size_t)n_centres;
+  double* c = P.cn_glob.alloc(std::max<size_t>(m, 1) * 8);
+  unsigned char* o = P.owned.alloc(std::max<size_t>(m, 1));
+  FOFB_CUDA(cudaMemcpyAsync(c, centres, sizeof(double) * 8 * m, cudaMemcpyDefault, st));
+  FOFB_CUDA(cudaMemcpyAsync(o, owned, m, cudaMemcpyDefault, st));
+  View Cv;
+  Cv.data = c; Cv.rows = n_centres; Cv.cols = 8; Cv.rs = 8; Cv.cs = 1;
+  P.fof.prepare(h, P.params, P.Gv, Cv, o);
+  timer.stop();
+  if (local_bbox4) {  // bounding box of this process's FoF() rows; the driver reduces it over processes
+    local_bbox4[0] = P.fof.cat.gbox.ra_min; local_bbox4[1] = P.fof.cat.gbox.ra_max;
+    local_bbox4[2] = P.fof.cat.gbox.dec_min; local_bbox4[3] = P.fof.cat.gbox.dec_max;
+  }
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_round_evaluate(fofb_handle* h) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  P.fof.round_evaluate(h);
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+/* direction 0: library -> caller buffers (device pointers, n_centres bytes each); 1: caller -> library */
+int fofb_dist_state(fofb_handle* h, uint8_t* alive, uint8_t* decided, int32_t direction) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(alive && decided, "fofb_dist_state: null buffer");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  const size_t m = (size_t)P.fof.m;
+  if (m) {
+    if (direction == 0) {
+      FOFB_CUDA(cudaMemcpyAsync(alive, P.fof.alive.p, m, cudaMemcpyDeviceToDevice, h->stream));
+      FOFB_CUDA(cudaMemcpyAsync(decided, P.fof.decided.p, m, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+      FOFB_CUDA(cudaMemcpyAsync(P.fof.alive.p, alive, m, cudaMemcpyDeviceToDevice, h->stream));
+      FOFB_CUDA(cudaMemcpyAsync(P.fof.decided.p, decided, m, cudaMemcpyDeviceToDevice, h->stream));
+    }
+  }
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_round_advance(fofb_handle* h, int64_t* n_active) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  P.fof.round_advance(h);
+  if (n_active) *n_active = P.fof.na;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_finalize(fofb_handle* h, int64_t* n_clusters, int64_t* n_members) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  P.fof.finalize(h);
+  if (n_clusters) *n_clusters = P.fof.candidates.K;
+  if (n_members) *n_members = P.fof.candidates.K ? P.fof.candidates.total : 0;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+/* local stage-1 clusters: centre[K] = index into the all-process centre table, offsets[K+1], ids[total] = column 6 */
+int fofb_dist_local_clusters(fofb_handle* h, int32_t* centre, int64_t* offsets, double* ids) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const ClusterList& L = P.fof.candidates;
+  if (L.K == 0) {
+    if (offsets) offsets[0] = 0;
+    return FOFB_OK;
+  }
+  if (centre) FOFB_CUDA(cudaMemcpyAsync(centre, L.centre.p, sizeof(int32_t) * L.K, cudaMemcpyDeviceToHost, st));
+  if (offsets) FOFB_CUDA(cudaMemcpyAsync(offsets, L.off.p, sizeof(int64_t) * (L.K + 1), cudaMemcpyDeviceToHost, st));
+  if (ids) {
+    std::vector<int32_t> rows(L.total);
+    FOFB_CUDA(cudaMemcpyAsync(rows.data(), L.rows.p, sizeof(int32_t) * L.total, cudaMemcpyDeviceToHost, st));
+    std::vector<double> col6(P.n_g);
+    FOFB_CUDA(cudaMemcpy2DAsync(col6.data(), sizeof(double), P.g_rows.p + 6, sizeof(double) * 8, sizeof(double), P.n_g,
+                                cudaMemcpyDeviceToHost, st));
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    for (long long t = 0; t < L.total; ++t) ids[t] = col6[rows[t]];
+  }
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+/* stage 2 on the all-process cluster list (host arrays, ordered by centre index); keep[K] out */
+int fofb_dist_overlap(fofb_handle* h, int64_t K, const int32_t* centre, const int64_t* offsets, const double* ids, int32_t* keep) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(K >= 0 && K < (1ll << 31), "fofb_dist_overlap: bad K");
+  if (K == 0) return FOFB_OK;
+  FOFB_REQUIRE(centre && offsets && ids && keep, "fofb_dist_overlap: null argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const long long total = offsets[K];
+  int* c = P.ext_centre.alloc((size_t)K);
+  long long* o = P.ext_off.alloc((size_t)K + 1);
+  double* d = P.ext_ids.alloc((size_t)std::max<long long>(total, 1));
+  int* kd = P.keep_dev.alloc((size_t)K);
+  FOFB_CUDA(cudaMemcpyAsync(c, centre, sizeof(int32_t) * K, cudaMemcpyHostToDevice, st));
+  FOFB_CUDA(cudaMemcpyAsync(o, offsets, sizeof(int64_t) * (K + 1), cudaMemcpyHostToDevice, st));
+  FOFB_CUDA(cudaMemcpyAsync(d, ids, sizeof(double) * total, cudaMemcpyHostToDevice, st));
+  fof_overlap_external(h, P.fof, (int)K, c, o, total, d, kd);
+  FOFB_CUDA(cudaMemcpyAsync(keep, kd, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+/* keep_local[K_local]; global_index[number kept] = position of each kept local cluster in the all-process merged list */
+int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_t* global_index, int64_t n_global_merged,
+                         const double* global_bbox4) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int K = P.fof.candidates.K;
+  int kept = 0;
+  if (K > 0) {
+    FOFB_REQUIRE(keep_local, "fofb_dist_set_merged: null flags");
+    int* kd = P.keep_dev.alloc((size_t)K);
+    FOFB_CUDA(cudaMemcpyAsync(kd, keep_local, sizeof(int32_t) * K, cudaMemcpyHostToDevice, st));
+    fof_set_merged(h, P.fof, kd);
+    kept = P.fof.merged.K;
+  } else {
+    P.fof.merged.K = 0;
+    P.fof.merged.total = 0;
+  }
+  if (kept > 0) {
+    FOFB_REQUIRE(global_index, "fofb_dist_set_merged: null indices");
+    FOFB_CUDA(cudaMemcpyAsync(P.fof.merged_gidx.alloc(kept), global_index, sizeof(int32_t) * kept, cudaMemcpyHostToDevice, st));
+  }
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  P.fof.K_glob_merged = n_global_merged;
+  FOFB_REQUIRE(global_bbox4, "fofb_dist_set_merged: null bounding box");
+  P.fof.have_global_bbox = true;
+  P.fof.global_bbox = BBox{global_bbox4[0], global_bbox4[1], global_bbox4[2], global_bbox4[3]};
+  P.fof.ran = true;
+  P.began = true;
+  return FOFB_OK;
+  FOFB_CATCH(h)
 }
 
 // ---- transitive mode (not a reference code path) ------------------------------------------------------------

@@ -59,6 +59,11 @@ __global__ void k_iota_i32(int n, int* out) {
   if (i < n) out[i] = i;
 }
 
+__global__ void k_gather_flag(int m, const int* idx, const unsigned char* owned, int* flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m) flag[t] = owned[idx[t]] ? 1 : 0;
+}
+
 __global__ void k_cos_row(int n, const double* dec, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = cos(__dmul_rn(dec[i], kDeg2Rad));
@@ -716,8 +721,23 @@ static void segmented_sort(fofb_handle* h, const unsigned long long* in, unsigne
 void fof_overlap_and_bcg(fofb_handle* h, FofState& S);  // overlap.cu
 
 void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const View& Cn_in) {
+  prepare(h, p, G_in, Cn_in, nullptr);
+  while (na > 0) {
+    round_evaluate(h);
+    round_advance(h);
+  }
+  finalize(h);
+  fof_overlap_and_bcg(h, *this);
+  ran = true;
+}
+
+// Everything before the priority rounds.  `owned` (device, one byte per centre, may be null = all): the centres this
+// process evaluates; the others take part only as potential blockers whose state arrives from their owner.
+void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, const View& Cn_in, const unsigned char* owned) {
   cudaStream_t st = h->stream;
   ran = finished = false;
+  distributed = owned != nullptr;
+  na = 0;
   params = p;
   G = G_in;
   Cn = Cn_in;
@@ -738,10 +758,7 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
   pool_K = 0;
   rounds = 0;
   evaluated = 0;
-  if (m == 0) {
-    ran = true;
-    return;
-  }
+  if (m == 0) return;
   const size_t mm = (size_t)m;
   FOFB_PROFILED(h, "k_centre_prep", k_centre_prep<<<grid_for(m, B), B, 0, st>>>(Cn, m, cv, cosmo, p.max_velocity, p.virial_radius, p.count_radius,
                                               c_ra.alloc(mm), c_dec.alloc(mm), c_cos.alloc(mm), c_z.alloc(mm),
@@ -833,21 +850,39 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
     k_gather_d<<<grid_for(m, B), B, 0, st>>>(m, vb, c_z.p, cc_z.alloc(mm));
     FOFB_LAUNCH_CHECK(h);
   }
-  CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p, cc_z.p};
-  CellListView clbig = big.view();
-
-  // ---- priority rounds ---------------------------------------------------------------------------
+  // ---- priority rounds: initial active list -------------------------------------------------------
   int* act = active_a.alloc(mm);
-  int* act_next = active_b.alloc(mm);
+  active_b.alloc(mm);
+  act_in_a = true;
   // the active list walks the centre cell list, so a warp's 32 centres share cells and redshift neighbourhoods
-  FOFB_CUDA(cudaMemcpyAsync(act, cc_idx.p, sizeof(int) * mm, cudaMemcpyDeviceToDevice, st));
-  int na = m;
-  int* d_count = reinterpret_cast<int*>(scal_p + 8);
+  if (!owned) {
+    FOFB_CUDA(cudaMemcpyAsync(act, cc_idx.p, sizeof(int) * mm, cudaMemcpyDeviceToDevice, st));
+    na = m;
+  } else {
+    int* fl = flags.alloc(mm);
+    k_gather_flag<<<grid_for(m, B), B, 0, st>>>(m, cc_idx.p, owned, fl);
+    FOFB_LAUNCH_CHECK(h);
+    na = select_flagged(h, cc_idx.p, fl, act, m, reinterpret_cast<int*>(scal_p + 8));
+  }
   FOFB_CUDA(cudaMemsetAsync(dbg_buf.alloc(8), 0, 64, st));
   pool_centre.alloc(mm);
   pool_off.alloc(mm);
   pool_len.alloc(mm);
-  while (na > 0) {
+}
+
+// One round: find the active centres no alive, undecided predecessor can still claim, and evaluate them.
+void FofState::round_evaluate(fofb_handle* h) {
+  cudaStream_t st = h->stream;
+  const fofb_params& p = params;
+  const int B = 256;
+  if (na <= 0) return;
+  const Cosmo cosmo = device_cosmo(h, p);
+  CatalogView cv = cat.view();
+  CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p, cc_z.p};
+  CellListView clbig = big.view();
+  int* act = act_in_a ? active_a.p : active_b.p;
+  int* d_count = reinterpret_cast<int*>(scal.p + 8);
+  {
     ++rounds;
     int* fl = flags.alloc((size_t)na);
     if (na > 8192) {
@@ -861,7 +896,7 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
     }
     int* rdy = ready.alloc((size_t)na);
     const int nr_all = select_flagged(h, act, fl, rdy, na, d_count);
-    if (nr_all == 0) throw Error(FOFB_ERR_INTERNAL, "priority rounds made no progress");
+    if (nr_all == 0 && !distributed) throw Error(FOFB_ERR_INTERNAL, "priority rounds made no progress");
     // evaluate the ready centres in bounded batches
     const int kBatch = 1 << 16;
     for (int b0 = 0; b0 < nr_all; b0 += kBatch) {
@@ -961,13 +996,27 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
         pool_K += (int)newK;
       }
     }
-    // next active list
-    k_still_active<<<grid_for(na, B), B, 0, st>>>(na, act, alive.p, decided.p, fl);
-    FOFB_LAUNCH_CHECK(h);
-    na = select_flagged(h, act, fl, act_next, na, d_count);
-    std::swap(act, act_next);
   }
+}
 
+// After the round's kills (and, when distributed, after the state arrays were merged across processes).
+void FofState::round_advance(fofb_handle* h) {
+  cudaStream_t st = h->stream;
+  if (na <= 0) return;
+  int* act = act_in_a ? active_a.p : active_b.p;
+  int* act_next = act_in_a ? active_b.p : active_a.p;
+  int* fl = flags.alloc((size_t)na);
+  k_still_active<<<grid_for(na, 256), 256, 0, st>>>(na, act, alive.p, decided.p, fl);
+  FOFB_LAUNCH_CHECK(h);
+  na = select_flagged(h, act, fl, act_next, na, reinterpret_cast<int*>(scal.p + 8));
+  act_in_a = !act_in_a;
+}
+
+void FofState::finalize(fofb_handle* h) {
+  cudaStream_t st = h->stream;
+  const int B = 256;
+  const size_t mm = (size_t)std::max(m, 1);
+  size_t bytes = 0;
   // ---- candidates in priority order (= the order the sequential loop appends them, fof.py:232) ------
   candidates.K = pool_K;
   candidates.total = pool_used;
@@ -992,8 +1041,6 @@ void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const
                                                                        candidates.rows.alloc((size_t)std::max<long long>(tot, 1)));
     FOFB_LAUNCH_CHECK(h);
   }
-  fof_overlap_and_bcg(h, *this);
-  ran = true;
 }
 
 }  // namespace fofb

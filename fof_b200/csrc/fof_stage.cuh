@@ -65,6 +65,20 @@ struct FofState {
   int64_t evaluated = 0;
 
   void run(fofb_handle* h, const fofb_params& p, const View& G, const View& Cn);
+  // the same in steps (the distributed driver merges alive/decided across processes between evaluate and advance)
+  void prepare(fofb_handle* h, const fofb_params& p, const View& G, const View& Cn, const unsigned char* owned);
+  void round_evaluate(fofb_handle* h);
+  void round_advance(fofb_handle* h);
+  void finalize(fofb_handle* h);
+  void* overlap_scratch = nullptr;          // OverlapScratch (overlap.cu)
+  void (*overlap_scratch_free)(void*) = nullptr;
+  ~FofState() {
+    if (overlap_scratch && overlap_scratch_free) overlap_scratch_free(overlap_scratch);
+    if (rng_done) cudaEventDestroy(rng_done);
+    if (rng_stream) cudaStreamDestroy(rng_stream);
+  }
+  bool distributed = false, act_in_a = true;
+  int na = 0;
   void finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int mem);
   // u: K x 2 x n_random samples of [0, 1) (per cluster the RA block, then the Dec block)
   void finish_unit(fofb_handle* h, const double* u, int mem);
@@ -80,6 +94,11 @@ struct FofState {
   long long mt_head = 0, mt_blocks = 0;
   unsigned mt_key_host[624];
   int last_K = 0;
+  // distributed runs: index of each local merged cluster in the all-process list, and that list's length
+  DBuf<int> merged_gidx;
+  long long K_glob_merged = -1;
+  bool have_global_bbox = false;
+  BBox global_bbox{};
 };
 
 }  // namespace fofb

@@ -318,23 +318,28 @@ __global__ void k_bcg_check(int K, const int* centre, const long long* off, cons
   if (__any_sync(0xffffffffu, fire) && lane == 0) atomicAdd(fired, 1);
 }
 
-static OverlapScratch& scratch() {
-  static OverlapScratch* s = new OverlapScratch();  // device buffers live until process exit
-  return *s;
+void fof_bcg_check(fofb_handle* h, FofState& S);
+
+static OverlapScratch& scratch(FofState& S) {
+  if (!S.overlap_scratch) {
+    S.overlap_scratch = new OverlapScratch();
+    S.overlap_scratch_free = [](void* p) { delete static_cast<OverlapScratch*>(p); };
+  }
+  return *static_cast<OverlapScratch*>(S.overlap_scratch);
 }
 
-void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
+// Stage 2 on an arbitrary cluster list (centre index per cluster, CSR offsets, member ids): returns a device array of
+// K keep flags (non-zero = survives the contests).  `ext_ids` == nullptr: ids are column 6 of S.G at `rows`.
+static int* overlap_keep_flags(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total_members,
+                               const int* rows, const double* ext_ids) {
   cudaStream_t st = h->stream;
-  OverlapScratch& sc = scratch();
+  OverlapScratch& sc = scratch(S);
   const int B = 256;
-  const int K = S.candidates.K;
-  S.merged.K = S.bcg.K = 0;
-  S.merged.total = S.bcg.total = 0;
-  if (K == 0) return;
+  if (K == 0) return nullptr;
   const fofb_params& p = S.params;
   size_t bytes = 0;
   // clusters sorted by centre redshift -> velocity windows over the candidate list
-  k_cluster_z<<<grid_for(K, B), B, 0, st>>>(K, S.candidates.centre.p, S.c_z.p, S.c_id.p, sc.kz.alloc(K), sc.kidx.alloc(K),
+  k_cluster_z<<<grid_for(K, B), B, 0, st>>>(K, centre, S.c_z.p, S.c_id.p, sc.kz.alloc(K), sc.kidx.alloc(K),
                                             sc.idk.alloc(K), sc.idv.alloc(K));
   FOFB_LAUNCH_CHECK(h);
   sc.kz_sorted.alloc(K); sc.kidx_sorted.alloc(K); sc.idk_sorted.alloc(K); sc.idv_sorted.alloc(K);
@@ -347,7 +352,7 @@ void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
   // events
   const int wblocks = grid_for((int64_t)K * 32, 128);
   int* ecount = sc.ecount.alloc(K);
-  k_overlap_events<0><<<wblocks, 128, 0, st>>>(K, S.candidates.centre.p, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
+  k_overlap_events<0><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
                                                S.c_cos.p, S.c_z.p, S.c_thvir.p, p.max_velocity, p.grid_cells, ecount, nullptr, nullptr);
   FOFB_LAUNCH_CHECK(h);
   long long* elen = sc.elen.alloc((size_t)K + 1);
@@ -361,27 +366,31 @@ void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
   if (E > 0) {
     unsigned long long* ekey = sc.ekey.alloc((size_t)E);
     unsigned long long* ekey_s = sc.ekey_sorted.alloc((size_t)E);
-    k_overlap_events<1><<<wblocks, 128, 0, st>>>(K, S.candidates.centre.p, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
+    k_overlap_events<1><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
                                                  S.c_cos.p, S.c_z.p, S.c_thvir.p, p.max_velocity, p.grid_cells, ecount, eoff, ekey);
     FOFB_LAUNCH_CHECK(h);
     FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
     FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
     count_launch(h, 4);
     // sorted member ids per candidate cluster
-    const long long total = S.candidates.total;
-    double* ids = sc.ids.alloc((size_t)total);
+    const long long total = total_members;
+    const double* ids = ext_ids;
+    if (!ids) {
+      double* own = sc.ids.alloc((size_t)total);
+      k_member_ids<<<grid_for(total, B), B, 0, st>>>(total, rows, S.G, own);
+      FOFB_LAUNCH_CHECK(h);
+      ids = own;
+    }
     double* ids_s = sc.ids_sorted.alloc((size_t)total);
-    k_member_ids<<<grid_for(total, B), B, 0, st>>>(total, S.candidates.rows.p, S.G, ids);
-    FOFB_LAUNCH_CHECK(h);
-    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ids, ids_s, total, K, S.candidates.off.p, S.candidates.off.p + 1, st));
-    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ids, ids_s, total, K, S.candidates.off.p, S.candidates.off.p + 1, st));
+    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ids, ids_s, total, K, off, off + 1, st));
+    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ids, ids_s, total, K, off, off + 1, st));
     count_launch(h, 4);
     int* ev_a = sc.ev_a.alloc((size_t)E);
     int* ev_c = sc.ev_c.alloc((size_t)E);
     int* ev_l = sc.ev_loser.alloc((size_t)E);
     int* state = sc.state.p;
-    FOFB_PROFILED(h, "k_event_static", k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, S.candidates.centre.p, S.c_id.p,
-                                                          S.c_N.p, S.c_mag.p, S.candidates.off.p, ids_s, ev_a, ev_c, ev_l, state));
+    FOFB_PROFILED(h, "k_event_static", k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, centre, S.c_id.p,
+                                                          S.c_N.p, S.c_mag.p, off, ids_s, ev_a, ev_c, ev_l, state));
     // per-cluster lists of the events it would lose, in event order
     unsigned long long* lkey = sc.lkey.alloc((size_t)E);
     unsigned long long* lkey_s = sc.lkey_sorted.alloc((size_t)E);
@@ -406,8 +415,44 @@ void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
   } else {
     FOFB_CUDA(cudaMemsetAsync(keep_flags, 1, sizeof(int) * K, st));  // any non-zero value keeps
   }
-  sublist(h, S.candidates, keep_flags, S.merged, sc);
+  return keep_flags;
+}
 
+void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
+  cudaStream_t st = h->stream;
+  OverlapScratch& sc = scratch(S);
+  const fofb_params& p = S.params;
+  const int K = S.candidates.K;
+  S.merged.K = S.bcg.K = 0;
+  S.merged.total = S.bcg.total = 0;
+  if (K == 0) return;
+  int* keep_flags = overlap_keep_flags(h, S, K, S.candidates.centre.p, S.candidates.off.p, S.candidates.total, S.candidates.rows.p, nullptr);
+  sublist(h, S.candidates, keep_flags, S.merged, sc);
+  fof_bcg_check(h, S);
+}
+
+// Stage 2 for a cluster list assembled from several processes (device arrays); keep_out: K int32 flags (device).
+void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total,
+                          const double* ids, int* keep_out) {
+  if (K == 0) return;
+  int* keep = overlap_keep_flags(h, S, K, centre, off, total, nullptr, ids);
+  FOFB_CUDA(cudaMemcpyAsync(keep_out, keep, sizeof(int) * K, cudaMemcpyDeviceToDevice, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// merged := the local candidates whose flag is set (flags on the device, one per local candidate)
+void fof_set_merged(fofb_handle* h, FofState& S, const int* keep_local) {
+  S.merged.K = S.bcg.K = 0;
+  S.merged.total = S.bcg.total = 0;
+  if (S.candidates.K == 0) return;
+  sublist(h, S.candidates, keep_local, S.merged, scratch(S));
+  fof_bcg_check(h, S);
+}
+
+void fof_bcg_check(fofb_handle* h, FofState& S) {
+  cudaStream_t st = h->stream;
+  OverlapScratch& sc = scratch(S);
+  const fofb_params& p = S.params;
   // stage 3: BCG recentring (fof.py:318-371).  Under the pipeline's column layout the replacement
   // test compares |z_lower| with |RMag| and never fires; the device path verifies that.
   if (S.merged.K > 0) {
@@ -643,11 +688,12 @@ __global__ void k_mt_untemper(const unsigned* words, unsigned* key) {
   key[k] = y;
 }
 
-__global__ void k_points_from_words(long long total, int npts, const unsigned* w, long long head, double ra_lo,
-                                    double ra_range, double dec_lo, double dec_range, double* ra, double* dec) {
+__global__ void k_points_from_words(long long total, int npts, const unsigned* w, long long head, const int* gidx,
+                                    double ra_lo, double ra_range, double dec_lo, double dec_range, double* ra, double* dec) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= total) return;
-  const long long k = q / npts, i = q % npts;
+  // cluster q / npts consumes block k of the stream: its own index, or its index in the global (all-process) list
+  const long long k = gidx ? gidx[q / npts] : q / npts, i = q % npts;
   const long long ia = ((2 * k) * npts + i) * 2, id = ((2 * k + 1) * npts + i) * 2;
   auto word = [&](long long t) -> unsigned { return t < head ? w[t] : w[624 + (t - head)]; };
   const double ua = ((double)(word(ia) >> 5) * 67108864.0 + (double)(word(ia + 1) >> 6)) / 9007199254740992.0;
@@ -682,7 +728,7 @@ void FofState::mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, lo
 void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
   if (!ran) throw Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
   const int K = merged.K;
-  if (K == 0) {
+  if (K == 0 && K_glob_merged <= 0) {
     mt_prefetched = false;
     finish(h, nullptr, nullptr, 1);
     return;
@@ -691,10 +737,11 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
   cudaStream_t st = h->stream;
   const int npts = params.n_random;
   const long long total = (long long)K * npts;
-  const long long W = total * 4;  // 2 coordinates x 2 words
+  const long long K_stream = K_glob_merged >= 0 ? K_glob_merged : K;  // distributed: the stream covers every process's clusters
+  const long long W = K_stream * npts * 4;  // 2 coordinates x 2 words
   if (!mt_prefetched || mt_pos0 != *pos_host || std::memcmp(mt_key_host, key_host, sizeof(unsigned) * 624) != 0) {
     params_n_random_hint = npts;
-    mt_prefetch(h, key_host, *pos_host, K);
+    mt_prefetch(h, key_host, *pos_host, K_stream);
   }
   FOFB_CUDA(cudaStreamWaitEvent(st, rng_done, 0));
   const long long need_blocks = W > mt_head ? (W - mt_head + 623) / 624 : 0;
@@ -710,10 +757,16 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
     mt_blocks = need_blocks;
   }
   double* pts = unit_pts.alloc((size_t)total * 2);
-  const double ra_range = cat.gbox.ra_max - cat.gbox.ra_min, dec_range = cat.gbox.dec_max - cat.gbox.dec_min;
-  k_points_from_words<<<grid_for(total, 256), 256, 0, st>>>(total, npts, mt_words.p, mt_head, cat.gbox.ra_min, ra_range,
-                                                            cat.gbox.dec_min, dec_range, pts, pts + total);
-  FOFB_LAUNCH_CHECK(h);
+  // the box helper.py:197-202 draws from: min/max of galaxy_data (all processes' FoF() rows when distributed)
+  const BBox pb = have_global_bbox ? global_bbox : cat.gbox;
+  const double ra_range = pb.ra_max - pb.ra_min, dec_range = pb.dec_max - pb.dec_min;
+  const double ra_lo = pb.ra_min, dec_lo = pb.dec_min;
+  if (total > 0) {
+    k_points_from_words<<<grid_for(total, 256), 256, 0, st>>>(total, npts, mt_words.p, mt_head,
+                                                              K_glob_merged >= 0 ? merged_gidx.p : nullptr, ra_lo, ra_range,
+                                                              dec_lo, dec_range, pts, pts + total);
+    FOFB_LAUNCH_CHECK(h);
+  }
   // the generator state after exactly W words
   if (W <= mt_head) {
     *pos_host += (int)W;
@@ -727,7 +780,8 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
     *pos_host = (int)(rem - last * 624);
   }
   mt_prefetched = false;
-  finish(h, pts, pts + total, 1);
+  if (K > 0) finish(h, pts, pts + total, 1);
+  else finish(h, nullptr, nullptr, 1);
   FOFB_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -759,7 +813,7 @@ void FofState::finish_unit(fofb_handle* h, const double* u, int mem) {
 
 void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_dec, int mem) {
   cudaStream_t st = h->stream;
-  OverlapScratch& sc = scratch();
+  OverlapScratch& sc = scratch(*this);
   const fofb_params& p = params;
   if (!ran) throw Error(FOFB_ERR_STATE, "fofb_fof_finish called before fofb_fof_run");
   final_.K = 0;
@@ -781,6 +835,14 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   }
   const int B = 256;
   const int wblocks = grid_for((int64_t)K * 32, 128);
+  if (getenv("FOFB_DEBUG")) {
+    double a[4], b[4]; int c0 = 0;
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    FOFB_CUDA(cudaMemcpy(a, rra, sizeof(a), cudaMemcpyDeviceToHost));
+    FOFB_CUDA(cudaMemcpy(b, rdec, sizeof(b), cudaMemcpyDeviceToHost));
+    FOFB_CUDA(cudaMemcpy(&c0, merged.centre.p, sizeof(int), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[finish] K=%d first centre idx %d points ra %.12f %.12f dec %.12f %.12f gidx? %lld\n", K, c0, a[0], a[1], b[0], b[1], K_glob_merged);
+  }
   int* N_own = merged.N.alloc(K);
   double* D = merged.D.alloc(K);
   FOFB_PROFILED(h, "k_own_count", k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,

@@ -44,11 +44,11 @@ __global__ void k_zflag(int n, const double* z, double zmin, double zmax, int* f
   iota[i] = i;
 }
 
-__global__ void k_cand_flag(int m, const int* cand_rows, const double* z, double zmin, double zmax, int* flag) {
+__global__ void k_cand_flag(int m, const int* cand_rows, const double* z, double zmin, double zmax, double zlt, int* flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const double v = z[cand_rows[i]];
-  flag[i] = (v >= zmin && v <= zmax) ? 1 : 0;
+  flag[i] = (v >= zmin && v <= zmax && v < zlt) ? 1 : 0;
 }
 
 // main_arr rows (fof.py:61): the input columns plus N(0.5), written row-major with 8 columns
@@ -107,7 +107,8 @@ __global__ void k_final_meta(int K2, const int* sel, const int* centre, const in
   if (k >= K2) return;
   const int s = sel[k];
   const int c = centre[s];
-  out_centre_row[k] = c < m ? cen_src[c] : g_src[c - m];
+  // distributed runs (cen_src == nullptr) report the index into the all-process centre table instead of a row
+  out_centre_row[k] = !cen_src ? c : (c < m ? cen_src[c] : g_src[c - m]);
   out_N[k] = (double)N[s];
   out_D[k] = D[s];
 }
@@ -124,6 +125,30 @@ __global__ void k_max_len(int K, const long long* off, int* out) {
 
 void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen,
                      const unsigned* mt_key, int mt_pos) {
+  dist = false;
+  fof.K_glob_merged = -1;
+  fof.have_global_bbox = false;
+  stage0_and_inputs(h, p, raw, zmin, zmax_gal, zmin, zmax_cen, mt_key, mt_pos);
+  fof.run(h, p, Gv, Cv);
+  fof.last_K = fof.merged.K;
+  began = true;
+}
+
+// Distributed variant: this process holds a redshift slab plus halos.  Rows with z in [valid_lo, valid_hi] have
+// their whole velocity window on this process (so N(0.5) is exact for them and they may enter FoF()); candidate
+// centres with own_lo <= z < own_hi are the ones this process evaluates.
+void Pipeline::begin_dist(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen,
+                          double valid_lo, double valid_hi, double own_lo, double own_hi) {
+  dist = true;
+  fof.K_glob_merged = -1;
+  fof.have_global_bbox = false;
+  own_hi_exclusive = own_hi;
+  stage0_and_inputs(h, p, raw, fmax(zmin, valid_lo), fmin(zmax_gal, valid_hi), fmax(zmin, own_lo), zmax_cen, nullptr, 0);
+  began = false;  // becomes true after the distributed rounds
+}
+
+void Pipeline::stage0_and_inputs(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal,
+                                 double czmin, double zmax_cen, const unsigned* mt_key, int mt_pos) {
   cudaStream_t st = h->stream;
   const int B = 256;
   began = finished = false;
@@ -160,7 +185,7 @@ void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, doub
   int* csrc = c_src.alloc(std::max(m0, 1));
   if (m0 > 0) {
     int* cflag = flags.alloc(std::max(n, m0));
-    k_cand_flag<<<grid_for(m0, B), B, 0, st>>>(m0, s0.cand_rows.p, cat.z_row.p, zmin, zmax_cen, cflag);
+    k_cand_flag<<<grid_for(m0, B), B, 0, st>>>(m0, s0.cand_rows.p, cat.z_row.p, czmin, zmax_cen, dist ? own_hi_exclusive : INFINITY, cflag);
     FOFB_LAUNCH_CHECK(h);
     FOFB_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, s0.cand_rows.p, cflag, csrc, dcount, m0, st));
     FOFB_CUDA(cub::DeviceSelect::Flagged(cub_tmp(h, bytes), bytes, s0.cand_rows.p, cflag, csrc, dcount, m0, st));
@@ -171,12 +196,8 @@ void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, doub
   if (m_c > 0) {
     FOFB_PROFILED(h, "k_build_rows", k_build_rows<<<grid_for((int64_t)m_c * ocols, B), B, 0, st>>>(m_c, csrc, raw, s0.N_row.p, C, ocols));
   }
-  View Gv, Cv;
   Gv.data = G; Gv.rows = n_g; Gv.cols = ocols; Gv.rs = ocols; Gv.cs = 1;
   Cv.data = C; Cv.rows = m_c; Cv.cols = ocols; Cv.rs = ocols; Cv.cs = 1;
-  fof.run(h, p, Gv, Cv);
-  fof.last_K = fof.merged.K;
-  began = true;
 }
 
 void Pipeline::finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key, int* mt_pos) {
@@ -237,7 +258,7 @@ void Pipeline::finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key
   const int nmax = d2h_scalar(h, dmax);
   clean.virial_core(h, p, K2, ooff, M2v, nmax, props.alloc((size_t)K2 * 8));
   // results in terms of the caller's rows
-  k_final_meta<<<grid_for(K2, B), B, 0, st>>>(K2, sel, F.centre.p, F.N.p, F.D.p, c_src.p, g_src.p, fof.m,
+  k_final_meta<<<grid_for(K2, B), B, 0, st>>>(K2, sel, F.centre.p, F.N.p, F.D.p, dist ? nullptr : c_src.p, g_src.p, fof.m,
                                               out_centre.alloc(K2), out_N.alloc(K2), out_D.alloc(K2));
   FOFB_LAUNCH_CHECK(h);
   k_map_rows<<<grid_for(total_out, B), B, 0, st>>>(total_out, grow, g_src.p, out_rows.alloc((size_t)total_out));

@@ -24,6 +24,18 @@ struct Pipeline {
   void begin(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen,
              const unsigned* mt_key = nullptr, int mt_pos = 0);
   void finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key = nullptr, int* mt_pos = nullptr);
+  void begin_dist(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen,
+                  double valid_lo, double valid_hi, double own_lo, double own_hi);
+  void stage0_and_inputs(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double czmin,
+                         double zmax_cen, const unsigned* mt_key, int mt_pos);
+  bool dist = false;
+  double own_hi_exclusive = 0;
+  View Gv, Cv;
+  DBuf<double> cn_glob;
+  DBuf<unsigned char> owned;
+  DBuf<int> keep_dev, ext_centre;
+  DBuf<long long> ext_off;
+  DBuf<double> ext_ids;
 };
 
 }  // namespace fofb

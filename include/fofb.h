@@ -186,6 +186,38 @@ int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, 
  * total stage-1 members, priority rounds, centres evaluated, clusters entering stage 4 */
 int fofb_pipeline_stats(fofb_handle* h, int64_t* stats7);
 
+/* ---- one catalogue over several GPUs: redshift slabs with window-wide halos --------------
+ * One process per GPU holds the rows of a redshift slab plus halos; these calls are the device-side steps, the
+ * driver (fof_b200/distributed.py) runs the collectives between them:
+ *   fofb_dist_begin          stage 0 on the local rows; zcut3 = (zmin, zmax_gal, zmax_cen) of pipeline.py:80-86,
+ *                            z_valid2 = redshift range whose velocity windows are complete on this process,
+ *                            z_own2 = [lo, hi) of the centres this process evaluates
+ *   fofb_dist_local_inputs   local candidate centres (8 columns, local priority order), their source rows, the
+ *                            source row of every FoF() row, and the bounding box of the local FoF() rows
+ *   [all-gather centres; global priority order = N desc, global row desc]
+ *   fofb_dist_prepare        centres[n x 8] in global priority order, owned[n] flags; returns the bounding box of the
+ *                            local FoF() rows [all-reduce min/max -> the box helper.py:197-202 draws points from]
+ *   loop: fofb_dist_round_evaluate; fofb_dist_state(0); [all-reduce MIN alive, MAX decided]; fofb_dist_state(1);
+ *         fofb_dist_round_advance  -> until the global number of active centres is 0
+ *   fofb_dist_finalize, fofb_dist_local_clusters   [all-gather; order by centre index]
+ *   fofb_dist_overlap        stage 2 on the all-process list (replicated)
+ *   fofb_dist_set_merged     then fofb_pipeline_finish_mt / fofb_pipeline_fetch as in the single-GPU path; the
+ *                            MT19937 stream covers every process's clusters, each process uses its own blocks;
+ *                            centre_row of fofb_pipeline_fetch is then an index into the global centre table.
+ */
+int fofb_dist_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, const double* zcut3,
+                    const double* z_valid2, const double* z_own2, int64_t* n_fof_rows, int64_t* n_local_centres);
+int fofb_dist_local_inputs(fofb_handle* h, double* centre_rows, int32_t* centre_src_row, int32_t* fof_src_row, double* bbox4);
+int fofb_dist_prepare(fofb_handle* h, const double* centres, int64_t n_centres, const uint8_t* owned, double* local_bbox4);
+int fofb_dist_round_evaluate(fofb_handle* h);
+int fofb_dist_state(fofb_handle* h, uint8_t* alive, uint8_t* decided, int32_t direction);
+int fofb_dist_round_advance(fofb_handle* h, int64_t* n_active);
+int fofb_dist_finalize(fofb_handle* h, int64_t* n_clusters, int64_t* n_members);
+int fofb_dist_local_clusters(fofb_handle* h, int32_t* centre, int64_t* offsets, double* ids);
+int fofb_dist_overlap(fofb_handle* h, int64_t K, const int32_t* centre, const int64_t* offsets, const double* ids, int32_t* keep);
+int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_t* global_index, int64_t n_global_merged,
+                         const double* global_bbox4);
+
 /* ---- transitive friends-of-friends (connected components) ------------------------------------------------------
  * NOT a reference code path (kencx/FoF never computes connected components): the lock-free
  * union-find mode named in BASELINE.json.  Galaxies i, j are friends iff each lies in the other's velocity window
