@@ -182,6 +182,62 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_slabs(args, rank, world, local_rank, h, p, dist):
+    """One catalogue of world x galaxies rows, split into redshift slabs with window-wide halos; the per-round tracker
+    state, the candidate centres and the cluster lists travel over NCCL (fof_b200/distributed.py)."""
+    import torch
+    from fof_b200 import distributed as D
+    from fof_b200.mock import make_catalog
+    n_total = args.galaxies * world
+    arr = make_catalog(n_total, seed=20260103, as_frame=False)  # every rank builds the same table, keeps its slab
+    edges = D.slab_edges(arr[:, 2], world)
+    rows, own, valid = D.select_local_rows(arr[:, 2], edges, rank, p.max_velocity)
+    local = np.ascontiguousarray(arr[rows])
+    del arr
+    comm = D.TorchComm()
+    tim = {}
+
+    def step():
+        np.random.seed(4242)  # every rank must hold the same generator state
+        return D.find_clusters_slabs(local, rows, own, valid, comm, h, params=p, zcut=ZCUT, timings=tim)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    clock_info = clocks.stop()
+    if rank == 0:
+        value = n_total / (dt / max(args.steps, 1))
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"ONE {n_total}-galaxy COSMOS-like mock ({args.galaxies} per GPU), whole path",
+                           "params": f"params.py defaults, linking_length_factor={args.linking_length_factor}",
+                           "parallelism": f"{world} redshift slabs with window-wide halos; NCCL all-gather of centres and cluster lists, "
+                                          "all-reduce of the tracker state every priority round",
+                           "clusters_final": int(len(res[0]) - 1), "members_final": int(res[0][-1]), **{k: int(v) for k, v in tim.items()}},
+                "clocks": clock_info,
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(local.nbytes), "d2h_bytes_per_step": int(res[1].nbytes),
+                        "note": "the slab driver always starts from host rows and returns host arrays"},
+                "gpu_launches": int(h.last_timing()[1]) * args.steps, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +248,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--linking-length-factor", type=float, default=0.2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decomposition", default="fields", choices=["fields", "slabs"],
+                    help="N > 1: independent fields per GPU (default) or ONE N x galaxies catalogue in redshift slabs with halos")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,6 +277,8 @@ def main():
     p = _lib.default_params(linking_length_factor=args.linking_length_factor)
 
     n = args.galaxies
+    if args.decomposition == "slabs" and world > 1:
+        return run_slabs(args, rank, world, local_rank, h, p, dist)
     arr = make_catalog(n, seed=20260103 + rank, as_frame=False)
     host = torch.empty((n, 7), dtype=torch.float64, pin_memory=True)
     host.numpy()[:] = arr
