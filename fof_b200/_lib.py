@@ -96,6 +96,7 @@ def load():
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
         "fofb_three_sigma": (C.c_int, [vp, P(Params), i64, vp, P(Matrix), vp, vp, vp]),
         "fofb_virial": (C.c_int, [vp, P(Params), i64, vp, P(Matrix), vp]),
+        "fofb_projected_mass": (C.c_int, [vp, P(Params), i64, vp, P(Matrix), vp]),
         "fofb_bootstrap_indices": (C.c_int, [i64, i64, vp]),
         "fofb_pipeline_begin": (C.c_int, [vp, P(Params), P(Matrix), dbl, dbl, dbl, P(i64)]),
         "fofb_pipeline_finish": (C.c_int, [vp, vp, i32, P(i64), P(i64)]),
@@ -346,6 +347,16 @@ class Handle:
                                                    lab.ctypes.data, 0, C.byref(g), C.byref(l)))
         del keep
         return lab, g.value, l.value
+
+    def projected(self, offsets, members, params):
+        """(K, 2): projected mass [Msun/h], mass_err."""
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        K = len(off) - 1
+        m, keep = matrix_of(members)
+        out = np.empty((K, 2))
+        self.check(self.lib.fofb_projected_mass(self.h, C.byref(params), K, off.ctypes.data, C.byref(m), out.ctypes.data))
+        del keep
+        return out
 
     def fof_stats(self):
         r, e = C.c_int64(), C.c_int64()

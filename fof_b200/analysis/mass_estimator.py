@@ -29,6 +29,14 @@ def virial_mass_estimator(cluster, device=0):
             Q(out[4], "Mpc/littleh"))
 
 
+def projected_mass_estimator(cluster, device=0):
+    """mass_estimator.py:115-145: (projected mass [Msun/h], mass_err)."""
+    g = np.ascontiguousarray(np.asarray(cluster.galaxies, dtype=np.float64))
+    h = _lib.get_handle(device)
+    out = h.projected(np.array([0, len(g)], dtype=np.int64), g, _lib_params())[0]
+    return Q(out[0], "Msun/littleh"), Q(out[1], "km2/s2")
+
+
 def mass_error(mass, vel_disp, vel_disp_err):
     """mass_estimator.py:170-171."""
     return mass * (vel_disp_err / vel_disp)

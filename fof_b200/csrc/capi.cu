@@ -479,6 +479,23 @@ int fofb_virial(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* 
   FOFB_CATCH(h)
 }
 
+int fofb_projected_mass(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* offsets, const fofb_matrix* members,
+                        double* out) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(offsets && members && out, "projected: null argument");
+  FOFB_REQUIRE(K >= 0 && K < (1ll << 31), "projected: bad K");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->clean) h->clean = new CleanState();
+  Timed timer(h);
+  const View M = to_device(h, *members, h->upload);
+  h->clean->projected(h, *p, (int)K, reinterpret_cast<const long long*>(offsets), M, out);
+  timer.stop();
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
 int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out) {
   if (n < 1 || count < 0 || !out) return FOFB_ERR_INVALID;
   if (n == 1) {

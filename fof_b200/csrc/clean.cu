@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   __shared__ double sh[kVirialThreads];
   __shared__ double boot[kBootNum];
   __shared__ double s_zbar, s_vdisp, s_zavg_err;
-  __shared__ int s_scan[kVirialThreads];
   __shared__ long long s_taken;
   __shared__ int s_fail;
   double* o = out + (long long)k * 8;
@@ -410,49 +409,62 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   }
   const double total_sep = Reduce(rtmp).Sum(psum);
   __syncthreads();
-  // bootstrap: 100 resamples of n-1 indices from the masked MT19937 stream
+  // bootstrap: 100 resamples of n-1 indices from the masked MT19937 stream.  Every thread owns a contiguous span of
+  // the raw stream: one counting pass, one block scan for the ordinal of its first accepted word, then a second
+  // pass that accumulates v^2 per resample and touches shared memory only when the resample changes.
   unsigned mask = (unsigned)(n - 1);
   mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
   const long long want = (long long)kBootNum * (n - 1);
-  typedef cub::BlockScan<int, kVirialThreads> Scan;
+  typedef cub::BlockScan<long long, kVirialThreads> Scan;
   __shared__ typename Scan::TempStorage stmp;
-  for (long long base = 0; base < mt_len; base += kVirialThreads) {
-    __syncthreads();
-    const long long taken = s_taken;
-    if (taken >= want) break;
-    const long long w = base + tid;
-    unsigned val = 0;
-    int ok = 0;
-    if (w < mt_len) {
-      val = mt[w] & mask;
-      ok = val <= (unsigned)(n - 1) ? 1 : 0;
+  __shared__ double sv2[1024];
+  const bool cached = n <= 1024;
+  if (cached)
+    for (int i = tid; i < n; i += kVirialThreads) {
+      const double v = redshift_to_velocity(M.at(s0 + i, 2), zbar);
+      sv2[i] = v * v;
     }
-    int rank, agg;
-    Scan(stmp).ExclusiveSum(ok, rank, agg);
-    // accepted ordinals are consecutive across the block, so a warp touches one or two resamples: reduce per
-    // resample inside the warp and issue one shared-memory atomic per (warp, resample)
-    int rs = -1;
-    double v2 = 0.0;
-    if (ok) {
-      const long long ord = taken + rank;
-      if (ord < want) {
-        rs = (int)(ord / (n - 1));
+  long long L = (long long)((double)want * ((double)mask + 1.0) / (double)n * 1.05) + 2048;
+  if (L > mt_len) L = mt_len;
+  long long lo_w, hi_w, base, total;
+  for (;;) {
+    const long long span = (L + kVirialThreads - 1) / kVirialThreads;
+    lo_w = (long long)tid * span;
+    hi_w = lo_w + span < L ? lo_w + span : L;
+    long long cnt = 0;
+    for (long long w = lo_w; w < hi_w; ++w) cnt += (mt[w] & mask) <= (unsigned)(n - 1) ? 1 : 0;
+    __syncthreads();
+    Scan(stmp).ExclusiveSum(cnt, base, total);
+    if (total >= want || L >= mt_len) break;
+    L = L + L / 4 + 4096;
+    if (L > mt_len) L = mt_len;
+  }
+  if (tid == 0) s_taken = total;
+  {
+    long long ord = base;
+    int r = (int)(ord / (n - 1));
+    int rem = (int)(ord - (long long)r * (n - 1));
+    double acc = 0.0;
+    for (long long w = lo_w; w < hi_w && ord < want; ++w) {
+      const unsigned val = mt[w] & mask;
+      if (val > (unsigned)(n - 1)) continue;
+      double v2;
+      if (cached) {
+        v2 = sv2[val];
+      } else {
         const double v = redshift_to_velocity(M.at(s0 + val, 2), zbar);
         v2 = v * v;
       }
+      acc += v2;
+      ++ord;
+      if (++rem == n - 1) {
+        atomicAdd(&boot[r], acc);
+        acc = 0.0;
+        rem = 0;
+        ++r;
+      }
     }
-    unsigned remaining = __ballot_sync(0xffffffffu, rs >= 0);
-    while (remaining) {
-      const int leader = __ffs(remaining) - 1;
-      const int key = __shfl_sync(0xffffffffu, rs, leader);
-      const unsigned grp = __ballot_sync(0xffffffffu, rs == key);
-      double part = rs == key ? v2 : 0.0;
-      for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if ((threadIdx.x & 31) == leader) atomicAdd(&boot[key], part);
-      remaining &= ~grp;
-    }
-    __syncthreads();
-    if (tid == 0) s_taken = taken + agg;
+    if (acc != 0.0 && r < kBootNum) atomicAdd(&boot[r], acc);
   }
   __syncthreads();
   if (tid == 0) {
@@ -481,6 +493,82 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
     o[7] = (double)n;
     if (s_fail) atomicAdd(status, 1);
   }
+}
+
+// ---- projected mass estimator (analysis/mass_estimator.py:115-145), one CTA per cluster -----------------------
+__global__ void __launch_bounds__(kVirialThreads) k_projected_mass(int K, const long long* off, View M, Cosmo cosmo,
+                                                                   double mass_unit, double* out) {
+  const int k = blockIdx.x;
+  if (k >= K) return;
+  const long long s0 = off[k];
+  const int n = (int)(off[k + 1] - s0);
+  const int tid = threadIdx.x;
+  typedef cub::BlockReduce<double, kVirialThreads> Reduce;
+  __shared__ typename Reduce::TempStorage rtmp;
+  __shared__ double s_zbar, s_ra, s_dec, s_zavg_err;
+  double* o = out + (long long)k * 2;
+  if (n < 2) {
+    if (tid == 0) { o[0] = NAN; o[1] = NAN; }
+    return;
+  }
+  if (tid == 0) {
+    auto getz = [&](long long i) -> double { return M.at(s0 + i, 2); };
+    auto getra = [&](long long i) -> double { return M.at(s0 + i, 0); };
+    auto getdec = [&](long long i) -> double { return M.at(s0 + i, 1); };
+    s_zbar = __ddiv_rn(np_pairwise_sum(getz, 0, n), (double)n);
+    s_ra = __ddiv_rn(np_pairwise_sum(getra, 0, n), (double)n);    // centroid = plain means of ra and dec
+    s_dec = __ddiv_rn(np_pairwise_sum(getdec, 0, n), (double)n);
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double z = M.at(s0 + i, 2);
+      const double e = fmax(fabs(__dsub_rn(M.at(s0 + i, 3), z)), fabs(__dsub_rn(M.at(s0 + i, 4), z)));
+      acc = __dadd_rn(acc, __dmul_rn(e, e));
+    }
+    s_zavg_err = __ddiv_rn(sqrt(acc), (double)n);
+  }
+  __syncthreads();
+  const double zbar = s_zbar;
+  const double dA = cosmo_angular_diameter_distance(cosmo, zbar);
+  const double clon = __dmul_rn(s_ra, kDeg2Rad), clat = __dmul_rn(s_dec, kDeg2Rad);
+  double sp = 0.0, se = 0.0;
+  for (int i = tid; i < n; i += kVirialThreads) {
+    const double z = M.at(s0 + i, 2);
+    const double v = redshift_to_velocity(z, zbar);
+    const double sep = vincenty_rad(clon, clat, __dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad));
+    const double actual = sep * kRad2Deg * dA * kDeg2Rad * cosmo.h;
+    sp += actual * v * v;
+    const double e = fmax(fabs(M.at(s0 + i, 3) - z), fabs(M.at(s0 + i, 4) - z));
+    const double zd = sqrt(s_zavg_err * s_zavg_err + e * e);
+    const double a = s_zavg_err / zbar, b = zd / (z - zbar);
+    const double err = fabs(v) * sqrt(a * a + b * b);
+    const double t = 2.0 * v * err;
+    se += t * t;
+  }
+  const double sumproduct = Reduce(rtmp).Sum(sp);
+  __syncthreads();
+  const double errsum = Reduce(rtmp).Sum(se);
+  if (tid == 0) {
+    o[0] = (32.0 / kPi) * (1.0 / ((double)n - 1.5)) * sumproduct * mass_unit;
+    o[1] = sqrt(errsum);
+  }
+}
+
+void CleanState::projected(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
+                           double* out_host) {
+  cudaStream_t st = h->stream;
+  if (K == 0) return;
+  FOFB_REQUIRE(off_host[K] == M.rows, "projected: offsets do not cover the member matrix");
+  FOFB_REQUIRE(M.cols >= 5, "projected: members need columns ra, dec, z, z_lower, z_upper");
+  const Cosmo cosmo = device_cosmo(h, p);
+  long long* off = d_off.alloc((size_t)K + 1);
+  FOFB_CUDA(cudaMemcpyAsync(off, off_host, sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice, st));
+  double* out = d_props.alloc((size_t)K * 8);
+  const double pc_m = 149597870700.0 * 648000.0 / kPi;
+  const double msun_kg = 1.3271244e20 / 6.6743e-11;
+  const double mass_unit = 1.0e6 * (1.0e6 * pc_m) / 6.6743e-11 / msun_kg;
+  FOFB_PROFILED(h, "k_projected_mass", k_projected_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, cosmo, mass_unit, out));
+  FOFB_CUDA(cudaMemcpyAsync(out_host, out, sizeof(double) * (size_t)K * 2, cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
 }
 
 void CleanState::virial_core(fofb_handle* h, const fofb_params& p, int K, const long long* off, const View& M, int nmax,

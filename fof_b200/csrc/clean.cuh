@@ -20,6 +20,7 @@ struct CleanState {
   void three_sigma(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M,
                    const double* centres_host, int nbins, long long* out_off_host, int* out_index_host);
   void virial(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M, double* out_host);
+  void projected(fofb_handle* h, const fofb_params& p, int K, const long long* off_host, const View& M, double* out_host);
 };
 
 void bootstrap_indices_host(long long n, long long count, int* out);

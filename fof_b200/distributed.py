@@ -60,10 +60,17 @@ def plan_slab(edges, rank, max_velocity):
     return own, valid, local
 
 
-def global_priority(N, global_row):
+def global_priority(N, global_row, device=None):
     """Order of the gathered candidate centres: N(0.5) descending, ties by descending global row (oracle pin D1,
-    what ``argsort(kind="stable")[::-1]`` gives on the whole table)."""
-    return np.lexsort((-np.asarray(global_row, dtype=np.int64), -np.asarray(N, dtype=np.float64)))
+    what ``argsort(kind="stable")[::-1]`` gives on the whole table).  With ``device`` the sort runs on that GPU."""
+    N = np.asarray(N, dtype=np.float64)
+    global_row = np.asarray(global_row, dtype=np.int64)
+    if device is not None and len(N) > 100000 and np.all(N == np.floor(N)) and N.max(initial=0) < 2 ** 20 and \
+            global_row.max(initial=0) < 2 ** 40:
+        import torch
+        key = torch.from_numpy(N.astype(np.int64)).to(device) * (1 << 40) + torch.from_numpy(global_row).to(device)
+        return torch.sort(key, descending=True).indices.cpu().numpy()
+    return np.lexsort((-global_row, -N))
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -230,7 +237,7 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     parts = comm.allgatherv(np.column_stack([cen_rows, grow[cen_src].astype(np.float64)]) if m_loc else np.zeros((0, 9)))
     owner = np.concatenate([np.full(len(x), r, dtype=np.int32) for r, x in enumerate(parts)])
     allc = np.concatenate(parts, axis=0)
-    order = global_priority(allc[:, 7], allc[:, 8].astype(np.int64))
+    order = global_priority(allc[:, 7], allc[:, 8].astype(np.int64), device=torch.device("cuda", h.device))
     centres = np.ascontiguousarray(allc[order, :8])
     centre_grow = allc[order, 8].astype(np.int64)
     owned = np.ascontiguousarray((owner[order] == rank).astype(np.uint8))

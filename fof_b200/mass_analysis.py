@@ -13,13 +13,21 @@ def find_masses(data, estimator, device=0):
     dispersion (a variance, km^2/s^2), projected radius and total absolute magnitude."""
     if estimator not in ("virial", "projected"):
         raise ValueError("estimator must be 'virial' or 'projected'")
-    if estimator == "projected":
-        raise NotImplementedError("projected_mass_estimator (mass_estimator.py:115-145) is not on the device path yet")
     if not len(data):
         return []
     h = _lib.get_handle(device)
     p = _lib.default_params(H0=cosmo.H0, Om0=cosmo.Om0, Ode0=cosmo.Ode0)
     off, members = _pack(data)
+    if estimator == "projected":  # mass_analysis.py:36-40
+        pm = h.projected(off, members, p)
+        out = []
+        for k, c in enumerate(data):
+            new_c = CleanedCluster(c.center_attributes, c.galaxies, Q(pm[k, 0], "Msun/littleh"), Q(pm[k, 1], "km2/s2"),
+                                   None, None, None, None)
+            new_c.D = c.D
+            new_c.flag_poor = c.flag_poor
+            out.append(new_c)
+        return out
     props = h.virial(off, members, p)
     new_cs = []
     for k, c in enumerate(data):

@@ -160,6 +160,9 @@ int fofb_three_sigma(fofb_handle* h, const fofb_params* p, int64_t K, const int6
                      const double* centres, int64_t* out_offsets, int32_t* out_index);
 int fofb_virial(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* offsets, const fofb_matrix* members,
                 double* out);
+/* projected_mass_estimator (mass_estimator.py:115-145): out[2k] = mass [Msun/h], out[2k+1] = mass_err [km^2/s^2] */
+int fofb_projected_mass(fofb_handle* h, const fofb_params* p, int64_t K, const int64_t* offsets, const fofb_matrix* members,
+                        double* out);
 int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out);
 
 /* ---- whole job: pipeline.py:62-64,80-99,113,173 with every intermediate on the device ---------------------

@@ -688,6 +688,24 @@ def virial_mass_estimator(galaxies):
     return mass, mass * (combined / vel_disp), vel_disp, combined, radius
 
 
+def projected_mass_estimator(galaxies):
+    """analysis/mass_estimator.py:115-145. Returns (M [Msun/h], M_err [km^2/s^2])."""
+    N = len(galaxies)
+    z_arr = galaxies[:, 2]
+    zbar = np.mean(z_arr)
+    vel = redshift_to_velocity(z_arr, zbar)
+    lon, lat = np.deg2rad(galaxies[:, 0]), np.deg2rad(galaxies[:, 1])
+    clon, clat = np.deg2rad(np.mean(galaxies[:, 0])), np.deg2rad(np.mean(galaxies[:, 1]))
+    sep_deg = np.rad2deg(vincenty_rad(clon, clat, lon, lat))
+    d_A = float(angular_diameter_distance(zbar))
+    actual = sep_deg * d_A * (math.pi / 180.0) * LITTLE_H
+    sumproduct = np.sum(actual * vel ** 2)
+    mass = (32 / np.pi) * (1 / (N - 1.5)) * sumproduct * MASS_UNIT
+    vel_err = velocity_error(galaxies, z_arr, zbar, vel)
+    mass_err = np.sqrt(sum((2 * vel * vel_err) ** 2))
+    return float(mass), float(mass_err)
+
+
 def find_masses(data):
     """mass_analysis.py:8-44, estimator == 'virial'. Returns a list of dicts."""
     out = []

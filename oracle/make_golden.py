@@ -60,7 +60,8 @@ def main():
             cleaned_off=k_off, cleaned_member_ids=k_ids,
             cleaned_centre_ids=np.array([c[0][6] for c in R["cleaned"]]),
             number_removed=np.array(R["number_removed"], dtype=np.int64),
-            virial=np.array([[v[k] for k in keys] for v in R["virial"]]).reshape(-1, len(keys)))
+            virial=np.array([[v[k] for k in keys] for v in R["virial"]]).reshape(-1, len(keys)),
+            projected=np.array(R["projected"]).reshape(-1, 2))
         print(name, "clusters", len(R["clusters"]), "cleaned", len(R["cleaned"]), "candidates", len(R["candidate_centers"]))
 
 

@@ -96,4 +96,6 @@ def run_pipeline(ref, df, richness=None, overdensity=None, linking_length_factor
                  vel_disp=float(v.vel_disp.value), vel_disp_err=float(v.vel_disp_err.value),
                  projected_radius=float(v.projected_radius.value), total_absmag=float(v.total_absmag))
             for v in virial]
+        proj = ref.mass_analysis.find_masses(cleaned, "projected")
+        out["projected"] = [(float(v.cluster_mass.value), float(getattr(v.mass_err, "value", v.mass_err))) for v in proj]
     return out

@@ -35,3 +35,6 @@ def test_gpu_reproduces_reference_golden(lib, path):
     vir = mass_analysis.find_masses(cleaned, "virial")
     got = np.array([[float(getattr(v, k)) for k in KEYS] for v in vir]).reshape(-1, len(KEYS))
     np.testing.assert_allclose(got, g["virial"], rtol=1e-9)
+    proj = mass_analysis.find_masses(cleaned, "projected")
+    gotp = np.array([[float(v.cluster_mass), float(v.mass_err)] for v in proj]).reshape(-1, 2)
+    np.testing.assert_allclose(gotp, g["projected"], rtol=1e-9)

@@ -37,6 +37,8 @@ def test_oracle_reproduces_reference(path, mode):
     vir = O.find_masses(cleaned)
     got = np.array([[v[k] for k in KEYS] for v in vir]).reshape(-1, len(KEYS))
     np.testing.assert_allclose(got, g["virial"], rtol=1e-12)
+    proj = np.array([O.projected_mass_estimator(c.galaxies) for c in cleaned]).reshape(-1, 2)
+    np.testing.assert_allclose(proj, g["projected"], rtol=1e-12)
 
 
 def test_known_numpy_semantics():
