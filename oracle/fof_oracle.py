@@ -13,7 +13,8 @@ holds no tests, golden vectors or fixtures for it.
 Pinned orderings: D1 equal-N candidates in descending original index
 (``argsort(kind="stable")[::-1]``); D2 GriSPy neighbour order = cell-major (dec cell outer, RA cell
 inner), ascending index inside a cell; D3 the caller seeds numpy's legacy global RNG right before
-``FoF`` and the 2x300 uniforms per cluster are drawn from it in cluster order.
+``FoF`` and the 2x300 uniforms per cluster are drawn from it in cluster order; D4 exact ties in the
+3-sigma deviation sort (fof.py:456-458) keep their order.
 
 Two execution modes with identical results:
   mode="literal"  the reference's control flow: a full-catalogue velocity mask and a fresh 64x64 grid
@@ -363,6 +364,8 @@ def number_counts_fast(galaxy_arr, p, widx=None):
     qi, pj = qi[keep], pj[keep]
     # GriSPy cell-box predicate with the per-query grid (bbox of the query's window)
     uq = np.unique(qi)
+    if len(uq) == 0:
+        return np.zeros(n)
     bb = np.array([widx.bbox(int(lo[i]), int(hi[i])) for i in uq])
     bmap = np.full(n, -1, dtype=np.int64)
     bmap[uq] = np.arange(len(uq))
@@ -607,7 +610,9 @@ def three_sigma(center, member_galaxies, n):
             size_before = len(b)
             if len(b) > 2:
                 vel = b[:, -2]
-                b = b[np.argsort(np.abs(vel - np.mean(vel)))]
+                # pin D4: exact ties in |v - mean| (duplicated redshifts) keep their order; the reference's default
+                # argsort leaves them to the sort implementation (measure zero for real data)
+                b = b[np.argsort(np.abs(vel - np.mean(vel)), kind="stable")]
                 if b[-1, -1] == 0.0:
                     ignored = b[-2, :]
                     new_b = np.delete(b, (-2), axis=0)

@@ -1,0 +1,100 @@
+"""Edge cases and randomly generated tiny catalogues: GPU path vs the oracle."""
+import numpy as np
+import pytest
+
+from fof_b200.mock import make_catalog
+from oracle import fof_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(arr, b=0.2, rich=12, D=2.0, seed=5):
+    from fof_b200 import _lib, pipeline
+    op = O.Params(linking_length_factor=b, richness=rich, overdensity=D)
+    ref = O.run_pipeline(arr, op, mode="fast", seed=seed)
+    np.random.seed(seed)
+    cat = pipeline.find_clusters(arr, linking_length_factor=b, richness=rich, overdensity=D)
+    h = _lib.get_handle(0)
+    N, rows = h.number_counts(arr, _lib.default_params())
+    assert np.array_equal(N.astype(float), ref["main_arr"][:, 7])
+    assert np.array_equal(arr[rows, 6], ref["candidate_centers"][:, 6])
+    assert len(cat) == len(ref["virial"])
+    ids = arr[:, 6]
+    for k, r in enumerate(ref["virial"]):
+        assert np.array_equal(ids[cat.members(k)], r["galaxies"][:, 6])
+        assert cat.N[k] == r["N"] and (cat.D[k] == r["D"] or (np.isnan(cat.D[k]) and np.isnan(r["D"])))
+        for j, key in enumerate(("cluster_mass", "vel_disp", "projected_radius", "total_absmag")):
+            jj = {"cluster_mass": 0, "vel_disp": 2, "projected_radius": 4, "total_absmag": 5}[key]
+            assert abs(cat.props[k, jj] - r[key]) <= 1e-9 * abs(r[key])
+    return cat
+
+
+def _row(ra, dec, z, i):
+    return [ra, dec, z, z - 0.01 - 1e-4 * i, z + 0.01 + 1e-4 * i, -21.0 - 0.01 * i, float(i)]
+
+
+def test_tiny_and_empty_outcomes(lib):
+    # a handful of isolated galaxies: no window reaches 8 members -> N = 0 everywhere, no centres, no clusters
+    arr = np.array([_row(150.0 + 0.3 * i, 2.0, 0.6 + 0.1 * i, i) for i in range(5)])
+    assert len(_compare(arr)) == 0
+    arr1 = np.array([_row(150.0, 2.0, 1.0, 0)])
+    assert len(_compare(arr1)) == 0
+    # candidates exist but nothing passes an absurd richness
+    big = make_catalog(3000, seed=2, as_frame=False)
+    assert len(_compare(big, rich=100000)) == 0
+    # richness / overdensity low enough that every candidate cluster survives to the end
+    assert len(_compare(big, rich=3, D=-1e9)) > 0
+
+
+def test_exact_duplicates_and_ties(lib):
+    """Coincident positions (separation exactly 0), identical redshifts and many equal-N ties."""
+    rng = np.random.default_rng(3)
+    base = make_catalog(1500, seed=8, as_frame=False)
+    # a tight knot: 40 galaxies on 4 distinct positions and 2 distinct redshifts
+    knot = []
+    for i in range(40):
+        knot.append([150.1 + 1e-3 * (i % 4), 2.2 + 1e-3 * ((i // 4) % 2), 0.9 + 1e-4 * (i % 2), 0, 0, -21.0 - 0.01 * i, 0])
+    arr = np.vstack([base, np.array(knot)])
+    arr[:, 6] = np.arange(len(arr), dtype=float)
+    z = arr[:, 2]
+    arr[:, 3] = z - 0.02 - 1e-6 * np.arange(len(arr))     # keep z_lower / z_upper unique (the tracker keys on them)
+    arr[:, 4] = z + 0.02 + 1e-6 * np.arange(len(arr))
+    arr = arr[np.argsort(arr[:, 2], kind="stable")]
+    cat = _compare(arr, b=0.2, rich=8, D=-1e9)
+    assert len(cat) >= 1
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_catalogues(lib, seed):
+    """Hypothesis-style sweep: small, very dense fields with random parameters."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(150, 900))
+    arr = make_catalog(n, seed=200 + seed, density=float(rng.choice([5e4, 2e5, 1e6])), richness_range=(10, 60),
+                       cluster_fraction=float(rng.choice([0.2, 0.5, 0.8])), as_frame=False)
+    _compare(arr, b=float(rng.choice([0.02, 0.05, 0.1, 0.2, 0.4])), rich=int(rng.choice([3, 5, 8, 12])),
+             D=float(rng.choice([-1e9, 0.0, 2.0])), seed=seed)
+
+
+def test_unsupported_inputs_are_refused(lib):
+    """Degenerate inputs the device path documents as unsupported fail loudly instead of diverging."""
+    from fof_b200 import _lib
+    h = _lib.get_handle(0)
+    arr = make_catalog(3000, seed=2, as_frame=False)
+    main_arr, cand = O.candidate_center_search(arr, O.Params(), mode="fast")
+    # (a) |column 3| > |column 5| near a centre: the BCG replacement of fof.py:346-367 would fire
+    bad = main_arr.copy()
+    bad[:, 3] = 100.0 + np.arange(len(bad))
+    cb = bad[[int(np.nonzero(bad[:, 6] == i)[0][0]) for i in cand[:, 6]]]
+    with pytest.raises(_lib.FofbError) as e:
+        h.fof_run(bad, cb, _lib.default_params())
+    assert e.value.code == -5
+    # (b) two galaxy rows sharing a candidate centre's z_upper
+    dup = main_arr.copy()
+    r0 = int(np.nonzero(dup[:, 6] == cand[0, 6])[0][0])
+    dup[(r0 + 1) % len(dup), 4] = dup[r0, 4]
+    with pytest.raises(_lib.FofbError) as e:
+        h.fof_run(dup, cand, _lib.default_params())
+    assert e.value.code == -5
+    # (c) bad shapes
+    with pytest.raises(_lib.FofbError):
+        h.fof_run(main_arr[:, :5], cand[:, :5], _lib.default_params())
