@@ -367,6 +367,20 @@ def main():
                     "algorithmic_bytes_per_launch": bytes_per_launch, "bytes_per_unit": bytes_per_unit, "unit_of_work": unit_name,
                     "share_of_kernel_time": share}
 
+    # the one HBM-shaped hot kernel of the path (the N(0.5) link test) is reported beside the dominant kernel
+    stream = None
+    if prof and "k_count" in prof and roofline is not None:
+        kms, cnt = prof["k_count"]
+        b = ALGO_BYTES["k_count"][1] * n / max(cnt / max(args.steps, 1), 1)
+        tr = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            tr = json.load(open(tpath)).get("k_count")
+        stream = {"kernel": "k_count", "bound": "hbm", "achieved": b / (kms / cnt * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                  "frac": b / (kms / cnt * 1e-3) / 1e9 / peak, "traffic": tr, "avg_launch_ms": kms / cnt,
+                  "algorithmic_bytes_per_launch": b}
+        roofline["link_test_kernel"] = stream
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tcpu, _ = cpu_literal_sample(args.cpu_sample, 777, workers=1)
