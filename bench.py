@@ -229,7 +229,7 @@ def run_slabs(args, rank, world, local_rank, h, p, dist):
                            "params": f"params.py defaults, linking_length_factor={args.linking_length_factor}",
                            "parallelism": f"{world} redshift slabs with window-wide halos; NCCL all-gather of centres and cluster lists, "
                                           "all-reduce of the tracker state every priority round",
-                           "clusters_final": int(len(res[0]) - 1), "members_final": int(res[0][-1]), **{k: int(v) for k, v in tim.items()}},
+                           "clusters_final": int(len(res[0]) - 1), "members_final": int(res[0][-1]), **{k: (int(v) if float(v).is_integer() else v) for k, v in tim.items()}},
                 "clocks": clock_info,
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(local.nbytes), "d2h_bytes_per_step": int(res[1].nbytes),
                         "note": "the slab driver always starts from host rows and returns host arrays"},

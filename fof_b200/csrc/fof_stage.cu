@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(kHop2Threads) k_hop2(
     const long long* hcap, unsigned long long* htab, View G, const double* v2ra, const double* v2dec, const double* v2cos,
     const unsigned char* novel, const double* LLin, const double4* bbox2, fofb_params p, const int* v2row, int* mrows,
     int* nm_list, int* first_batch, int* nm_sorted, int* nM, int* pass, const int* kill_target, unsigned char* alive,
-    unsigned char* decided, unsigned long long* dbg) {
+    unsigned char* decided) {
   const int w = blockIdx.x;
   if (w >= nr) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -542,7 +542,6 @@ __global__ void __launch_bounds__(kHop2Threads) k_hop2(
         n_nm += all;
         __syncthreads();
       }
-      if (dbg && tid == 0) { atomicMax(dbg, (unsigned long long)n_v); atomicMax(dbg + 1, (unsigned long long)n_nm); atomicAdd(dbg + 2, (unsigned long long)n_nm); atomicAdd(dbg + 3, 1ull); atomicMax(dbg + 4, (unsigned long long)n_f); }
       if (n_nm > 0) {
         const double LL = LLin[w];
         const double4 b4 = bbox2[w];
@@ -864,7 +863,6 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
     FOFB_LAUNCH_CHECK(h);
     na = select_flagged(h, cc_idx.p, fl, act, m, reinterpret_cast<int*>(scal_p + 8));
   }
-  FOFB_CUDA(cudaMemsetAsync(dbg_buf.alloc(8), 0, 64, st));
   pool_centre.alloc(mm);
   pool_off.alloc(mm);
   pool_len.alloc(mm);
@@ -966,8 +964,7 @@ void FofState::round_evaluate(fofb_handle* h) {
       }
       FOFB_PROFILED(h, "k_hop2", k_hop2<<<nr, kHop2Threads, 0, st>>>(nr, rb, nv_p, nF_p, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p,
                                       ismember.p, LLp, bb2, p, v2, mr, nml, fbatch, nm_sorted.alloc(tv), nM_p, pass_p, kill_target.p, alive.p,
-                                      decided.p, dbg_buf.p));
-      if (getenv("FOFB_DEBUG")) { unsigned long long d[8]; FOFB_CUDA(cudaMemcpy(d, dbg_buf.p, sizeof(d), cudaMemcpyDeviceToHost)); fprintf(stderr, "[hop2] round %d nr=%d total_v=%lld max_nv=%llu max_nnm=%llu sum_nnm=%llu centres_with_table=%llu max_nf=%llu\n", rounds, nr, total_v, d[0], d[1], d[2], d[3], d[4]); FOFB_CUDA(cudaMemset(dbg_buf.p, 0, sizeof(d))); }
+                                      decided.p));
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse
       long long* dst = ho;    // reuse

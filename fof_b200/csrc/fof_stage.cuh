@@ -47,7 +47,6 @@ struct FofState {
   DBuf<int> v2row, mrows, nm_list, first_batch;
   DBuf<double> cc_z, v2ra, v2dec, v2cos;
   DBuf<int> owner, nm_sorted;
-  DBuf<unsigned long long> dbg_buf;
   DBuf<unsigned char> ismember;
   DBuf<double> LL;
   DBuf<double4> bbox1, bbox2;

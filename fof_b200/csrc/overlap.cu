@@ -835,14 +835,6 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   }
   const int B = 256;
   const int wblocks = grid_for((int64_t)K * 32, 128);
-  if (getenv("FOFB_DEBUG")) {
-    double a[4], b[4]; int c0 = 0;
-    FOFB_CUDA(cudaStreamSynchronize(st));
-    FOFB_CUDA(cudaMemcpy(a, rra, sizeof(a), cudaMemcpyDeviceToHost));
-    FOFB_CUDA(cudaMemcpy(b, rdec, sizeof(b), cudaMemcpyDeviceToHost));
-    FOFB_CUDA(cudaMemcpy(&c0, merged.centre.p, sizeof(int), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[finish] K=%d first centre idx %d points ra %.12f %.12f dec %.12f %.12f gidx? %lld\n", K, c0, a[0], a[1], b[0], b[1], K_glob_merged);
-  }
   int* N_own = merged.N.alloc(K);
   double* D = merged.D.alloc(K);
   FOFB_PROFILED(h, "k_own_count", k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,

@@ -25,7 +25,6 @@ from .pipeline import Catalogue
 from .units import as_float
 
 C_KMS = 299792.458
-_DEBUG_LOCK = threading.Lock()
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -211,9 +210,18 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     Returns (offsets, member_global_rows, centre_global_row, N, D, props) of the GLOBAL final catalogue, identical
     on every rank, in the order the single-GPU run produces (plus the advanced (key, pos) when mt_state is given).
     """
+    import time
     import torch
     h = handle
     L = h.lib
+    _t = [time.perf_counter()]
+    phases = {}
+
+    def lap(name):
+        now = time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + 1e3 * (now - _t[0])
+        _t[0] = now
+
     p = params or _lib_params(None, None, None, None, None)
     zcut = zcut or (P.min_redshift, P.max_redshift + 0.02, P.max_redshift)
     local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
@@ -233,6 +241,7 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     g_src = np.empty(n_g, dtype=np.int32)
     h.check(L.fofb_dist_local_inputs(h.h, cen_rows.ctypes.data, cen_src.ctypes.data, g_src.ctypes.data, None))
 
+    lap("stage0")
     # global priority order of the centres
     parts = comm.allgatherv(np.column_stack([cen_rows, grow[cen_src].astype(np.float64)]) if m_loc else np.zeros((0, 9)))
     owner = np.concatenate([np.full(len(x), r, dtype=np.int32) for r, x in enumerate(parts)])
@@ -243,12 +252,14 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     owned = np.ascontiguousarray((owner[order] == rank).astype(np.uint8))
     m_glob = len(centres)
 
+    lap("gather_centres")
     bbox = np.empty(4)
     h.check(L.fofb_dist_prepare(h.h, centres.ctypes.data, m_glob, owned.ctypes.data, bbox.ctypes.data))
     lo = comm.allreduce(np.array([bbox[0], bbox[2]]), "min")
     hi = comm.allreduce(np.array([bbox[1], bbox[3]]), "max")
     gbbox = np.array([lo[0], hi[0], lo[1], hi[1]])
 
+    lap("prepare")
     # priority rounds, the tracker state merged after each
     dev = torch.device("cuda", h.device)
     alive = torch.empty(max(m_glob, 1), dtype=torch.uint8, device=dev)
@@ -269,6 +280,7 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     h.check(L.fofb_dist_finalize(h.h, C.byref(kc), C.byref(kt)))
     K_loc, tot_loc = kc.value, kt.value
 
+    lap("rounds")
     # stage 2 on the all-process cluster list
     lc = np.empty(K_loc, dtype=np.int32)
     loff = np.zeros(K_loc + 1, dtype=np.int64)
@@ -292,6 +304,7 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     else:
         ids_sorted = np.zeros(0)
     centre_sorted = np.ascontiguousarray(c_all[corder].astype(np.int32))
+    lap("gather_clusters")
     keep_glob = np.ones(K_glob, dtype=np.int32)
     h.check(L.fofb_dist_overlap(h.h, K_glob, centre_sorted.ctypes.data, off_sorted.ctypes.data, ids_sorted.ctypes.data,
                                 keep_glob.ctypes.data))
@@ -301,25 +314,18 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     keep_local = np.ascontiguousarray(keep_glob[mine_sorted].astype(np.int32))
     gidx_local = np.ascontiguousarray(gidx_of_sorted[mine_sorted & keep_glob].astype(np.int32))
     K_merged = int(keep_glob.sum())
-    import os
-    if os.environ.get('FOFB_DEBUG'):
-        print(f'[slabs rank {rank}] bbox local {bbox} global {gbbox} K_glob {K_glob} K_merged {K_merged} gidx_local {gidx_local[:8]}... n={len(gidx_local)} m_glob {m_glob} own {own} valid {valid}', flush=True)
     h.check(L.fofb_dist_set_merged(h.h, keep_local.ctypes.data, gidx_local.ctypes.data, K_merged, gbbox.ctypes.data))
 
+    lap("overlap")
     # stage 4 (every rank consumes the same np.random stream and uses its own clusters' blocks), stages 5-6
     new_state = None
-    import os
-    lock = _DEBUG_LOCK if os.environ.get("FOFB_SERIAL") else None
-    if lock:
-        lock.acquire()
     if mt_state is None:
         Kf, total = h.pipeline_finish_np_random()
     else:
         Kf, total, nkey, npos = h.pipeline_finish_mt(mt_state[0], mt_state[1])
         new_state = (nkey, npos)
-    if lock:
-        lock.release()
     off, rows, cidx, N, D, props = h.pipeline_fetch(Kf, total)
+    lap("finish")
     sizes = np.diff(off)
     # assemble the global catalogue in ascending centre priority
     f_c = comm.allgatherv(cidx)
@@ -337,7 +343,9 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     np.cumsum(fs[fo], out=out_off[1:])
     out_rows = (np.concatenate([allrows[fstarts[k]:fstarts[k] + fs[k]] for k in fo]) if len(fo) and out_off[-1]
                 else np.zeros(0, dtype=np.int64))
+    lap("gather_final")
     if timings is not None:
+        timings.update({"ms_" + k: round(v, 2) for k, v in phases.items()})
         timings.update(rounds=rounds, centres=m_glob, stage1_clusters=K_glob, merged=K_merged, local_rows=len(local_rows),
                        fof_rows=n_g)
     del keep
