@@ -98,11 +98,18 @@ struct GridAxis {
 // (ilo = clamp(digit(c - r)), ihi = clamp(digit(c + r))).  digit() is monotone, so the cell-box
 // test on a point is equivalent to lo <= x <= hi; the bounds are found by stepping single ulps
 // around the analytic cell edge until the exact predicate flips.
-__device__ __forceinline__ void grid_axis_bounds(const GridAxis& g, double c, double r, double* lo, double* hi) {
-  const int ilo = g.digit_clamped(__dsub_rn(c, r));
-  const int ihi = g.digit_clamped(__dadd_rn(c, r));
+//
+// `reach` >= the largest |x - c| a point can have and still pass the haversine test the box is always combined
+// with.  When c - reach falls in the same cell as c - r the lower side can never exclude such a point, so the
+// bound is -inf and the (division-heavy) edge search is skipped; likewise above.  This is the common case: an edge
+// must fall inside the sliver (r, reach] for the box to bind at all.
+__device__ __forceinline__ void grid_axis_bounds(const GridAxis& g, double c, double r, double reach, double* lo, double* hi) {
+  const double dlo = g.digit(__dsub_rn(c, r)), dhi = g.digit(__dadd_rn(c, r));
+  const double top = (double)(g.ncell - 1);
+  const int ilo = dlo < 0.0 ? 0 : (dlo > top ? g.ncell - 1 : (int)dlo);
+  const int ihi = dhi < 0.0 ? 0 : (dhi > top ? g.ncell - 1 : (int)dhi);
   const double w = (g.bN - g.b0) / g.ncell;
-  if (ilo <= 0) {
+  if (ilo <= 0 || (dlo <= top && g.digit(c - reach) == dlo)) {
     *lo = -INFINITY;  // every member of the grid's point set has digit >= 0
   } else {
     double x = g.b0 + ilo * w;
@@ -110,7 +117,7 @@ __device__ __forceinline__ void grid_axis_bounds(const GridAxis& g, double c, do
     for (int it = 0; it < 64 && g.digit(x) < (double)ilo; ++it) x = nextafter(x, INFINITY);
     *lo = x;
   }
-  if (ihi >= g.ncell - 1) {
+  if (ihi >= g.ncell - 1 || (dhi >= 0.0 && g.digit(c + reach) == dhi)) {
     *hi = INFINITY;
   } else {
     double x = g.b0 + (ihi + 1) * w;
@@ -131,13 +138,17 @@ struct BBox {  // bounding box of a point set: (ra_min, ra_max, dec_min, dec_max
   double ra_min, ra_max, dec_min, dec_max;
 };
 
+// The box of a bubble query (centre, r); only valid in conjunction with the haversine test d <= r.
 __device__ __forceinline__ Box grid_box(const BBox& bb, int ncell, double c_ra, double c_dec, double r) {
   GridAxis gx, gy;
   gx.init(bb.ra_min, bb.ra_max, ncell);
   gy.init(bb.dec_min, bb.dec_max, ncell);
   Box b;
-  grid_axis_bounds(gx, c_ra, r, &b.ra_lo, &b.ra_hi);
-  grid_axis_bounds(gy, c_dec, r, &b.dec_lo, &b.dec_hi);
+  // d <= r bounds |ddec| by r and |dra| by r / cos(|dec| + r) (1 % margin inside bubble_ra_reach)
+  const double dd = fmin(89.0, fabs(c_dec) + r);
+  const double reach_ra = 1.01 * r / cos(dd * kDeg2Rad) + 1e-12;
+  grid_axis_bounds(gx, c_ra, r, reach_ra, &b.ra_lo, &b.ra_hi);
+  grid_axis_bounds(gy, c_dec, r, r * (1.0 + 1e-9) + 1e-12, &b.dec_lo, &b.dec_hi);
   return b;
 }
 
