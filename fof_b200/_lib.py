@@ -91,6 +91,7 @@ def load():
         "fofb_dist_local_clusters": (C.c_int, [vp, vp, vp, vp]),
         "fofb_dist_overlap": (C.c_int, [vp, i64, vp, vp, vp, vp]),
         "fofb_dist_set_merged": (C.c_int, [vp, vp, vp, i64, vp]),
+        "fofb_pipeline_rerun": (C.c_int, [vp, dbl, i32, dbl, vp, P(i32), P(i64), P(i64)]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
@@ -261,6 +262,15 @@ class Handle:
                                               key.ctypes.data, C.byref(pos), C.byref(k), C.byref(t)))
         np.random.set_state(("MT19937", key, pos.value, has_gauss, cached))
         del keep
+        return k.value, t.value
+
+    def pipeline_rerun_np_random(self, linking_length_factor, richness, overdensity):
+        """Parameter sweep step on the catalogue of the last pipeline_run (stage 0 and the catalogue are reused)."""
+        key, pos, has_gauss, cached = self._numpy_mt_state()
+        k, t = C.c_int64(), C.c_int64()
+        self.check(self.lib.fofb_pipeline_rerun(self.h, float(linking_length_factor), int(richness), float(overdensity),
+                                                key.ctypes.data, C.byref(pos), C.byref(k), C.byref(t)))
+        np.random.set_state(("MT19937", key, pos.value, has_gauss, cached))
         return k.value, t.value
 
     def fof_fetch(self, which=3):

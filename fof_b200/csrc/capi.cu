@@ -580,6 +580,23 @@ int fofb_pipeline_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* g
   FOFB_CATCH(h)
 }
 
+int fofb_pipeline_rerun(fofb_handle* h, double linking_length_factor, int32_t richness, double overdensity, uint32_t* mt_key,
+                        int32_t* mt_pos, int64_t* n_final, int64_t* n_members) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  if (!h->pipe) throw fofb::Error(FOFB_ERR_STATE, "fofb_pipeline_rerun called before fofb_pipeline_run");
+  FOFB_REQUIRE(mt_key && mt_pos, "MT19937 state is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  Timed timer(h);
+  h->pipe->rerun(h, linking_length_factor, richness, overdensity, mt_key, *mt_pos);
+  h->pipe->finish(h, nullptr, 0, mt_key, mt_pos);
+  timer.stop();
+  if (n_final) *n_final = h->pipe->K_out;
+  if (n_members) *n_members = h->pipe->total_out;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
 int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
                         double* props) {
   if (!h) return FOFB_ERR_INVALID;

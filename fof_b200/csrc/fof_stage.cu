@@ -868,6 +868,30 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
   pool_len.alloc(mm);
 }
 
+// Start the rounds again on the prepared catalogue with other stage-1/2/4 parameters (linking_length_factor,
+// richness, overdensity): everything prepare() built depends only on max_velocity, the radii and the cosmology.
+void FofState::restart_rounds(fofb_handle* h, double linking_length_factor, int richness, double overdensity) {
+  cudaStream_t st = h->stream;
+  if (distributed) throw Error(FOFB_ERR_STATE, "parameter sweeps are not available in distributed runs");
+  params.linking_length_factor = linking_length_factor;
+  params.richness = richness;
+  params.overdensity = overdensity;
+  ran = finished = false;
+  candidates.K = merged.K = bcg.K = final_.K = 0;
+  candidates.total = merged.total = bcg.total = final_.total = 0;
+  pool_used = 0;
+  pool_K = 0;
+  rounds = 0;
+  evaluated = 0;
+  na = 0;
+  if (m == 0) return;
+  FOFB_CUDA(cudaMemsetAsync(alive.p, 1, (size_t)m, st));
+  FOFB_CUDA(cudaMemsetAsync(decided.p, 0, (size_t)m, st));
+  FOFB_CUDA(cudaMemcpyAsync(active_a.p, cc_idx.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToDevice, st));
+  act_in_a = true;
+  na = m;
+}
+
 // One round: find the active centres no alive, undecided predecessor can still claim, and evaluate them.
 void FofState::round_evaluate(fofb_handle* h) {
   cudaStream_t st = h->stream;

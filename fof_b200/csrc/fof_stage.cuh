@@ -66,6 +66,7 @@ struct FofState {
   void run(fofb_handle* h, const fofb_params& p, const View& G, const View& Cn);
   // the same in steps (the distributed driver merges alive/decided across processes between evaluate and advance)
   void prepare(fofb_handle* h, const fofb_params& p, const View& G, const View& Cn, const unsigned char* owned);
+  void restart_rounds(fofb_handle* h, double linking_length_factor, int richness, double overdensity);
   void round_evaluate(fofb_handle* h);
   void round_advance(fofb_handle* h);
   void finalize(fofb_handle* h);

@@ -10,6 +10,8 @@
 
 namespace fofb {
 
+void fof_overlap_and_bcg(fofb_handle* h, FofState& S);  // overlap.cu
+
 static unsigned char* cub_tmp(fofb_handle* h, size_t bytes) { return h->cub_tmp.alloc(bytes + 256); }
 
 template <class T>
@@ -132,6 +134,30 @@ void Pipeline::begin(fofb_handle* h, const fofb_params& p, const View& raw, doub
   fof.run(h, p, Gv, Cv);
   fof.last_K = fof.merged.K;
   began = true;
+}
+
+// Parameter sweep: stage 0, the catalogue, the cell lists and the per-centre scalars are reused; only
+// the priority rounds and what follows run again.
+void Pipeline::rerun(fofb_handle* h, double linking_length_factor, int richness, double overdensity, const unsigned* mt_key,
+                     int mt_pos) {
+  if (!began || dist) throw Error(FOFB_ERR_STATE, "fofb_pipeline_rerun needs a completed single-process fofb_pipeline_begin / run");
+  finished = false;
+  params.linking_length_factor = linking_length_factor;
+  params.richness = richness;
+  params.overdensity = overdensity;
+  if (mt_key) {
+    fof.params_n_random_hint = params.n_random;
+    fof.mt_prefetch(h, mt_key, mt_pos, (long long)(fof.last_K * 1.25) + 256);
+  }
+  fof.restart_rounds(h, linking_length_factor, richness, overdensity);
+  while (fof.na > 0) {
+    fof.round_evaluate(h);
+    fof.round_advance(h);
+  }
+  fof.finalize(h);
+  fof_overlap_and_bcg(h, fof);
+  fof.ran = true;
+  fof.last_K = fof.merged.K;
 }
 
 // Distributed variant: this process holds a redshift slab plus halos.  Rows with z in [valid_lo, valid_hi] have

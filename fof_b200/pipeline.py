@@ -74,3 +74,29 @@ def find_clusters(galaxy_data, max_velocity=None, linking_length_factor=None, vi
         h.pipeline_begin(g, p, zmin, zmax + 0.02, zmax)
         Kf, total = h.pipeline_finish(uniforms)
     return Catalogue(g, *h.pipeline_fetch(Kf, total))
+
+
+def sweep(galaxy_data, linking_length_factors, richness=None, overdensity=None, max_velocity=None, virial_radius=None,
+          min_redshift=None, max_redshift=None, device=0):
+    """The thesis' tuning loop (README.md:21; BASELINE.json configs[2]): one catalogue, several linking-length
+    factors.  Stage 0, the z-sorted catalogue, the cell lists and the per-centre scalars are built once; every further
+    factor reruns only the priority rounds and what follows.  Returns {b: Catalogue}."""
+    g = _as_matrix(galaxy_data)
+    h = _lib.get_handle(device)
+    rich = int(P.richness if richness is None else richness)
+    od = float(P.D if overdensity is None else overdensity)
+    p = _lib.default_params(
+        H0=P.cosmo.H0, Om0=P.cosmo.Om0, Ode0=P.cosmo.Ode0,
+        max_velocity=as_float(P.max_velocity if max_velocity is None else max_velocity, "km/s"),
+        virial_radius=as_float(P.max_radius if virial_radius is None else virial_radius), richness=rich, overdensity=od,
+        linking_length_factor=float(linking_length_factors[0]))
+    zmin = P.min_redshift if min_redshift is None else min_redshift
+    zmax = P.max_redshift if max_redshift is None else max_redshift
+    out = {}
+    for i, b in enumerate(linking_length_factors):
+        if i == 0:
+            Kf, total = h.pipeline_run_np_random(g, p, zmin, zmax + 0.02, zmax)
+        else:
+            Kf, total = h.pipeline_rerun_np_random(b, rich, od)
+        out[float(b)] = Catalogue(g, *h.pipeline_fetch(Kf, total))
+    return out

@@ -183,6 +183,11 @@ int fofb_pipeline_finish_mt(fofb_handle* h, uint32_t* mt_key, int32_t* mt_pos, i
 /* begin + finish_mt in one call; the MT19937 stream is generated on a side stream while stages 0-3 run */
 int fofb_pipeline_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double zmin, double zmax_gal,
                       double zmax_cen, uint32_t* mt_key, int32_t* mt_pos, int64_t* n_final, int64_t* n_members);
+/* parameter sweep on the catalogue of the last fofb_pipeline_run / begin: stage 0 and everything that depends only on
+ * max_velocity, the radii and the cosmology is reused; the rounds, overlap removal, selection, interloper removal and
+ * masses run again with the new linking_length_factor / richness / overdensity (the thesis tuned exactly these). */
+int fofb_pipeline_rerun(fofb_handle* h, double linking_length_factor, int32_t richness, double overdensity, uint32_t* mt_key,
+                        int32_t* mt_pos, int64_t* n_final, int64_t* n_members);
 int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
                         double* props);
 /* sizes seen by the last pipeline run: galaxies after the z cut, candidate centres, stage-1 candidate clusters,

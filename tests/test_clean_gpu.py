@@ -78,3 +78,20 @@ def test_whole_job_equals_staged_facade(lib, n, seed):
             assert abs(cat.props[k, j] - r[key]) <= REL * abs(r[key]), (key, cat.props[k, j], r[key])
     lab = cat.labels()
     assert lab.shape == (n,) and (lab >= -1).all()
+
+
+def test_parameter_sweep_reuses_stage0_and_matches_fresh_runs(lib):
+    """pipeline.sweep (fofb_pipeline_rerun) == independent runs for every linking-length factor."""
+    from fof_b200 import pipeline
+    arr = make_catalog(30000, seed=31, as_frame=False)
+    bs = [0.2, 0.05, 0.4, 0.1]
+    np.random.seed(11)
+    swept = pipeline.sweep(arr, bs)
+    np.random.seed(11)
+    for b in bs:
+        fresh = pipeline.find_clusters(arr, linking_length_factor=b)
+        s = swept[b]
+        assert np.array_equal(s.offsets, fresh.offsets) and np.array_equal(s.member_rows, fresh.member_rows)
+        assert np.array_equal(s.centre_row, fresh.centre_row)
+        assert np.array_equal(s.N, fresh.N) and np.array_equal(s.D, fresh.D)
+        np.testing.assert_allclose(s.props, fresh.props, rtol=1e-12)
