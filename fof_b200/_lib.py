@@ -92,6 +92,7 @@ def load():
         "fofb_dist_overlap": (C.c_int, [vp, i64, vp, vp, vp, vp]),
         "fofb_dist_set_merged": (C.c_int, [vp, vp, vp, i64, vp]),
         "fofb_pipeline_rerun": (C.c_int, [vp, dbl, i32, dbl, vp, P(i32), P(i64), P(i64)]),
+        "fofb_bubble_count": (C.c_int, [vp, P(Params), P(Matrix), i64, vp, vp, i32, dbl, vp]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
@@ -365,6 +366,18 @@ class Handle:
         m, keep = matrix_of(members)
         out = np.empty((K, 2))
         self.check(self.lib.fofb_projected_mass(self.h, C.byref(params), K, off.ctypes.data, C.byref(m), out.ctypes.data))
+        del keep
+        return out
+
+    def bubble_count(self, points, centres, radius_deg, params, window_z=None):
+        """Counts of GriSPy(points[window]).bubble_neighbors(centres, radius) (haversine, degrees)."""
+        m, keep = matrix_of(points)
+        cen = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius_deg, dtype=np.float64), (len(cen),)))
+        out = np.empty(len(cen), dtype=np.int32)
+        self.check(self.lib.fofb_bubble_count(self.h, C.byref(params), C.byref(m), len(cen), cen.ctypes.data, rad.ctypes.data,
+                                              0 if window_z is None else 1, 0.0 if window_z is None else float(window_z),
+                                              out.ctypes.data))
         del keep
         return out
 

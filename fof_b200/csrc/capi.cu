@@ -8,6 +8,7 @@
 #include "clean.cuh"
 #include "pipeline.cuh"
 #include "transitive.cuh"
+#include "bubble.cuh"
 
 namespace fofb {
 void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total,
@@ -184,6 +185,8 @@ void fofb_destroy(fofb_handle* h) {
   h->pipe = nullptr;
   delete h->trans;
   h->trans = nullptr;
+  delete h->bubble;
+  h->bubble = nullptr;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -833,6 +836,28 @@ int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_
   P.fof.global_bbox = BBox{global_bbox4[0], global_bbox4[1], global_bbox4[2], global_bbox4[3]};
   P.fof.ran = true;
   P.began = true;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+// ---- helper-level bubble counts ------------------------------------------------------------------------------
+int fofb_bubble_count(fofb_handle* h, const fofb_params* p, const fofb_matrix* points, int64_t n_centres, const double* centres,
+                      const double* radius_deg, int32_t use_window, double window_z, int32_t* counts) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(points && centres && radius_deg && counts && n_centres >= 0 && n_centres < (1ll << 26), "bubble count: bad argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->bubble) h->bubble = new Bubble();
+  Timed timer(h);
+  View v;
+  if (points->rows > 0) {
+    v = to_device(h, *points, h->upload);
+  } else {
+    v.rows = 0; v.cols = points->cols;
+  }
+  h->bubble->count(h, *p, v, (int)n_centres, centres, radius_deg, use_window, window_z, counts);
+  timer.stop();
   return FOFB_OK;
   FOFB_CATCH(h)
 }

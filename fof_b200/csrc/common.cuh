@@ -95,6 +95,7 @@ struct FofState;   // fof_stage.cu
 struct CleanState; // clean.cu
 struct Pipeline;   // pipeline.cu
 struct Transitive; // transitive.cu
+struct Bubble;     // bubble.cu
 
 }  // namespace fofb
 
@@ -137,6 +138,7 @@ struct fofb_handle {
   fofb::CleanState* clean = nullptr;
   fofb::Pipeline* pipe = nullptr;
   fofb::Transitive* trans = nullptr;
+  fofb::Bubble* bubble = nullptr;
   fofb::DBuf<unsigned char> cub_tmp;
   fofb::DBuf<double> upload;      // staging for host matrices
   fofb::DBuf<double> upload2;

@@ -226,6 +226,13 @@ int fofb_dist_overlap(fofb_handle* h, int64_t K, const int32_t* centre, const in
 int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_t* global_index, int64_t n_global_merged,
                          const double* global_bbox4);
 
+/* ---- helper-level bubble counts: GriSPy(points).bubble_neighbors(centres, r) as counts --------------------------
+ * find_number_count (helper.py:149-188) and the 300-point counts of center_overdensity (helper.py:207-216).  The grid
+ * is built on the rows of `points` (ra, dec[, z]) that lie in the velocity window of `window_z` when use_window != 0
+ * (p->max_velocity), else on all rows.  centres[2q], radius_deg[q], counts[q] are host arrays. */
+int fofb_bubble_count(fofb_handle* h, const fofb_params* p, const fofb_matrix* points, int64_t n_centres, const double* centres,
+                      const double* radius_deg, int32_t use_window, double window_z, int32_t* counts);
+
 /* ---- transitive friends-of-friends (connected components) ------------------------------------------------------
  * NOT a reference code path (kencx/FoF never computes connected components): the lock-free
  * union-find mode named in BASELINE.json.  Galaxies i, j are friends iff each lies in the other's velocity window

@@ -89,3 +89,24 @@ def test_device_mt19937_leaves_np_random_where_the_reference_would(lib, handle):
         ra, dec = fof.draw_overdensity_points(K_stage4, (g[:, 0].min(), g[:, 0].max(), g[:, 1].min(), g[:, 1].max()))
         assert np.array_equal(after, np.random.random_sample(3))
         assert K <= K_stage4
+
+
+def test_helper_functions_match_the_oracle(lib):
+    """helper.find_number_count / center_overdensity / setdiff2d with the reference's names and semantics."""
+    from fof_b200 import helper
+    g, c = _inputs(6000, 2, "cosmos", 50000.0)
+    rng = np.random.default_rng(4)
+    for i in rng.integers(0, len(c), 12):
+        centre = c[i]
+        mask = np.abs(O.redshift_to_velocity(g[:, 2], centre[2])) <= 2000.0
+        vb = g[mask]
+        want = O.find_number_count(centre[0], centre[1], centre[2], vb[:, 0], vb[:, 1], 0.5)
+        assert helper.find_number_count(centre, vb[:, :2]) == want
+        assert want == centre[7]  # the N(0.5) column itself
+    cl = O.Cluster(c[0], g[:50])
+    np.random.seed(3)
+    want = O.center_overdensity(cl, g, O.Params())
+    np.random.seed(3)
+    got = helper.center_overdensity(cl, g, 2000.0)
+    assert got == want
+    assert np.array_equal(helper.setdiff2d(g[:10], g[5:20]), g[:5])
