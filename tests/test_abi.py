@@ -108,3 +108,34 @@ def test_cluster_types_mirror_the_reference():
     assert cc.properties.shape == (11,) and cc.properties[3] == 1e14
     from fof_b200.params import cosmo
     assert 0.1 < float(cc.r200(cosmo, 200)) < 5.0
+
+
+def test_cluster_objects_pickle_like_the_reference_pipeline():
+    """pipeline.py:103-104,119-120,175-176 pickles the cluster lists between stages."""
+    import pickle
+    from fof_b200.cluster import Cluster, CleanedCluster
+    from fof_b200.units import Q
+    c = Cluster(np.arange(8.0), np.ones((3, 8)))
+    c.D = 2.5
+    c2 = pickle.loads(pickle.dumps(c))
+    assert c2.gal_id == 6.0 and c2.D == 2.5 and np.array_equal(c2.galaxies, c.galaxies)
+    cc = CleanedCluster(np.arange(8.0), np.ones((3, 8)), Q(1e14, "Msun/littleh"), Q(1e13), Q(5e5), Q(1e4), Q(0.7), -26.0)
+    cc2 = pickle.loads(pickle.dumps(cc))
+    assert float(cc2.cluster_mass) == 1e14 and cc2.cluster_mass.unit == "Msun/littleh" and cc2.total_absmag == -26.0
+
+
+def test_units_accept_plain_numbers_and_quantity_likes():
+    from fof_b200.units import Q, as_float
+
+    class FakeQuantity:  # astropy-like: has .to(unit).value
+        def __init__(self, v):
+            self.value = v
+
+        def to(self, unit):
+            return FakeQuantity(self.value * 1000.0) if unit == "km/s" else self
+
+    assert as_float(2000.0) == 2000.0 and as_float(Q(1.5, "Mpc/littleh")) == 1.5
+    assert as_float(FakeQuantity(2.0), "km/s") == 2000.0
+    from fof_b200 import params
+    assert (params.min_redshift, params.max_redshift, float(params.max_velocity), params.linking_length_factor,
+            float(params.max_radius), params.richness, params.D) == (0.5, 2.5, 2000.0, 0.2, 1.5, 12, 2)
