@@ -48,6 +48,24 @@ class Cluster:
     def __str__(self):
         return f"Cluster at ({self.ra:.2f},{self.dec:.2f},{self.z:.2f}) with {self.richness} galaxies"
 
+    # pipeline.py pickles the cluster lists between stages; the slot named ``properties`` is shadowed by a
+    # read-only property in CleanedCluster, which the default slot pickling cannot restore
+    def __getstate__(self):
+        state = {}
+        for cls in type(self).__mro__:
+            for name in getattr(cls, "__slots__", ()):
+                if isinstance(getattr(type(self), name, None), property) or name in state:
+                    continue
+                try:
+                    state[name] = object.__getattribute__(self, name)
+                except AttributeError:
+                    pass
+        return state
+
+    def __setstate__(self, state):
+        for name, value in state.items():
+            setattr(self, name, value)
+
 
 class CleanedCluster(Cluster):
     """cluster.py:88-136.  Quantity-valued fields are ``units.Q`` floats (``.value`` works)."""
