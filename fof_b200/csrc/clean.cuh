@@ -12,6 +12,7 @@ struct CleanState {
   DBuf<unsigned> d_mt;
   DBuf<double4> d_trig;
   size_t mt_len = 0;
+  size_t clip_smem_set = 0;
   // device-resident cores: results stay in d_out_off (K+1) / d_out_index; returns the kept total
   long long three_sigma_core(fofb_handle* h, const fofb_params& p, int K, const long long* d_off_in, long long total,
                              const View& M, const double* d_cen_in, int nbins);

@@ -4,6 +4,8 @@
 // member has been decided (kernels K7-K9 of DESIGN.md).
 #include <cub/cub.cuh>
 
+#include <ctime>
+
 #include "fof_stage.cuh"
 
 namespace fofb {
@@ -719,14 +721,29 @@ static void segmented_sort(fofb_handle* h, const unsigned long long* in, unsigne
 
 void fof_overlap_and_bcg(fofb_handle* h, FofState& S);  // overlap.cu
 
+// wall-clock of the steps of one run, for FOFB_TRACE=1 (diagnostics only)
+static double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 void FofState::run(fofb_handle* h, const fofb_params& p, const View& G_in, const View& Cn_in) {
+  const bool trace = getenv("FOFB_TRACE") != nullptr;
+  double t0 = trace ? now_ms() : 0.0;
   prepare(h, p, G_in, Cn_in, nullptr);
+  if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[trace] prepare %.2f ms (m=%d)\n", now_ms() - t0, m); t0 = now_ms(); }
   while (na > 0) {
+    const int na0 = na;
+    const long long ev0 = evaluated;
     round_evaluate(h);
     round_advance(h);
+    if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[trace] round %d: active %d evaluated %lld -> %.2f ms\n", rounds, na0, evaluated - ev0, now_ms() - t0); t0 = now_ms(); }
   }
   finalize(h);
+  if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[trace] finalize %.2f ms\n", now_ms() - t0); t0 = now_ms(); }
   fof_overlap_and_bcg(h, *this);
+  if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[trace] overlap+bcg %.2f ms (K=%d)\n", now_ms() - t0, candidates.K); }
   ran = true;
 }
 

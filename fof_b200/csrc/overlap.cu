@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 
 #include <cstring>
+#include <ctime>
 
 #include "fof_stage.cuh"
 
@@ -743,7 +744,16 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
     params_n_random_hint = npts;
     mt_prefetch(h, key_host, *pos_host, K_stream);
   }
+  const bool trace = getenv("FOFB_TRACE") != nullptr;
+  timespec t_a, t_b;
+  if (trace) { cudaStreamSynchronize(st); clock_gettime(CLOCK_MONOTONIC, &t_a); }
   FOFB_CUDA(cudaStreamWaitEvent(st, rng_done, 0));
+  if (trace) {
+    cudaStreamSynchronize(st);
+    clock_gettime(CLOCK_MONOTONIC, &t_b);
+    fprintf(stderr, "[trace]   waited %.2f ms for the MT19937 stream (%lld blocks prefetched)\n",
+            (t_b.tv_sec - t_a.tv_sec) * 1e3 + (t_b.tv_nsec - t_a.tv_nsec) * 1e-6, mt_blocks);
+  }
   const long long need_blocks = W > mt_head ? (W - mt_head + 623) / 624 : 0;
   if (need_blocks > mt_blocks) {  // the speculation fell short: continue from the last generated state
     const long long extra = need_blocks - mt_blocks;

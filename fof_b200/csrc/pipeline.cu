@@ -2,6 +2,8 @@
 // removal -> virial masses) with every intermediate kept on the device.  This is what bench.py times.
 #include <cub/cub.cuh>
 
+#include <ctime>
+
 #include "catalog_host.cuh"
 #include "clean.cuh"
 #include "fof_stage.cuh"
@@ -185,8 +187,16 @@ void Pipeline::stage0_and_inputs(fofb_handle* h, const fofb_params& p, const Vie
     fof.mt_prefetch(h, mt_key, mt_pos, k_spec);
   }
   FOFB_REQUIRE(raw.cols == 7, "the pipeline expects the 7 input columns ra, dec, z, z_lower, z_upper, RMag, ID");
+  const bool trace = getenv("FOFB_TRACE") != nullptr;
+  timespec t_a, t_b;
+  if (trace) { cudaStreamSynchronize(st); clock_gettime(CLOCK_MONOTONIC, &t_a); }
   cat.build(h, raw);
   s0.run(h, p, cat, cells);
+  if (trace) {
+    cudaStreamSynchronize(st);
+    clock_gettime(CLOCK_MONOTONIC, &t_b);
+    fprintf(stderr, "[trace] stage 0 %.2f ms\n", (t_b.tv_sec - t_a.tv_sec) * 1e3 + (t_b.tv_nsec - t_a.tv_nsec) * 1e-6);
+  }
   const int n = (int)cat.n;
   n_in = n;
   // galaxies that enter FoF()
@@ -231,8 +241,17 @@ void Pipeline::finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key
   const int B = 256;
   if (!began) throw Error(FOFB_ERR_STATE, "fofb_pipeline_finish called before fofb_pipeline_begin");
   const fofb_params& p = params;
+  const bool trace = getenv("FOFB_TRACE") != nullptr;
+  timespec t_a, t_b;
+  if (trace) { cudaStreamSynchronize(st); clock_gettime(CLOCK_MONOTONIC, &t_a); }
   if (mt_key) fof.finish_mt(h, mt_key, mt_pos);
   else fof.finish_unit(h, u, mem);
+  if (trace) {
+    cudaStreamSynchronize(st);
+    clock_gettime(CLOCK_MONOTONIC, &t_b);
+    fprintf(stderr, "[trace] stage 4 %.2f ms\n", (t_b.tv_sec - t_a.tv_sec) * 1e3 + (t_b.tv_nsec - t_a.tv_nsec) * 1e-6);
+    t_a = t_b;
+  }
   K_out = 0;
   total_out = 0;
   finished = true;
@@ -289,6 +308,11 @@ void Pipeline::finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key
   FOFB_LAUNCH_CHECK(h);
   k_map_rows<<<grid_for(total_out, B), B, 0, st>>>(total_out, grow, g_src.p, out_rows.alloc((size_t)total_out));
   FOFB_LAUNCH_CHECK(h);
+  if (trace) {
+    cudaStreamSynchronize(st);
+    clock_gettime(CLOCK_MONOTONIC, &t_b);
+    fprintf(stderr, "[trace] stages 5-6 %.2f ms\n", (t_b.tv_sec - t_a.tv_sec) * 1e3 + (t_b.tv_nsec - t_a.tv_nsec) * 1e-6);
+  }
 }
 
 }  // namespace fofb

@@ -12,9 +12,7 @@ arr = make_catalog(n, seed=20260103, as_frame=False)
 np.random.seed(1)
 for it in range(reps):
     h.profile(2)
-    K = h.pipeline_begin(arr, p, 0.5, 2.52, 2.5)
-    u = np.random.random_sample((K, 2, 300))
-    Kf, tot = h.pipeline_finish(u)
+    Kf, tot = h.pipeline_run_np_random(arr, p, 0.5, 2.52, 2.5)
     h.profile(0)
     res = h.pipeline_fetch(Kf, tot)
 prof = h.profile_read()
