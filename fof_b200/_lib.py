@@ -93,6 +93,9 @@ def load():
         "fofb_dist_set_merged": (C.c_int, [vp, vp, vp, i64, vp]),
         "fofb_pipeline_rerun": (C.c_int, [vp, dbl, i32, dbl, vp, P(i32), P(i64), P(i64)]),
         "fofb_bubble_count": (C.c_int, [vp, P(Params), P(Matrix), i64, vp, vp, i32, dbl, vp]),
+        "fofb_dist_prefetch_mt": (C.c_int, [vp, vp, i32, i64]),
+        "fofb_dist_local_clusters_dev": (C.c_int, [vp, vp, vp, vp]),
+        "fofb_dist_overlap_rows": (C.c_int, [vp, i64, vp, vp, i64, vp, vp]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),
         "fofb_fof_fetch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "fofb_fof_stats": (C.c_int, [vp, P(i64), P(i64)]),
@@ -341,6 +344,19 @@ class Handle:
         props = np.empty((K, 8))
         self.check(self.lib.fofb_pipeline_fetch(self.h, off.ctypes.data, rows.ctypes.data, cen.ctypes.data,
                                                 N.ctypes.data, D.ctypes.data, props.ctypes.data))
+        return off, rows, cen, N, D, props
+
+    def pipeline_fetch_torch(self, K, total, device):
+        """The same as pipeline_fetch into torch tensors on ``device`` (no host round trip)."""
+        import torch
+        off = torch.zeros(K + 1, dtype=torch.int64, device=device)
+        rows = torch.empty(max(total, 1), dtype=torch.int32, device=device)[:total]
+        cen = torch.empty(max(K, 1), dtype=torch.int32, device=device)[:K]
+        N = torch.empty(max(K, 1), dtype=torch.float64, device=device)[:K]
+        D = torch.empty(max(K, 1), dtype=torch.float64, device=device)[:K]
+        props = torch.empty((max(K, 1), 8), dtype=torch.float64, device=device)[:K]
+        self.check(self.lib.fofb_pipeline_fetch(self.h, off.data_ptr(), rows.data_ptr(), cen.data_ptr(), N.data_ptr(),
+                                                D.data_ptr(), props.data_ptr()))
         return off, rows, cen, N, D, props
 
     def pipeline_stats(self):

@@ -13,6 +13,8 @@
 namespace fofb {
 void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total,
                           const double* ids, int* keep_out);
+void fof_overlap_external_rows(fofb_handle* h, FofState& S, int K, const double* centre_rows, const long long* off, long long total,
+                               const double* ids, int* keep_out);
 void fof_set_merged(fofb_handle* h, FofState& S, const int* keep_local);
 }
 
@@ -613,12 +615,12 @@ int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, 
     if (offsets) offsets[0] = 0;
     return FOFB_OK;
   }
-  if (offsets) FOFB_CUDA(cudaMemcpyAsync(offsets, P.out_off.p, sizeof(int64_t) * (K + 1), cudaMemcpyDeviceToHost, st));
-  if (member_rows) FOFB_CUDA(cudaMemcpyAsync(member_rows, P.out_rows.p, sizeof(int32_t) * P.total_out, cudaMemcpyDeviceToHost, st));
-  if (centre_row) FOFB_CUDA(cudaMemcpyAsync(centre_row, P.out_centre.p, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, st));
-  if (N) FOFB_CUDA(cudaMemcpyAsync(N, P.out_N.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
-  if (D) FOFB_CUDA(cudaMemcpyAsync(D, P.out_D.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
-  if (props) FOFB_CUDA(cudaMemcpyAsync(props, P.props.p, sizeof(double) * K * 8, cudaMemcpyDeviceToHost, st));
+  if (offsets) FOFB_CUDA(cudaMemcpyAsync(offsets, P.out_off.p, sizeof(int64_t) * (K + 1), cudaMemcpyDefault, st));
+  if (member_rows) FOFB_CUDA(cudaMemcpyAsync(member_rows, P.out_rows.p, sizeof(int32_t) * P.total_out, cudaMemcpyDefault, st));
+  if (centre_row) FOFB_CUDA(cudaMemcpyAsync(centre_row, P.out_centre.p, sizeof(int32_t) * K, cudaMemcpyDefault, st));
+  if (N) FOFB_CUDA(cudaMemcpyAsync(N, P.out_N.p, sizeof(double) * K, cudaMemcpyDefault, st));
+  if (D) FOFB_CUDA(cudaMemcpyAsync(D, P.out_D.p, sizeof(double) * K, cudaMemcpyDefault, st));
+  if (props) FOFB_CUDA(cudaMemcpyAsync(props, P.props.p, sizeof(double) * K * 8, cudaMemcpyDefault, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
   return FOFB_OK;
   FOFB_CATCH(h)
@@ -656,15 +658,27 @@ int fofb_dist_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* gal
   FOFB_CATCH(h)
 }
 
+/* start generating the MT19937 stream for about k_spec clusters on the side stream (overlaps the rounds) */
+int fofb_dist_prefetch_mt(fofb_handle* h, const uint32_t* mt_key, int32_t mt_pos, int64_t k_spec) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  P.fof.params_n_random_hint = P.params.n_random;
+  P.fof.mt_prefetch(h, mt_key, mt_pos, k_spec);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
 int fofb_dist_local_inputs(fofb_handle* h, double* centre_rows, int32_t* centre_src_row, int32_t* fof_src_row, double* bbox4) {
   if (!h) return FOFB_ERR_INVALID;
   FOFB_TRY(h)
   Pipeline& P = dist_pipe(h);
   FOFB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  if (centre_rows && P.m_c) FOFB_CUDA(cudaMemcpyAsync(centre_rows, P.c_rows.p, sizeof(double) * 8 * P.m_c, cudaMemcpyDeviceToHost, st));
-  if (centre_src_row && P.m_c) FOFB_CUDA(cudaMemcpyAsync(centre_src_row, P.c_src.p, sizeof(int32_t) * P.m_c, cudaMemcpyDeviceToHost, st));
-  if (fof_src_row && P.n_g) FOFB_CUDA(cudaMemcpyAsync(fof_src_row, P.g_src.p, sizeof(int32_t) * P.n_g, cudaMemcpyDeviceToHost, st));
+  if (centre_rows && P.m_c) FOFB_CUDA(cudaMemcpyAsync(centre_rows, P.c_rows.p, sizeof(double) * 8 * P.m_c, cudaMemcpyDefault, st));
+  if (centre_src_row && P.m_c) FOFB_CUDA(cudaMemcpyAsync(centre_src_row, P.c_src.p, sizeof(int32_t) * P.m_c, cudaMemcpyDefault, st));
+  if (fof_src_row && P.n_g) FOFB_CUDA(cudaMemcpyAsync(fof_src_row, P.g_src.p, sizeof(int32_t) * P.n_g, cudaMemcpyDefault, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
   (void)bbox4;
   return FOFB_OK;
@@ -805,6 +819,34 @@ int fofb_dist_overlap(fofb_handle* h, int64_t K, const int32_t* centre, const in
   FOFB_CATCH(h)
 }
 
+/* stage 2 on the all-process cluster list given as DEVICE arrays ordered by priority: centre_rows[K x 8], offsets[K+1],
+ * ids[total]; keep[K] (device, int32) out */
+int fofb_dist_overlap_rows(fofb_handle* h, int64_t K, const double* centre_rows, const int64_t* offsets, int64_t total,
+                           const double* ids, int32_t* keep) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(K >= 0 && K < (1ll << 31), "fofb_dist_overlap_rows: bad K");
+  if (K == 0) return FOFB_OK;
+  FOFB_REQUIRE(centre_rows && offsets && ids && keep, "fofb_dist_overlap_rows: null argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  fof_overlap_external_rows(h, P.fof, (int)K, centre_rows, reinterpret_cast<const long long*>(offsets), total, ids, keep);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+/* member ids (column 6) and sizes of the local stage-1 clusters as DEVICE arrays: centre[K] (int32 local centre index),
+ * sizes[K] (int64), ids[total] (float64) */
+int fofb_dist_local_clusters_dev(fofb_handle* h, int32_t* centre, int64_t* sizes, double* ids) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  P.export_local_clusters(h, centre, reinterpret_cast<long long*>(sizes), ids);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
 /* keep_local[K_local]; global_index[number kept] = position of each kept local cluster in the all-process merged list */
 int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_t* global_index, int64_t n_global_merged,
                          const double* global_bbox4) {
@@ -818,7 +860,7 @@ int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_
   if (K > 0) {
     FOFB_REQUIRE(keep_local, "fofb_dist_set_merged: null flags");
     int* kd = P.keep_dev.alloc((size_t)K);
-    FOFB_CUDA(cudaMemcpyAsync(kd, keep_local, sizeof(int32_t) * K, cudaMemcpyHostToDevice, st));
+    FOFB_CUDA(cudaMemcpyAsync(kd, keep_local, sizeof(int32_t) * K, cudaMemcpyDefault, st));
     fof_set_merged(h, P.fof, kd);
     kept = P.fof.merged.K;
   } else {
@@ -827,7 +869,7 @@ int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_
   }
   if (kept > 0) {
     FOFB_REQUIRE(global_index, "fofb_dist_set_merged: null indices");
-    FOFB_CUDA(cudaMemcpyAsync(P.fof.merged_gidx.alloc(kept), global_index, sizeof(int32_t) * kept, cudaMemcpyHostToDevice, st));
+    FOFB_CUDA(cudaMemcpyAsync(P.fof.merged_gidx.alloc(kept), global_index, sizeof(int32_t) * kept, cudaMemcpyDefault, st));
   }
   FOFB_CUDA(cudaStreamSynchronize(st));
   P.fof.K_glob_merged = n_global_merged;

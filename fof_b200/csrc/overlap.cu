@@ -43,7 +43,8 @@ struct OverlapScratch {
   DBuf<unsigned long long> ekey, ekey_sorted, lkey, lkey_sorted;
   DBuf<double4> bbox;
   DBuf<unsigned char> keep;
-  DBuf<int> sel, selcount;
+  DBuf<int> sel, selcount, attr_iota;
+  DBuf<double> attr;
 };
 
 __global__ void k_iota(int n, int* out) {
@@ -329,10 +330,35 @@ static OverlapScratch& scratch(FofState& S) {
   return *static_cast<OverlapScratch*>(S.overlap_scratch);
 }
 
+struct CentreAttrs {  // per-centre scalars stage 2 reads, indexed by the cluster list's centre index
+  const double *ra, *dec, *cos, *z, *thvir, *N, *mag, *id;
+};
+
+static CentreAttrs attrs_of(const FofState& S) {
+  return CentreAttrs{S.c_ra.p, S.c_dec.p, S.c_cos.p, S.c_z.p, S.c_thvir.p, S.c_N.p, S.c_mag.p, S.c_id.p};
+}
+
+// centre rows (8 columns) -> the scalars of CentreAttrs (fof.py:277-279; cluster.py:29-38)
+__global__ void k_attrs_from_rows(int K, const double* rows, Cosmo cosmo, double virial_radius, double* ra, double* dec,
+                                  double* cs, double* z, double* thvir, double* N, double* mag, double* id, int* iota) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const double* r = rows + 8LL * k;
+  ra[k] = r[0];
+  dec[k] = r[1];
+  cs[k] = cos(__dmul_rn(r[1], kDeg2Rad));
+  z[k] = r[2];
+  thvir[k] = cosmo_linear_to_angular_dist(cosmo, virial_radius, r[2]);
+  mag[k] = r[5];
+  id[k] = r[6];
+  N[k] = r[7];
+  iota[k] = k;
+}
+
 // Stage 2 on an arbitrary cluster list (centre index per cluster, CSR offsets, member ids): returns a device array of
 // K keep flags (non-zero = survives the contests).  `ext_ids` == nullptr: ids are column 6 of S.G at `rows`.
-static int* overlap_keep_flags(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total_members,
-                               const int* rows, const double* ext_ids) {
+static int* overlap_keep_flags(fofb_handle* h, FofState& S, const CentreAttrs& A, int K, const int* centre, const long long* off,
+                               long long total_members, const int* rows, const double* ext_ids) {
   cudaStream_t st = h->stream;
   OverlapScratch& sc = scratch(S);
   const int B = 256;
@@ -340,7 +366,7 @@ static int* overlap_keep_flags(fofb_handle* h, FofState& S, int K, const int* ce
   const fofb_params& p = S.params;
   size_t bytes = 0;
   // clusters sorted by centre redshift -> velocity windows over the candidate list
-  k_cluster_z<<<grid_for(K, B), B, 0, st>>>(K, centre, S.c_z.p, S.c_id.p, sc.kz.alloc(K), sc.kidx.alloc(K),
+  k_cluster_z<<<grid_for(K, B), B, 0, st>>>(K, centre, A.z, A.id, sc.kz.alloc(K), sc.kidx.alloc(K),
                                             sc.idk.alloc(K), sc.idv.alloc(K));
   FOFB_LAUNCH_CHECK(h);
   sc.kz_sorted.alloc(K); sc.kidx_sorted.alloc(K); sc.idk_sorted.alloc(K); sc.idv_sorted.alloc(K);
@@ -353,8 +379,8 @@ static int* overlap_keep_flags(fofb_handle* h, FofState& S, int K, const int* ce
   // events
   const int wblocks = grid_for((int64_t)K * 32, 128);
   int* ecount = sc.ecount.alloc(K);
-  k_overlap_events<0><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
-                                               S.c_cos.p, S.c_z.p, S.c_thvir.p, p.max_velocity, p.grid_cells, ecount, nullptr, nullptr);
+  k_overlap_events<0><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, A.ra, A.dec,
+                                               A.cos, A.z, A.thvir, p.max_velocity, p.grid_cells, ecount, nullptr, nullptr);
   FOFB_LAUNCH_CHECK(h);
   long long* elen = sc.elen.alloc((size_t)K + 1);
   long long* eoff = sc.eoff.alloc((size_t)K + 1);
@@ -367,8 +393,8 @@ static int* overlap_keep_flags(fofb_handle* h, FofState& S, int K, const int* ce
   if (E > 0) {
     unsigned long long* ekey = sc.ekey.alloc((size_t)E);
     unsigned long long* ekey_s = sc.ekey_sorted.alloc((size_t)E);
-    k_overlap_events<1><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, S.c_ra.p, S.c_dec.p,
-                                                 S.c_cos.p, S.c_z.p, S.c_thvir.p, p.max_velocity, p.grid_cells, ecount, eoff, ekey);
+    k_overlap_events<1><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, A.ra, A.dec,
+                                                 A.cos, A.z, A.thvir, p.max_velocity, p.grid_cells, ecount, eoff, ekey);
     FOFB_LAUNCH_CHECK(h);
     FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
     FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
@@ -390,8 +416,8 @@ static int* overlap_keep_flags(fofb_handle* h, FofState& S, int K, const int* ce
     int* ev_c = sc.ev_c.alloc((size_t)E);
     int* ev_l = sc.ev_loser.alloc((size_t)E);
     int* state = sc.state.p;
-    FOFB_PROFILED(h, "k_event_static", k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, centre, S.c_id.p,
-                                                          S.c_N.p, S.c_mag.p, off, ids_s, ev_a, ev_c, ev_l, state));
+    FOFB_PROFILED(h, "k_event_static", k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, centre, A.id,
+                                                          A.N, A.mag, off, ids_s, ev_a, ev_c, ev_l, state));
     // per-cluster lists of the events it would lose, in event order
     unsigned long long* lkey = sc.lkey.alloc((size_t)E);
     unsigned long long* lkey_s = sc.lkey_sorted.alloc((size_t)E);
@@ -427,7 +453,7 @@ void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
   S.merged.K = S.bcg.K = 0;
   S.merged.total = S.bcg.total = 0;
   if (K == 0) return;
-  int* keep_flags = overlap_keep_flags(h, S, K, S.candidates.centre.p, S.candidates.off.p, S.candidates.total, S.candidates.rows.p, nullptr);
+  int* keep_flags = overlap_keep_flags(h, S, attrs_of(S), K, S.candidates.centre.p, S.candidates.off.p, S.candidates.total, S.candidates.rows.p, nullptr);
   sublist(h, S.candidates, keep_flags, S.merged, sc);
   fof_bcg_check(h, S);
 }
@@ -436,9 +462,28 @@ void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
 void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total,
                           const double* ids, int* keep_out) {
   if (K == 0) return;
-  int* keep = overlap_keep_flags(h, S, K, centre, off, total, nullptr, ids);
+  int* keep = overlap_keep_flags(h, S, attrs_of(S), K, centre, off, total, nullptr, ids);
   FOFB_CUDA(cudaMemcpyAsync(keep_out, keep, sizeof(int) * K, cudaMemcpyDeviceToDevice, h->stream));
   FOFB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// Stage 2 for a cluster list whose centres come as rows (K x 8, device) rather than as indices into this state's
+// centre table: used when every process only knows the centres of its own redshift neighbourhood.
+void fof_overlap_external_rows(fofb_handle* h, FofState& S, int K, const double* centre_rows, const long long* off, long long total,
+                               const double* ids, int* keep_out) {
+  if (K == 0) return;
+  cudaStream_t st = h->stream;
+  OverlapScratch& sc = scratch(S);
+  double* buf = sc.attr.alloc((size_t)K * 8);
+  int* iota = sc.attr_iota.alloc(K);
+  const Cosmo cosmo = device_cosmo(h, S.params);
+  k_attrs_from_rows<<<grid_for(K, 256), 256, 0, st>>>(K, centre_rows, cosmo, S.params.virial_radius, buf, buf + K, buf + 2LL * K,
+                                                      buf + 3LL * K, buf + 4LL * K, buf + 5LL * K, buf + 6LL * K, buf + 7LL * K, iota);
+  FOFB_LAUNCH_CHECK(h);
+  const CentreAttrs A{buf, buf + K, buf + 2LL * K, buf + 3LL * K, buf + 4LL * K, buf + 5LL * K, buf + 6LL * K, buf + 7LL * K};
+  int* keep = overlap_keep_flags(h, S, A, K, iota, off, total, nullptr, ids);
+  FOFB_CUDA(cudaMemcpyAsync(keep_out, keep, sizeof(int) * K, cudaMemcpyDeviceToDevice, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
 }
 
 // merged := the local candidates whose flag is set (flags on the device, one per local candidate)

@@ -162,6 +162,26 @@ void Pipeline::rerun(fofb_handle* h, double linking_length_factor, int richness,
   fof.last_K = fof.merged.K;
 }
 
+__global__ void k_cluster_sizes_ids(int K, const long long* off, const int* rows, const double* G, int cols, long long* sizes,
+                                    double* ids) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const long long s0 = off[k], len = off[k + 1] - s0;
+  if (lane == 0) sizes[k] = len;
+  for (long long t = lane; t < len; t += 32) ids[s0 + t] = G[(long long)rows[s0 + t] * cols + 6];
+}
+
+void Pipeline::export_local_clusters(fofb_handle* h, int* centre, long long* sizes, double* ids) {
+  const ClusterList& L = fof.candidates;
+  if (L.K == 0) return;
+  cudaStream_t st = h->stream;
+  FOFB_CUDA(cudaMemcpyAsync(centre, L.centre.p, sizeof(int) * L.K, cudaMemcpyDeviceToDevice, st));
+  k_cluster_sizes_ids<<<grid_for((int64_t)L.K * 32, 128), 128, 0, st>>>(L.K, L.off.p, L.rows.p, g_rows.p, 8, sizes, ids);
+  FOFB_LAUNCH_CHECK(h);
+  FOFB_CUDA(cudaStreamSynchronize(st));
+}
+
 // Distributed variant: this process holds a redshift slab plus halos.  Rows with z in [valid_lo, valid_hi] have
 // their whole velocity window on this process (so N(0.5) is exact for them and they may enter FoF()); candidate
 // centres with own_lo <= z < own_hi are the ones this process evaluates.

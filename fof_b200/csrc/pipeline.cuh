@@ -25,6 +25,7 @@ struct Pipeline {
              const unsigned* mt_key = nullptr, int mt_pos = 0);
   void finish(fofb_handle* h, const double* u, int mem, unsigned* mt_key = nullptr, int* mt_pos = nullptr);
   void rerun(fofb_handle* h, double linking_length_factor, int richness, double overdensity, const unsigned* mt_key, int mt_pos);
+  void export_local_clusters(fofb_handle* h, int* centre, long long* sizes, double* ids);
   void begin_dist(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double zmax_cen,
                   double valid_lo, double valid_hi, double own_lo, double own_hi);
   void stage0_and_inputs(fofb_handle* h, const fofb_params& p, const View& raw, double zmin, double zmax_gal, double czmin,

@@ -81,6 +81,9 @@ class SoloComm:
     def allgatherv(self, x):
         return [x]
 
+    def allgatherv_t(self, t):
+        return [t]
+
     def allreduce(self, x, op):
         return x
 
@@ -117,6 +120,9 @@ class ThreadComm:
 
     def allgatherv(self, x):
         return [np.array(a, copy=True) for a in self._exchange(x)]
+
+    def allgatherv_t(self, t):
+        return [a.clone() for a in self._exchange(t)]
 
     def allreduce(self, x, op):
         vals = self._exchange(np.asarray(x))
@@ -164,6 +170,20 @@ class TorchComm:
         self.dist.all_gather(outs, pad)
         return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)]
 
+    def allgatherv_t(self, t):
+        """All-gather of tensors whose first dimension differs between ranks (padded all_gather on the device)."""
+        import torch
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        self.dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        mx = max(max(sizes), 1)
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        outs = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(outs, pad)
+        return [o[:s] for o, s in zip(outs, sizes)]
+
     def allreduce(self, x, op):
         import torch
         t = torch.as_tensor(np.asarray(x, dtype=np.float64)).to(self._dev())
@@ -203,10 +223,13 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
                         mt_state=None):
     """Run the whole path on this rank's rows and assemble the global catalogue.
 
-    local_rows : (n_local, 7) float64, the rows of the global table this rank holds, in global row order;
-    global_row : their indices in the global table;  own / valid: intervals from ``plan_slab``.
+    local_rows : (n_local, 7) float64 (numpy, or a torch CUDA tensor already on the handle's device), the rows of
+                 the global table this rank holds, in global row order;
+    global_row : their indices in the global table;  own / valid: intervals from ``plan_slab``;
     mt_state   : (key[624], pos) of numpy's legacy MT19937 generator to draw the overdensity points from; None uses
                  (and advances) this process's ``np.random`` -- every process must then hold the same state.
+    Every rank works only with the candidate centres of its own redshift neighbourhood (its own plus the neighbours'
+    centres inside its valid interval); centres are identified across ranks by their priority key.
     Returns (offsets, member_global_rows, centre_global_row, N, D, props) of the GLOBAL final catalogue, identical
     on every rank, in the order the single-GPU run produces (plus the advanced (key, pos) when mt_state is given).
     """
@@ -214,21 +237,27 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     import torch
     h = handle
     L = h.lib
+    dev = torch.device("cuda", h.device)
     _t = [time.perf_counter()]
     phases = {}
 
     def lap(name):
+        torch.cuda.current_stream(dev).synchronize()
         now = time.perf_counter()
         phases[name] = phases.get(name, 0.0) + 1e3 * (now - _t[0])
         _t[0] = now
 
+    def cat0(parts):
+        return torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
+
     p = params or _lib_params(None, None, None, None, None)
     zcut = zcut or (P.min_redshift, P.max_redshift + 0.02, P.max_redshift)
-    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
-    grow = np.asarray(global_row, dtype=np.int64)
-    rank = comm.rank
+    rank, world = comm.rank, comm.world
+    i64, f64 = torch.int64, torch.float64
 
-    # stage 0 on the local rows; local candidate centres and FoF() rows
+    # ---- stage 0 on the local rows; local candidate centres and FoF() rows --------------------------------
+    if not hasattr(local_rows, "data_ptr"):
+        local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
     m, keep = _lib.matrix_of(local_rows)
     ng, mc = C.c_int64(), C.c_int64()
     z3 = (C.c_double * 3)(*zcut)
@@ -236,121 +265,190 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     o2 = (C.c_double * 2)(*own)
     h.check(L.fofb_dist_begin(h.h, C.byref(p), C.byref(m), z3, v2, o2, C.byref(ng), C.byref(mc)))
     n_g, m_loc = ng.value, mc.value
-    cen_rows = np.empty((m_loc, 8))
-    cen_src = np.empty(m_loc, dtype=np.int32)
-    g_src = np.empty(n_g, dtype=np.int32)
-    h.check(L.fofb_dist_local_inputs(h.h, cen_rows.ctypes.data, cen_src.ctypes.data, g_src.ctypes.data, None))
-
+    # the MT19937 stream of the overdensity points is generated on a side stream while the rounds run
+    if mt_state is None:
+        name, mt_key, mt_pos, _, _ = np.random.get_state()
+    else:
+        mt_key, mt_pos = mt_state
+    mt_key = np.ascontiguousarray(mt_key, dtype=np.uint32)
+    k_spec = int(getattr(h, "_slab_last_merged", 0) * 1.25) + 256 if getattr(h, "_slab_last_merged", 0) else int(m.rows) * world // 150 + 1024
+    h.check(L.fofb_dist_prefetch_mt(h.h, mt_key.ctypes.data, int(mt_pos), k_spec))
+    cen = torch.empty((max(m_loc, 1), 8), dtype=f64, device=dev)[:m_loc]
+    csrc = torch.empty(max(m_loc, 1), dtype=torch.int32, device=dev)[:m_loc]
+    h.check(L.fofb_dist_local_inputs(h.h, cen.data_ptr(), csrc.data_ptr(), None, None))
+    # global row ids of the local rows (a torch tensor on the device is used as it is)
+    grow_t = global_row.to(dev) if hasattr(global_row, "data_ptr") else torch.from_numpy(np.asarray(global_row, dtype=np.int64)).to(dev)
+    c_grow = grow_t[csrc.long()]
     lap("stage0")
-    # global priority order of the centres
-    parts = comm.allgatherv(np.column_stack([cen_rows, grow[cen_src].astype(np.float64)]) if m_loc else np.zeros((0, 9)))
-    owner = np.concatenate([np.full(len(x), r, dtype=np.int32) for r, x in enumerate(parts)])
-    allc = np.concatenate(parts, axis=0)
-    order = global_priority(allc[:, 7], allc[:, 8].astype(np.int64), device=torch.device("cuda", h.device))
-    centres = np.ascontiguousarray(allc[order, :8])
-    centre_grow = allc[order, 8].astype(np.int64)
-    owned = np.ascontiguousarray((owner[order] == rank).astype(np.uint8))
-    m_glob = len(centres)
 
-    lap("gather_centres")
+    # ---- exchange the centres that lie inside another rank's valid interval ---------------------------------
+    iv = np.concatenate(comm.allgatherv(np.array([[valid[0], valid[1]]], dtype=np.float64)), axis=0)
+    zc = cen[:, 2]
+    needed = torch.zeros(m_loc, dtype=torch.bool, device=dev)
+    for s in range(world):
+        if s != rank:
+            needed |= (zc >= iv[s, 0]) & (zc <= iv[s, 1])
+    nz_needed = torch.nonzero(needed).flatten()
+    parts_rows = comm.allgatherv_t(torch.cat([cen[nz_needed], c_grow[nz_needed].to(f64).unsqueeze(1)], dim=1))
+    counts = [len(x) for x in parts_rows]
+    offB = np.concatenate([[0], np.cumsum(counts)])
+    B = cat0(parts_rows)
+    nB = int(offB[-1])
+    B_owner = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(counts)]) if nB else \
+        torch.zeros(0, dtype=torch.int32, device=dev)
+    imp_idx = torch.nonzero((B_owner != rank) & (B[:, 2] >= valid[0]) & (B[:, 2] <= valid[1])).flatten() if nB else \
+        torch.zeros(0, dtype=i64, device=dev)
+    loc_rows = torch.cat([cen, B[imp_idx, :8]], dim=0)
+    loc_grow = torch.cat([c_grow, B[imp_idx, 8].to(i64)])
+    loc_owned = torch.cat([torch.ones(m_loc, dtype=torch.uint8, device=dev), torch.zeros(len(imp_idx), dtype=torch.uint8, device=dev)])
+    loc_bidx = torch.full((len(loc_grow),), -1, dtype=i64, device=dev)
+    loc_bidx[nz_needed] = int(offB[rank]) + torch.arange(len(nz_needed), device=dev)
+    loc_bidx[m_loc:] = imp_idx
+    key = loc_rows[:, 7].to(i64) * (1 << 40) + loc_grow
+    order = torch.argsort(key, descending=True)
+    loc_rows = loc_rows[order].contiguous()
+    loc_grow, loc_owned, loc_bidx, key = loc_grow[order], loc_owned[order].contiguous(), loc_bidx[order], key[order]
+    m_l = len(loc_grow)
+    lpos = torch.nonzero(loc_bidx >= 0).flatten()
+    bpos = loc_bidx[lpos]
+    lap("exchange_centres")
+
     bbox = np.empty(4)
-    h.check(L.fofb_dist_prepare(h.h, centres.ctypes.data, m_glob, owned.ctypes.data, bbox.ctypes.data))
+    torch.cuda.current_stream(dev).synchronize()
+    h.check(L.fofb_dist_prepare(h.h, loc_rows.data_ptr(), m_l, loc_owned.data_ptr(), bbox.ctypes.data))
     lo = comm.allreduce(np.array([bbox[0], bbox[2]]), "min")
     hi = comm.allreduce(np.array([bbox[1], bbox[3]]), "max")
     gbbox = np.array([lo[0], hi[0], lo[1], hi[1]])
-
     lap("prepare")
-    # priority rounds, the tracker state merged after each
-    dev = torch.device("cuda", h.device)
-    alive = torch.empty(max(m_glob, 1), dtype=torch.uint8, device=dev)
-    decided = torch.empty(max(m_glob, 1), dtype=torch.uint8, device=dev)
+
+    # ---- priority rounds; the state of the shared (boundary) centres is merged after each ---------------------
+    alive = torch.empty(max(m_l, 1), dtype=torch.uint8, device=dev)
+    decided = torch.empty(max(m_l, 1), dtype=torch.uint8, device=dev)
     rounds = 0
-    while m_glob > 0:
-        h.check(L.fofb_dist_round_evaluate(h.h))
-        h.check(L.fofb_dist_state(h.h, alive.data_ptr(), decided.data_ptr(), 0))
-        comm.allreduce_bytes(alive, decided)
-        torch.cuda.synchronize(dev)
-        h.check(L.fofb_dist_state(h.h, alive.data_ptr(), decided.data_ptr(), 1))
-        na = C.c_int64()
-        h.check(L.fofb_dist_round_advance(h.h, C.byref(na)))
+    while True:
+        na = C.c_int64(0)
+        if m_l > 0:
+            h.check(L.fofb_dist_round_evaluate(h.h))
+            h.check(L.fofb_dist_state(h.h, alive.data_ptr(), decided.data_ptr(), 0))
+        ab = torch.ones(max(nB, 1), dtype=torch.uint8, device=dev)
+        db = torch.zeros(max(nB, 1), dtype=torch.uint8, device=dev)
+        if m_l > 0 and len(lpos):
+            ab[bpos] = alive[lpos]
+            db[bpos] = decided[lpos]
+        comm.allreduce_bytes(ab, db)
+        if m_l > 0:
+            if len(lpos):
+                alive[lpos] = ab[bpos]
+                decided[lpos] = db[bpos]
+            torch.cuda.current_stream(dev).synchronize()
+            h.check(L.fofb_dist_state(h.h, alive.data_ptr(), decided.data_ptr(), 1))
+            h.check(L.fofb_dist_round_advance(h.h, C.byref(na)))
         rounds += 1
         if int(comm.allreduce(np.array([float(na.value)]), "sum")[0]) == 0:
             break
     kc, kt = C.c_int64(), C.c_int64()
     h.check(L.fofb_dist_finalize(h.h, C.byref(kc), C.byref(kt)))
     K_loc, tot_loc = kc.value, kt.value
-
     lap("rounds")
-    # stage 2 on the all-process cluster list
-    lc = np.empty(K_loc, dtype=np.int32)
-    loff = np.zeros(K_loc + 1, dtype=np.int64)
-    lids = np.empty(tot_loc)
-    h.check(L.fofb_dist_local_clusters(h.h, lc.ctypes.data, loff.ctypes.data, lids.ctypes.data))
-    g_centre = comm.allgatherv(lc)
-    g_sizes = comm.allgatherv(np.diff(loff))
-    g_ids = comm.allgatherv(lids)
-    c_all = np.concatenate(g_centre)
-    s_all = np.concatenate(g_sizes)
-    cl_owner = np.concatenate([np.full(len(x), r, dtype=np.int32) for r, x in enumerate(g_centre)])
-    starts = np.concatenate([[0], np.cumsum(s_all)])[:-1]
-    ids_all = np.concatenate(g_ids) if len(g_ids) else np.zeros(0)
-    corder = np.argsort(c_all, kind="stable")  # ascending centre index = the order fof.py:232 appends clusters
-    K_glob = len(c_all)
-    off_sorted = np.zeros(K_glob + 1, dtype=np.int64)
-    np.cumsum(s_all[corder], out=off_sorted[1:])
-    if K_glob:
-        gather = np.concatenate([np.arange(starts[k], starts[k] + s_all[k]) for k in corder]) if off_sorted[-1] else np.zeros(0, dtype=np.int64)
-        ids_sorted = np.ascontiguousarray(ids_all[gather.astype(np.int64)])
-    else:
-        ids_sorted = np.zeros(0)
-    centre_sorted = np.ascontiguousarray(c_all[corder].astype(np.int32))
-    lap("gather_clusters")
-    keep_glob = np.ones(K_glob, dtype=np.int32)
-    h.check(L.fofb_dist_overlap(h.h, K_glob, centre_sorted.ctypes.data, off_sorted.ctypes.data, ids_sorted.ctypes.data,
-                                keep_glob.ctypes.data))
-    keep_glob = (keep_glob != 0)
-    gidx_of_sorted = np.cumsum(keep_glob) - 1
-    mine_sorted = cl_owner[corder] == rank          # my clusters, ascending centre index = my local order
-    keep_local = np.ascontiguousarray(keep_glob[mine_sorted].astype(np.int32))
-    gidx_local = np.ascontiguousarray(gidx_of_sorted[mine_sorted & keep_glob].astype(np.int32))
-    K_merged = int(keep_glob.sum())
-    h.check(L.fofb_dist_set_merged(h.h, keep_local.ctypes.data, gidx_local.ctypes.data, K_merged, gbbox.ctypes.data))
 
+    # ---- stage 2 on the all-process cluster list (replicated) ------------------------------------------------
+    lc = torch.empty(max(K_loc, 1), dtype=torch.int32, device=dev)[:K_loc]
+    ls = torch.empty(max(K_loc, 1), dtype=i64, device=dev)[:K_loc]
+    lids = torch.empty(max(tot_loc, 1), dtype=f64, device=dev)[:tot_loc]
+    if K_loc:
+        h.check(L.fofb_dist_local_clusters_dev(h.h, lc.data_ptr(), ls.data_ptr(), lids.data_ptr()))
+    meta = torch.cat([loc_rows[lc.long()], key[lc.long()].to(f64).unsqueeze(1), ls.to(f64).unsqueeze(1)], dim=1)  # K x 10
+    g_meta = comm.allgatherv_t(meta)
+    g_ids = comm.allgatherv_t(lids)
+    kcounts = [len(x) for x in g_meta]
+    M_all = cat0(g_meta)
+    ids_all = cat0(g_ids)
+    K_glob = len(M_all)
+    keep_glob = torch.ones(max(K_glob, 1), dtype=torch.int32, device=dev)[:K_glob]
+    cl_owner = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(kcounts)]) if K_glob else \
+        torch.zeros(0, dtype=torch.int32, device=dev)
+    if K_glob:
+        corder = torch.argsort(M_all[:, 8], descending=True)  # priority order = the order fof.py:232 appends clusters
+        sizes_all = M_all[:, 9].to(i64)
+        starts = torch.cumsum(sizes_all, 0) - sizes_all
+        sizes_s = sizes_all[corder]
+        off_s = torch.zeros(K_glob + 1, dtype=i64, device=dev)
+        off_s[1:] = torch.cumsum(sizes_s, 0)
+        total_ids = int(off_s[-1].item())
+        seg = torch.repeat_interleave(torch.arange(K_glob, device=dev), sizes_s)
+        gather = starts[corder][seg] + (torch.arange(total_ids, device=dev) - off_s[:-1][seg])
+        ids_s = ids_all[gather].contiguous()
+        rows_s = M_all[corder, :8].contiguous()
+        torch.cuda.current_stream(dev).synchronize()
+        h.check(L.fofb_dist_overlap_rows(h.h, K_glob, rows_s.data_ptr(), off_s.data_ptr(), total_ids, ids_s.data_ptr(),
+                                         keep_glob.data_ptr()))
+        keepb = keep_glob != 0
+        gidx_sorted = torch.cumsum(keepb.to(i64), 0) - 1
+        mine_sorted = cl_owner[corder] == rank
+        keep_local = keepb[mine_sorted].to(torch.int32).contiguous()
+        gidx_local = gidx_sorted[mine_sorted & keepb].to(torch.int32).contiguous()
+        K_merged = int(keepb.sum().item())
+    else:
+        keep_local = torch.zeros(1, dtype=torch.int32, device=dev)
+        gidx_local = torch.zeros(1, dtype=torch.int32, device=dev)
+        K_merged = 0
+    torch.cuda.current_stream(dev).synchronize()
+    h.check(L.fofb_dist_set_merged(h.h, keep_local.data_ptr(), gidx_local.data_ptr(), K_merged, gbbox.ctypes.data))
+    h._slab_last_merged = K_merged
     lap("overlap")
-    # stage 4 (every rank consumes the same np.random stream and uses its own clusters' blocks), stages 5-6
+
+    # ---- stage 4 (every rank consumes the same MT19937 stream and uses its own clusters' blocks), stages 5-6 ----
     new_state = None
     if mt_state is None:
         Kf, total = h.pipeline_finish_np_random()
     else:
         Kf, total, nkey, npos = h.pipeline_finish_mt(mt_state[0], mt_state[1])
         new_state = (nkey, npos)
-    off, rows, cidx, N, D, props = h.pipeline_fetch(Kf, total)
+    off_t, rows_t, cidx32, N_t, D_t, props_t = h.pipeline_fetch_torch(Kf, total, dev)
     lap("finish")
-    sizes = np.diff(off)
-    # assemble the global catalogue in ascending centre priority
-    f_c = comm.allgatherv(cidx)
-    f_s = comm.allgatherv(sizes)
-    f_rows = comm.allgatherv(grow[rows] if total else np.zeros(0, dtype=np.int64))
-    f_N = comm.allgatherv(N)
-    f_D = comm.allgatherv(D)
-    f_p = comm.allgatherv(props.reshape(-1, 8))
-    fc = np.concatenate(f_c)
-    fs = np.concatenate(f_s)
-    fo = np.argsort(fc, kind="stable")
-    fstarts = np.concatenate([[0], np.cumsum(fs)])[:-1]
-    allrows = np.concatenate(f_rows)
-    out_off = np.zeros(len(fc) + 1, dtype=np.int64)
-    np.cumsum(fs[fo], out=out_off[1:])
-    out_rows = (np.concatenate([allrows[fstarts[k]:fstarts[k] + fs[k]] for k in fo]) if len(fo) and out_off[-1]
-                else np.zeros(0, dtype=np.int64))
+
+    # ---- the global catalogue, in priority order -------------------------------------------------------------
+    cidx_t = cidx32.long()
+    fmeta = torch.cat([key[cidx_t].to(f64).unsqueeze(1), loc_grow[cidx_t].to(f64).unsqueeze(1),
+                       (off_t[1:] - off_t[:-1]).to(f64).unsqueeze(1), N_t.unsqueeze(1), D_t.unsqueeze(1), props_t],
+                      dim=1) if Kf else torch.zeros((0, 13), dtype=f64, device=dev)
+    f_meta = cat0(comm.allgatherv_t(fmeta))
+    f_rows = cat0(comm.allgatherv_t(grow_t[rows_t.long()] if total else torch.zeros(0, dtype=i64, device=dev)))
+    Kt = len(f_meta)
+    if Kt:
+        fo = torch.argsort(f_meta[:, 0], descending=True)
+        fs_all = f_meta[:, 2].to(i64)
+        fstarts = torch.cumsum(fs_all, 0) - fs_all
+        fs = fs_all[fo]
+        out_off = torch.zeros(Kt + 1, dtype=i64, device=dev)
+        out_off[1:] = torch.cumsum(fs, 0)
+        tot = int(out_off[-1].item())
+        seg = torch.repeat_interleave(torch.arange(Kt, device=dev), fs)
+        out_rows = f_rows[fstarts[fo][seg] + (torch.arange(tot, device=dev) - out_off[:-1][seg])]
+        fm = f_meta[fo]
+
+        def to_host(name, t):  # pinned, reused host buffers: a fresh pageable allocation per call costs more than the copy
+            cache = h.__dict__.setdefault("_slab_pinned", {})
+            buf = cache.get(name)
+            if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+                buf = cache[name] = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype, pin_memory=True)
+            view = buf[: t.numel()].view(t.shape)
+            view.copy_(t, non_blocking=True)
+            return view
+
+        host = [to_host("off", out_off), to_host("rows", out_rows), to_host("centre", fm[:, 1].to(i64)),
+                to_host("N", fm[:, 3].contiguous()), to_host("D", fm[:, 4].contiguous()), to_host("props", fm[:, 5:13].contiguous())]
+        torch.cuda.current_stream(dev).synchronize()
+        res = tuple(x.numpy() for x in host)  # views of the pinned buffers: valid until the next call on this handle
+    else:
+        res = (np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0), np.zeros(0),
+               np.zeros((0, 8)))
     lap("gather_final")
     if timings is not None:
         timings.update({"ms_" + k: round(v, 2) for k, v in phases.items()})
-        timings.update(rounds=rounds, centres=m_glob, stage1_clusters=K_glob, merged=K_merged, local_rows=len(local_rows),
-                       fof_rows=n_g)
+        timings.update(rounds=rounds, local_centres=m_l, shared_centres=nB, stage1_clusters=K_glob, merged=K_merged,
+                       local_rows=int(m.rows), fof_rows=n_g)
     del keep
-    res = (out_off, out_rows.astype(np.int64), centre_grow[fc[fo]], np.concatenate(f_N)[fo], np.concatenate(f_D)[fo],
-           np.concatenate(f_p, axis=0)[fo])
     return res + (new_state,) if mt_state is not None else res
 
 

@@ -215,6 +215,7 @@ int fofb_pipeline_stats(fofb_handle* h, int64_t* stats7);
  */
 int fofb_dist_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, const double* zcut3,
                     const double* z_valid2, const double* z_own2, int64_t* n_fof_rows, int64_t* n_local_centres);
+int fofb_dist_prefetch_mt(fofb_handle* h, const uint32_t* mt_key, int32_t mt_pos, int64_t k_spec);
 int fofb_dist_local_inputs(fofb_handle* h, double* centre_rows, int32_t* centre_src_row, int32_t* fof_src_row, double* bbox4);
 int fofb_dist_prepare(fofb_handle* h, const double* centres, int64_t n_centres, const uint8_t* owned, double* local_bbox4);
 int fofb_dist_round_evaluate(fofb_handle* h);
@@ -223,6 +224,10 @@ int fofb_dist_round_advance(fofb_handle* h, int64_t* n_active);
 int fofb_dist_finalize(fofb_handle* h, int64_t* n_clusters, int64_t* n_members);
 int fofb_dist_local_clusters(fofb_handle* h, int32_t* centre, int64_t* offsets, double* ids);
 int fofb_dist_overlap(fofb_handle* h, int64_t K, const int32_t* centre, const int64_t* offsets, const double* ids, int32_t* keep);
+/* device-array variants: clusters' centres as rows instead of indices into a replicated centre table */
+int fofb_dist_local_clusters_dev(fofb_handle* h, int32_t* centre, int64_t* sizes, double* ids);
+int fofb_dist_overlap_rows(fofb_handle* h, int64_t K, const double* centre_rows, const int64_t* offsets, int64_t total,
+                           const double* ids, int32_t* keep);
 int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_t* global_index, int64_t n_global_merged,
                          const double* global_bbox4);
 
