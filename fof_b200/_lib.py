@@ -365,13 +365,13 @@ class Handle:
         return dict(zip(("galaxies_after_zcut", "candidate_centres", "stage1_clusters", "stage1_members",
                          "priority_rounds", "centres_evaluated", "stage4_clusters"), s.tolist()))
 
-    def transitive_labels(self, galaxies, params, linking_length_mpc_h):
-        """(labels int32[n] = smallest row of each row's component, number of groups, number of links)."""
+    def transitive_labels(self, galaxies, params, linking_length_mpc_h, count_links=True):
+        """(labels int32[n] = smallest row of each row's component, number of groups, number of links or -1)."""
         m, keep = matrix_of(galaxies)
         lab = np.empty(m.rows, dtype=np.int32)
-        g, l = C.c_int64(), C.c_int64()
+        g, l = C.c_int64(), C.c_int64(-1)
         self.check(self.lib.fofb_transitive_labels(self.h, C.byref(params), C.byref(m), float(linking_length_mpc_h),
-                                                   lab.ctypes.data, 0, C.byref(g), C.byref(l)))
+                                                   lab.ctypes.data, 0, C.byref(g), C.byref(l) if count_links else None))
         del keep
         return lab, g.value, l.value
 

@@ -915,7 +915,7 @@ int fofb_transitive_labels(fofb_handle* h, const fofb_params* p, const fofb_matr
   if (!h->trans) h->trans = new Transitive();
   Timed timer(h);
   const View v = to_device(h, *galaxies, h->upload);
-  h->trans->run(h, *p, v, linking_length_mpc_h);
+  h->trans->run(h, *p, v, linking_length_mpc_h, n_links != nullptr);
   FOFB_CUDA(cudaMemcpyAsync(labels, h->trans->label.p, sizeof(int32_t) * h->trans->n_rows,
                             labels_mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
   timer.stop();

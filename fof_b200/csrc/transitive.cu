@@ -63,6 +63,9 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 
 // One thread per galaxy in cell order; every accepted pair is seen from both ends, the end with the larger row
 // index performs the union.
+// COUNT_LINKS = false additionally skips pairs whose ends already share a root before any geometry is evaluated:
+// inside a percolating blob almost every pair is of that kind, and the link count is then not available.
+template <bool COUNT_LINKS>
 __global__ void __launch_bounds__(256) k_link_union(CellListView cl, int n, const QueryRec* __restrict__ rec, int* parent,
                                                     unsigned long long* n_links) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(256) k_link_union(CellListView cl, int n, cons
       for (int j = first; j < a; ++j) {
         const int rj = cl.row[j];
         if (rj >= row) continue;
+        if (!COUNT_LINKS && uf_find(parent, row) == uf_find(parent, rj)) continue;
         const int zj = cl.zrank[j];
         const QueryRec other = rec[zj];
         if (zr < other.wlo || zr >= other.whi) continue;       // i must lie in j's window too
@@ -116,7 +120,7 @@ __global__ void k_uf_labels(int n, int* parent, int* label, int* is_root) {
   is_root[i] = x == i ? 1 : 0;
 }
 
-void Transitive::run(fofb_handle* h, const fofb_params& p, const View& rows, double ll_mpc_h) {
+void Transitive::run(fofb_handle* h, const fofb_params& p, const View& rows, double ll_mpc_h, bool count_links) {
   cudaStream_t st = h->stream;
   FOFB_REQUIRE(ll_mpc_h > 0 && std::isfinite(ll_mpc_h), "linking length must be positive");
   cat.build(h, rows);
@@ -141,7 +145,11 @@ void Transitive::run(fofb_handle* h, const fofb_params& p, const View& rows, dou
   FOFB_CUDA(cudaMemsetAsync(nl, 0, sizeof(unsigned long long), st));
   k_uf_init<<<grid_for(n, B), B, 0, st>>>(n, par);
   FOFB_LAUNCH_CHECK(h);
-  FOFB_PROFILED(h, "k_link_union", k_link_union<<<grid_for(n, 256), 256, 0, st>>>(cells.view(), n, recs, par, nl));
+  if (count_links) {
+    FOFB_PROFILED(h, "k_link_union", k_link_union<true><<<grid_for(n, 256), 256, 0, st>>>(cells.view(), n, recs, par, nl));
+  } else {
+    FOFB_PROFILED(h, "k_link_union", k_link_union<false><<<grid_for(n, 256), 256, 0, st>>>(cells.view(), n, recs, par, nl));
+  }
   int* lab = label.alloc(n);
   int* roots = is_root.alloc(n);
   FOFB_PROFILED(h, "k_uf_labels", k_uf_labels<<<grid_for(n, B), B, 0, st>>>(n, par, lab, roots));
@@ -155,7 +163,7 @@ void Transitive::run(fofb_handle* h, const fofb_params& p, const View& rows, dou
   FOFB_CUDA(cudaMemcpyAsync(&l, nl, sizeof(l), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
   n_groups = g;
-  n_links = (long long)l;
+  n_links = count_links ? (long long)l : -1;
   n_rows = n;
 }
 

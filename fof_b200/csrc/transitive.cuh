@@ -13,7 +13,7 @@ struct Transitive {
   DBuf<int> parent, label, is_root, num_groups;
   DBuf<unsigned long long> links;
   long long n_rows = 0, n_groups = 0, n_links = 0;
-  void run(fofb_handle* h, const fofb_params& p, const View& rows, double ll_mpc_h);
+  void run(fofb_handle* h, const fofb_params& p, const View& rows, double ll_mpc_h, bool count_links);
 };
 
 }  // namespace fofb

@@ -243,7 +243,9 @@ int fofb_bubble_count(fofb_handle* h, const fofb_params* p, const fofb_matrix* p
  * union-find mode named in BASELINE.json.  Galaxies i, j are friends iff each lies in the other's velocity window
  * (analysis/methods.py:68-87 with p->max_velocity) and their haversine separation is within the angle of the
  * transverse linking length [h^-1 Mpc proper] at both redshifts (analysis/methods.py:12-32).  labels[i] = smallest
- * row index of the component of row i.  Oracle: oracle/transitive_oracle.py (scipy connected components).
+ * row index of the component of row i.  n_links (optional): number of friend pairs; passing NULL lets the kernel skip
+ * pairs whose ends are already connected (much faster on percolating blobs).  Oracle: oracle/transitive_oracle.py
+ * (scipy connected components).
  */
 int fofb_transitive_labels(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, double linking_length_mpc_h,
                            int32_t* labels, int32_t labels_mem, int64_t* n_groups, int64_t* n_links);

@@ -20,6 +20,8 @@ def test_labels_equal_connected_components(lib, n, seed, kind, ll):
     assert n_groups == len(np.unique(want))
     # canonical form: the label is the smallest member, and every root labels itself
     assert (got <= np.arange(n)).all() and (got[got] == got).all()
+    fast, n_groups2, links2 = transitive.friends_of_friends(arr, linking_length=ll, count_links=False)
+    assert np.array_equal(fast, want) and n_groups2 == n_groups and links2 == -1
 
 
 def test_percolating_blobs_deep_chains(lib):
@@ -33,7 +35,7 @@ def test_percolating_blobs_deep_chains(lib):
     assert np.array_equal(got, want)
     # the same at a size the oracle cannot reach: size-independent invariants only
     big = make_catalog(2000000, seed=10, kind="dense", n_blobs=12, as_frame=False)
-    lab, n_groups, links = transitive.friends_of_friends(big, linking_length=1.0)
+    lab, n_groups, links = transitive.friends_of_friends(big, linking_length=1.0, count_links=False)
     assert (lab <= np.arange(len(big))).all() and (lab[lab] == lab).all()
     assert n_groups == len(np.unique(lab))
     assert np.unique(lab, return_counts=True)[1].max() > 50000
