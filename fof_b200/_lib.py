@@ -93,6 +93,7 @@ def load():
         "fofb_dist_set_merged": (C.c_int, [vp, vp, vp, i64, vp]),
         "fofb_pipeline_rerun": (C.c_int, [vp, dbl, i32, dbl, vp, P(i32), P(i64), P(i64)]),
         "fofb_bubble_count": (C.c_int, [vp, P(Params), P(Matrix), i64, vp, vp, i32, dbl, vp]),
+        "fofb_match_catalog": (C.c_int, [vp, P(Params), P(Matrix), P(Matrix), dbl, dbl, vp, vp, i32, vp]),
         "fofb_dist_prefetch_mt": (C.c_int, [vp, vp, i32, i64]),
         "fofb_dist_local_clusters_dev": (C.c_int, [vp, vp, vp, vp]),
         "fofb_dist_overlap_rows": (C.c_int, [vp, i64, vp, vp, i64, vp, vp]),
@@ -364,6 +365,18 @@ class Handle:
         self.lib.fofb_pipeline_stats(self.h, s.ctypes.data)
         return dict(zip(("galaxies_after_zcut", "candidate_centres", "stage1_clusters", "stage1_members",
                          "priority_rounds", "centres_evaluated", "stage4_clusters"), s.tolist()))
+
+    def match_catalog(self, sample, catalogue, params, matching_distance_mpc_h, z_cut=0.1):
+        """(match_row int32[C], match_sep_deg float64[C], n_matched) -- see include/fofb.h fofb_match_catalog."""
+        ms, keep_s = matrix_of(sample)
+        mc, keep_c = matrix_of(catalogue)
+        rows = np.empty(mc.rows, dtype=np.int32)
+        sep = np.empty(mc.rows, dtype=np.float64)
+        n = C.c_int64()
+        self.check(self.lib.fofb_match_catalog(self.h, C.byref(params), C.byref(ms), C.byref(mc), float(matching_distance_mpc_h),
+                                               float(z_cut), rows.ctypes.data, sep.ctypes.data, 0, C.byref(n)))
+        del keep_s, keep_c
+        return rows, sep, n.value
 
     def transitive_labels(self, galaxies, params, linking_length_mpc_h, count_links=True):
         """(labels int32[n] = smallest row of each row's component, number of groups, number of links or -1)."""

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfofb200.so")
-SOURCES = ["capi.cu", "catalog.cu", "counts.cu", "fof_stage.cu", "overlap.cu", "clean.cu", "pipeline.cu", "transitive.cu", "bubble.cu"]
+SOURCES = ["capi.cu", "catalog.cu", "counts.cu", "fof_stage.cu", "overlap.cu", "clean.cu", "pipeline.cu", "transitive.cu", "bubble.cu", "match.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

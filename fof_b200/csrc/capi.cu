@@ -9,6 +9,7 @@
 #include "pipeline.cuh"
 #include "transitive.cuh"
 #include "bubble.cuh"
+#include "match.cuh"
 
 namespace fofb {
 void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre, const long long* off, long long total,
@@ -189,6 +190,8 @@ void fofb_destroy(fofb_handle* h) {
   h->trans = nullptr;
   delete h->bubble;
   h->bubble = nullptr;
+  delete h->matcher;
+  h->matcher = nullptr;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -900,6 +903,34 @@ int fofb_bubble_count(fofb_handle* h, const fofb_params* p, const fofb_matrix* p
   }
   h->bubble->count(h, *p, v, (int)n_centres, centres, radius_deg, use_window, window_z, counts);
   timer.stop();
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+// ---- catalogue matching ---------------------------------------------------------------------------------------
+int fofb_match_catalog(fofb_handle* h, const fofb_params* p, const fofb_matrix* sample, const fofb_matrix* catalogue,
+                       double matching_distance_mpc_h, double z_cut, int32_t* match_row, double* match_sep_deg, int32_t out_mem,
+                       int64_t* n_matched) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  check_params(p);
+  FOFB_REQUIRE(sample && catalogue && match_row && match_sep_deg, "catalogue matching: null argument");
+  FOFB_REQUIRE(sample->rows < (1ll << 31) && catalogue->rows < (1ll << 26), "catalogue matching: too many rows");
+  FOFB_REQUIRE(matching_distance_mpc_h >= 0 && z_cut >= 0, "catalogue matching: negative distance or redshift cut");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (!h->matcher) h->matcher = new Matcher();
+  Timed timer(h);
+  View vs, vc;
+  if (sample->rows > 0) vs = to_device(h, *sample, h->upload); else { vs.rows = 0; vs.cols = sample->cols; }
+  if (catalogue->rows > 0) vc = to_device(h, *catalogue, h->upload2); else { vc.rows = 0; vc.cols = catalogue->cols; }
+  h->matcher->run(h, *p, vs, vc, matching_distance_mpc_h, z_cut);
+  if (catalogue->rows > 0) {
+    const cudaMemcpyKind kind = out_mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    FOFB_CUDA(cudaMemcpyAsync(match_row, h->matcher->match_row.p, sizeof(int32_t) * catalogue->rows, kind, h->stream));
+    FOFB_CUDA(cudaMemcpyAsync(match_sep_deg, h->matcher->match_sep.p, sizeof(double) * catalogue->rows, kind, h->stream));
+  }
+  timer.stop();
+  if (n_matched) *n_matched = h->matcher->n_matched;
   return FOFB_OK;
   FOFB_CATCH(h)
 }

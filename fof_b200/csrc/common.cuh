@@ -96,6 +96,7 @@ struct CleanState; // clean.cu
 struct Pipeline;   // pipeline.cu
 struct Transitive; // transitive.cu
 struct Bubble;     // bubble.cu
+struct Matcher;    // match.cu
 
 }  // namespace fofb
 
@@ -139,6 +140,7 @@ struct fofb_handle {
   fofb::Pipeline* pipe = nullptr;
   fofb::Transitive* trans = nullptr;
   fofb::Bubble* bubble = nullptr;
+  fofb::Matcher* matcher = nullptr;
   fofb::DBuf<unsigned char> cub_tmp;
   fofb::DBuf<double> upload;      // staging for host matrices
   fofb::DBuf<double> upload2;

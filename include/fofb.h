@@ -238,6 +238,17 @@ int fofb_dist_set_merged(fofb_handle* h, const int32_t* keep_local, const int32_
 int fofb_bubble_count(fofb_handle* h, const fofb_params* p, const fofb_matrix* points, int64_t n_centres, const double* centres,
                       const double* radius_deg, int32_t use_window, double window_z, int32_t* counts);
 
+/* ---- catalogue matching: compare_clusters (catalog_matching.py:21-111) -------------------------------------------
+ * sample: (S, >=3) rows [ra, dec, z] of found clusters; catalogue: (C, >=3) rows [ra, dec, z] of a published survey.
+ * Per catalogue row i: match_row[i] = -2 when its z lies outside [min z_s - 0.1, max z_s + 0.1] (:66-68, such rows are
+ * dropped by the reference before indexing); otherwise the nearest sample row on the sky among those with
+ * |z_s - z_i| <= z_cut (:78-80, :89-91; ties: smallest squared chord, then smallest row -- pinned order D5) when its
+ * Vincenty separation is within the angle of :85-88 for `matching_distance_mpc_h`, else -1.  match_sep_deg[i] = that
+ * separation (nan when no sample row passes the cut).  Outputs are host (out_mem = 0) or device (1) arrays of C. */
+int fofb_match_catalog(fofb_handle* h, const fofb_params* p, const fofb_matrix* sample, const fofb_matrix* catalogue,
+                       double matching_distance_mpc_h, double z_cut, int32_t* match_row, double* match_sep_deg, int32_t out_mem,
+                       int64_t* n_matched);
+
 /* ---- transitive friends-of-friends (connected components) ------------------------------------------------------
  * NOT a reference code path (kencx/FoF never computes connected components): the lock-free
  * union-find mode named in BASELINE.json.  Galaxies i, j are friends iff each lies in the other's velocity window

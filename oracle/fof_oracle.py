@@ -741,3 +741,67 @@ def run_pipeline(df_values, p=None, mode="fast", seed=12345, zfilter=(0.5, 2.5),
     out["number_removed"] = removed
     out["virial"] = find_masses(cleaned)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Catalogue matching (catalog_matching.py:21-111) -- SURVEY section 8(f) item 3
+# ------------------------------------------------------------------------------------------------
+def matching_angle(d_mpc_h, z):
+    """catalog_matching.py:85-91: proper length -> angle -> comoving length (x D_M, flat: D_M = D_C) -> angle again;
+    degrees."""
+    first = linear_to_angular_dist(d_mpc_h, z)
+    comoving_mpc = np.deg2rad(first) * comoving_distance(z)
+    return proper_to_deg(comoving_mpc, z)
+
+
+def unit_vectors(ra_deg, dec_deg):
+    """astropy UnitSphericalRepresentation.to_cartesian."""
+    lon, lat = np.deg2rad(ra_deg), np.deg2rad(dec_deg)
+    return np.stack([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)], axis=-1)
+
+
+def compare_clusters(sample, catalog, matching_distance, z_cut=0.1, detail=False):
+    """catalog_matching.py:21-111 without logging / plotting.
+
+    sample: (S, 4) rows [ra, dec, z, richness]; catalog: (C, >=4) rows [ra, dec, z, richness, ...];
+    matching_distance in h^-1 Mpc.  Returns (sample_matched, catalog_matching_idx) over the catalogue rows that pass
+    the redshift filter of :66-68; detail=True adds (kept catalogue rows, matched sample index or -1, separation in
+    degrees of the nearest sample row or nan).
+
+    Pinned order D5: the nearest sample row is the one with the smallest squared chord between unit vectors,
+    ((dx*dx + dy*dy) + dz*dz) in float64, lowest index on exact ties (astropy asks a scipy cKDTree, whose tie order
+    is unspecified)."""
+    sample = np.asarray(sample, dtype=np.float64)
+    catalog = np.asarray(catalog)
+    z_arr = sample[:, 2]
+    lo, hi = min(z_arr), max(z_arr)
+    sample = sample[(sample[:, 2] >= lo - 0.1) & (sample[:, 2] <= hi + 0.1)]
+    kept = np.flatnonzero((catalog[:, 2] >= lo - 0.1) & (catalog[:, 2] <= hi + 0.1))
+    catalog = catalog[kept]
+    shape = len(catalog)
+    sample_matched = np.zeros((shape, 4))
+    catalog_matching_idx = np.zeros(shape)
+    match_row = np.full(shape, -1, dtype=np.int64)
+    match_sep = np.full(shape, np.nan)
+    sxyz = unit_vectors(sample[:, 0], sample[:, 1])
+    for i, c in enumerate(catalog):
+        cz = float(c[2])
+        rows = np.flatnonzero(np.abs(sample[:, 2] - cz) <= z_cut)
+        if not len(rows):
+            continue
+        max_sep = matching_angle(matching_distance, cz)
+        cxyz = unit_vectors(float(c[0]), float(c[1]))
+        d = sxyz[rows] - cxyz
+        chord2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        k = rows[int(np.argmin(chord2))]
+        sep = np.rad2deg(vincenty_rad(np.deg2rad(sample[k, 0]), np.deg2rad(sample[k, 1]),
+                                      np.deg2rad(float(c[0])), np.deg2rad(float(c[1]))))
+        match_sep[i] = sep
+        if sep <= max_sep:
+            catalog_matching_idx[i] = 1
+            sample_matched[i, :] = sample[k, :]
+            match_row[i] = k
+    sample_matched = sample_matched[np.all(sample_matched != 0, axis=1)]
+    if detail:
+        return sample_matched, catalog_matching_idx, kept, match_row, match_sep
+    return sample_matched, catalog_matching_idx
