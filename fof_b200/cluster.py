@@ -63,6 +63,11 @@ class Cluster:
         return state
 
     def __setstate__(self, state):
+        if isinstance(state, tuple):   # default slot pickling (None, {slot: value}), e.g. written by the reference
+            merged = {}
+            for part in state:
+                merged.update(part or {})
+            state = merged
         for name, value in state.items():
             setattr(self, name, value)
 

@@ -1,6 +1,7 @@
 """The hot-path helpers of /root/reference/FoF/helper.py with the same names and argument meaning:
 ``setdiff2d`` (helper.py:138-146), ``find_number_count`` (:149-188), ``center_overdensity`` (:191-221).
-Counting is done on the GPU (fofb_bubble_count); the plotting / LOWESS / FITS helpers are out of scope."""
+Counting is done on the GPU (fofb_bubble_count); ``export`` (helper.py:224-237) lives in fof_b200.io and is re-exported here;
+the plotting / LOWESS helpers are out of scope."""
 import numpy as np
 
 from . import _lib
@@ -8,6 +9,7 @@ from . import params as P
 from .analysis.methods import linear_to_angular_dist
 from .cluster import Cluster
 from .units import Q, as_float
+from .io import export  # noqa: F401  (helper.py:224-237)
 
 
 def setdiff2d(cluster1, cluster2):

@@ -89,6 +89,7 @@ def run_pipeline(ref, df, richness=None, overdensity=None, linking_length_factor
         cleaned, removed = ref.fof.interloper_removal(clusters)
         out["cleaned"] = [(cl.center_attributes.copy(), cl.galaxies.copy()) for cl in cleaned]
         out["number_removed"] = list(removed)
+        out["cleaned_objects"] = cleaned   # the reference's own Cluster instances (oracle/make_golden_io.py pickles them)
         virial = ref.mass_analysis.find_masses(cleaned, "virial")
         out["virial"] = [
             dict(center=v.center_attributes.copy(), galaxies=v.galaxies.copy(),
