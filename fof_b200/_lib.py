@@ -93,6 +93,7 @@ def load():
         "fofb_dist_set_merged": (C.c_int, [vp, vp, vp, i64, vp]),
         "fofb_pipeline_rerun": (C.c_int, [vp, dbl, i32, dbl, vp, P(i32), P(i64), P(i64)]),
         "fofb_bubble_count": (C.c_int, [vp, P(Params), P(Matrix), i64, vp, vp, i32, dbl, vp]),
+        "fofb_mt19937_words": (C.c_int, [vp, vp, vp, i64, vp, i32]),
         "fofb_match_catalog": (C.c_int, [vp, P(Params), P(Matrix), P(Matrix), dbl, dbl, vp, vp, i32, vp]),
         "fofb_dist_prefetch_mt": (C.c_int, [vp, vp, i32, i64]),
         "fofb_dist_local_clusters_dev": (C.c_int, [vp, vp, vp, vp]),
@@ -365,6 +366,20 @@ class Handle:
         self.lib.fofb_pipeline_stats(self.h, s.ctypes.data)
         return dict(zip(("galaxies_after_zcut", "candidate_centres", "stage1_clusters", "stage1_members",
                          "priority_rounds", "centres_evaluated", "stage4_clusters"), s.tolist()))
+
+    def mt19937_words(self, n_words, state=None):
+        """The next n_words raw 32-bit outputs of numpy's legacy generator, drawn on the device.  state: a
+        np.random.get_state() tuple (default: the global generator, which is advanced).  Returns (words, new_state)."""
+        use_global = state is None
+        st = np.random.get_state() if use_global else state
+        key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+        pos = C.c_int32(int(st[2]))
+        out = np.empty(int(n_words), dtype=np.uint32)
+        self.check(self.lib.fofb_mt19937_words(self.h, key.ctypes.data, C.byref(pos), int(n_words), out.ctypes.data, 0))
+        new_state = ("MT19937", key, pos.value, 0, 0.0)
+        if use_global:
+            np.random.set_state(new_state)
+        return out, new_state
 
     def match_catalog(self, sample, catalogue, params, matching_distance_mpc_h, z_cut=0.1):
         """(match_row int32[C], match_sep_deg float64[C], n_matched) -- see include/fofb.h fofb_match_catalog."""

@@ -17,6 +17,7 @@ void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre,
 void fof_overlap_external_rows(fofb_handle* h, FofState& S, int K, const double* centre_rows, const long long* off, long long total,
                                const double* ids, int* keep_out);
 void fof_set_merged(fofb_handle* h, FofState& S, const int* keep_local);
+void mt19937_words(fofb_handle* h, unsigned* key_host, int* pos_host, long long n_words, unsigned* out, int out_mem);
 }
 
 namespace fofb {
@@ -903,6 +904,21 @@ int fofb_bubble_count(fofb_handle* h, const fofb_params* p, const fofb_matrix* p
   }
   h->bubble->count(h, *p, v, (int)n_centres, centres, radius_deg, use_window, window_z, counts);
   timer.stop();
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+// ---- numpy's legacy MT19937 stream on the device (the generator behind fofb_*_finish_mt) ------------------------
+int fofb_mt19937_words(fofb_handle* h, uint32_t* key624, int32_t* pos, int64_t n_words, uint32_t* out, int32_t out_mem) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  FOFB_REQUIRE(out || n_words == 0, "mt19937 words: null output");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  Timed timer(h);
+  int p = pos ? *pos : -1;
+  mt19937_words(h, key624, &p, n_words, out, out_mem);
+  timer.stop();
+  *pos = p;
   return FOFB_OK;
   FOFB_CATCH(h)
 }

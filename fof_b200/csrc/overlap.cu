@@ -7,6 +7,7 @@
 #include <ctime>
 
 #include "fof_stage.cuh"
+#include "mt_jump_tables.h"
 
 namespace fofb {
 
@@ -675,8 +676,8 @@ __global__ void k_scale_points(long long total, int npts, const double* u, doubl
 
 // ---- numpy's legacy MT19937 on the device ------------------------------------------------------------------
 // center_overdensity (helper.py:196-202) consumes np.random's global MT19937 stream: 2 words per double,
-// (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.  One CTA advances the 624-word state block by block (three
-// dependent phases of 227 / 227 / 170 words) and writes the tempered words; a second kernel turns them into points.
+// (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.  k_mt19937_chunks writes the tempered words (one CTA per chunk of the
+// stream, after a polynomial jump to the chunk's start); a second kernel turns them into points.
 __device__ __forceinline__ unsigned mt_twist(unsigned u, unsigned v) {
   const unsigned y = (u & 0x80000000u) | (v & 0x7fffffffu);
   return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
@@ -690,36 +691,91 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y) {
   return y;
 }
 
-// Generates `nblocks` new state blocks after `key` (624 raw words) and writes their tempered words to
-// out[0 .. 624*nblocks); when first == 1 the unread tail key[pos .. 624) of the current block is tempered into
-// head[0 .. 624-pos) first.  The final raw state is written back to `key`.
-__global__ void __launch_bounds__(256) k_mt19937(unsigned* key, int pos, int first, unsigned* head, long long nblocks,
-                                                 unsigned* out) {
-  __shared__ unsigned buf[2][624];
-  const int tid = threadIdx.x;
-  for (int k = tid; k < 624; k += 256) buf[0][k] = key[k];
+// One regeneration: raw block `nx` from raw block `c` (three dependent phases of 227 / 227 / 170 words).
+__device__ __forceinline__ void mt_next_block(const unsigned* c, unsigned* nx, int tid) {
+  if (tid < 227) nx[tid] = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
   __syncthreads();
-  if (first)
-    for (int k = pos + tid; k < 624; k += 256) head[k - pos] = mt_temper(buf[0][k]);
-  int cur = 0;
-  for (long long b = 0; b < nblocks; ++b) {
-    unsigned* c = buf[cur];
-    unsigned* nx = buf[cur ^ 1];
-    if (tid < 227) nx[tid] = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
-    __syncthreads();
-    if (tid < 227) nx[227 + tid] = nx[tid] ^ mt_twist(c[227 + tid], c[228 + tid]);
-    __syncthreads();
-    if (tid < 170) {
-      const int k = 454 + tid;
-      nx[k] = nx[k - 227] ^ mt_twist(c[k], k == 623 ? nx[0] : c[k + 1]);
-    }
-    __syncthreads();
-    unsigned* o = out + b * 624;
-    for (int k = tid; k < 624; k += 256) o[k] = mt_temper(nx[k]);
-    cur ^= 1;
+  if (tid < 227) nx[227 + tid] = nx[tid] ^ mt_twist(c[227 + tid], c[228 + tid]);
+  __syncthreads();
+  if (tid < 170) {
+    const int k = 454 + tid;
+    nx[k] = nx[k - 227] ^ mt_twist(c[k], k == 623 ? nx[0] : c[k + 1]);
   }
   __syncthreads();
-  for (int k = tid; k < 624; k += 256) key[k] = buf[cur][k];
+}
+
+constexpr int kMtThreads = 640;
+constexpr int kMtSeqBlocks = 33;  // 19937 + 623 raw words fit in 33 blocks
+constexpr size_t kMtSmemBytes = sizeof(unsigned) * (kMtSeqBlocks * 624 + 624);
+
+// Generates `nblocks` new state blocks after `key_in` (624 raw words) and writes their tempered words to
+// out[0 .. 624*nblocks); when first == 1 the unread tail key_in[pos .. 624) of the current block is tempered into
+// head[0 .. 624-pos) first.  The raw state after the last block goes to key_out (distinct from key_in).
+//
+// The stream is cut into chunks of kMtChunkBlocks blocks, one CTA each.  CTA c first jumps its copy of the state
+// c * kMtChunkBlocks blocks ahead: the transition is linear over GF(2), so the block J words ahead is g(A) x with
+// g = t^J mod (minimal polynomial), evaluated as a correlation -- word j of the jumped block is the XOR over the set
+// coefficients i of g of raw word x[i + j] of the sequence starting at the current block (33 blocks of it, in
+// shared memory).  kMtJump[k] holds g for 2^k chunks (scripts/make_mt_jump.py, checked against numpy); the binary
+// digits of c are applied one after the other.  The jumped block may differ from the true one in the low 31 bits of
+// word 0, which never reach an output or a later block.
+__global__ void __launch_bounds__(kMtThreads) k_mt19937_chunks(const unsigned* key_in, unsigned* key_out, int pos, int first,
+                                                               unsigned* head, long long nblocks, unsigned* out) {
+  extern __shared__ unsigned mt_smem[];
+  unsigned* seq = mt_smem;
+  unsigned* poly = mt_smem + kMtSeqBlocks * 624;
+  const int tid = threadIdx.x;
+  const long long c = blockIdx.x, nchunks = gridDim.x;
+  if (tid < 624) seq[tid] = key_in[tid];
+  __syncthreads();
+  if (c == 0 && first)
+    for (int k = pos + tid; k < 624; k += kMtThreads) head[k - pos] = mt_temper(seq[k]);
+  for (int k = 0; (c >> k) != 0; ++k) {
+    if (!((c >> k) & 1)) continue;
+    for (int b = 0; b + 1 < kMtSeqBlocks; ++b) mt_next_block(seq + b * 624, seq + (b + 1) * 624, tid);
+    if (tid < 624) poly[tid] = kMtJump[k][tid];
+    __syncthreads();
+    unsigned acc = 0;
+    if (tid < 624) {
+      for (int w = 0; w < 624; ++w) {
+        unsigned bits = poly[w];
+        const unsigned* base = seq + w * 32 + tid;
+        while (bits) {
+          acc ^= base[__ffs(bits) - 1];
+          bits &= bits - 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 624) seq[tid] = acc;
+    __syncthreads();
+  }
+  const long long b0 = c * kMtChunkBlocks;
+  const long long b1 = c == nchunks - 1 ? nblocks : b0 + kMtChunkBlocks;
+  int cur = 0;
+  for (long long b = b0; b < b1; ++b) {
+    const unsigned* cb = seq + cur * 624;
+    unsigned* nx = seq + (cur ^ 1) * 624;
+    mt_next_block(cb, nx, tid);
+    if (tid < 624) out[b * 624 + tid] = mt_temper(nx[tid]);
+    cur ^= 1;
+  }
+  if (c == nchunks - 1 && tid < 624) key_out[tid] = seq[cur * 624 + tid];
+}
+
+// key_in = mt_key[0 .. 624) (or the previous final state), key_out = mt_key[1248 .. 1872)
+static void launch_mt19937(fofb_handle* h, cudaStream_t st, const unsigned* key_in, unsigned* key_out, int pos, int first,
+                           unsigned* head, long long nblocks, unsigned* out) {
+  static bool configured = false;
+  if (!configured) {
+    FOFB_CUDA(cudaFuncSetAttribute(k_mt19937_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMtSmemBytes));
+    configured = true;
+  }
+  long long nchunks = (nblocks + kMtChunkBlocks - 1) / kMtChunkBlocks;
+  nchunks = std::min<long long>(std::max<long long>(nchunks, 1), 1ll << kMtJumpTables);
+  k_mt19937_chunks<<<(unsigned)nchunks, kMtThreads, kMtSmemBytes, st>>>(key_in, key_out, pos, first, head, nblocks, out);
+  count_launch(h);
+  FOFB_CUDA(cudaGetLastError());
 }
 
 // raw state block from its tempered words (the tempering transform is a bijection)
@@ -748,6 +804,33 @@ __global__ void k_points_from_words(long long total, int npts, const unsigned* w
   dec[q] = __dadd_rn(dec_lo, __dmul_rn(dec_range, ud));
 }
 
+// The next n_words 32-bit outputs of numpy's legacy generator in state (key, pos), and the state after them
+// (fofb_mt19937_words: the device generator on its own, for checks against np.random).
+void mt19937_words(fofb_handle* h, unsigned* key_host, int* pos_host, long long n_words, unsigned* out, int out_mem) {
+  FOFB_REQUIRE(key_host && pos_host && *pos_host >= 0 && *pos_host <= 624 && n_words >= 0, "bad MT19937 state");
+  if (n_words == 0) return;
+  cudaStream_t st = h->stream;
+  const int pos = *pos_host;
+  const long long head = 624 - pos;
+  const long long nblocks = n_words > head ? (n_words - head + 623) / 624 : 0;
+  DBuf<unsigned> key, words;
+  key.alloc(624 * 3);
+  words.alloc((size_t)(624 + std::max<long long>(nblocks, 1) * 624));
+  FOFB_CUDA(cudaMemcpyAsync(key.p, key_host, sizeof(unsigned) * 624, cudaMemcpyHostToDevice, st));
+  // tempered words are laid out contiguously: the unread tail of the current block, then the new blocks
+  unsigned* base = words.p + pos;  // so that word t of the request is base[t]
+  launch_mt19937(h, st, key.p, key.p + 624, pos, 1, base, nblocks, base + head);
+  FOFB_CUDA(cudaMemcpyAsync(out, base, sizeof(unsigned) * (size_t)n_words, out_mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (n_words <= head) {
+    *pos_host = pos + (int)n_words;
+  } else {
+    const long long rem = n_words - head;
+    FOFB_CUDA(cudaMemcpyAsync(key_host, key.p + 624, sizeof(unsigned) * 624, cudaMemcpyDeviceToHost, st));
+    *pos_host = (int)(rem - (nblocks - 1) * 624);
+  }
+  FOFB_CUDA(cudaStreamSynchronize(st));
+}
+
 // Start generating the stream on a side stream while stages 0-3 run: enough words for k_spec clusters.
 void FofState::mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec) {
   FOFB_REQUIRE(key_host && pos >= 0 && pos <= 624, "bad MT19937 state");
@@ -759,13 +842,11 @@ void FofState::mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, lo
   mt_head = 624 - pos;
   const long long W = std::max<long long>(k_spec, 1) * params_n_random_hint * 4;
   mt_blocks = std::max<long long>((W - mt_head + 623) / 624, 1);
-  unsigned* key = mt_key.alloc(624 * 2);
+  unsigned* key = mt_key.alloc(624 * 4);  // [0] input state, [1] untempered output, [2] state after the stream, [3] scratch
   unsigned* words = mt_words.alloc((size_t)(624 + mt_blocks * 624));
   std::memcpy(mt_key_host, key_host, sizeof(unsigned) * 624);
   FOFB_CUDA(cudaMemcpyAsync(key, mt_key_host, sizeof(unsigned) * 624, cudaMemcpyHostToDevice, rng_stream));
-  k_mt19937<<<1, 256, 0, rng_stream>>>(key, pos, 1, words, mt_blocks, words + 624);
-  count_launch(h);
-  FOFB_CUDA(cudaGetLastError());
+  launch_mt19937(h, rng_stream, key, key + 1248, pos, 1, words, mt_blocks, words + 624);
   FOFB_CUDA(cudaEventRecord(rng_done, rng_stream));
   mt_prefetched = true;
 }
@@ -808,7 +889,8 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
     FOFB_CUDA(cudaStreamSynchronize(st));
     std::swap(bigger.p, mt_words.p);
     std::swap(bigger.cap, mt_words.cap);
-    FOFB_PROFILED(h, "k_mt19937", k_mt19937<<<1, 256, 0, st>>>(mt_key.p, 624, 0, nullptr, extra, mt_words.p + 624 + mt_blocks * 624));
+    launch_mt19937(h, st, mt_key.p + 1248, mt_key.p + 1872, 624, 0, nullptr, extra, mt_words.p + 624 + mt_blocks * 624);
+    FOFB_CUDA(cudaMemcpyAsync(mt_key.p + 1248, mt_key.p + 1872, sizeof(unsigned) * 624, cudaMemcpyDeviceToDevice, st));
     mt_blocks = need_blocks;
   }
   double* pts = unit_pts.alloc((size_t)total * 2);

@@ -165,6 +165,11 @@ int fofb_projected_mass(fofb_handle* h, const fofb_params* p, int64_t K, const i
                         double* out);
 int fofb_bootstrap_indices(int64_t n, int64_t count, int32_t* out);
 
+/* The device generator behind fofb_*_finish_mt on its own: the next n_words 32-bit outputs of numpy's legacy MT19937
+ * (np.random.get_state(): key624, pos) into out (host, or device when out_mem = 1); key624 / pos are advanced exactly as
+ * np.random would be.  The stream is produced in parallel chunks reached by polynomial jump-ahead. */
+int fofb_mt19937_words(fofb_handle* h, uint32_t* key624, int32_t* pos, int64_t n_words, uint32_t* out, int32_t out_mem);
+
 /* ---- whole job: pipeline.py:62-64,80-99,113,173 with every intermediate on the device ---------------------
  * fofb_pipeline_begin : candidate_center_search on `galaxies` (n x 7), the z cuts of pipeline.py:80-86
  *                       (galaxies zmin <= z <= zmax_gal, centres zmin <= z <= zmax_cen), FoF() stages 1-3.
