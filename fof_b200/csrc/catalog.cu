@@ -9,9 +9,11 @@ namespace fofb {
 __global__ void k_extract(View rows, int n, double* ra, double* dec, double* z, int* idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  ra[i] = rows.at(i, 0);
-  dec[i] = rows.at(i, 1);
-  z[i] = rows.at(i, 2);
+  // NaN would slip through the min/max reductions of the bounding box: store +inf so that Catalog::build refuses it
+  const double a = rows.at(i, 0), d = rows.at(i, 1), zz = rows.at(i, 2);
+  ra[i] = isfinite(a) ? a : INFINITY;
+  dec[i] = isfinite(d) ? d : INFINITY;
+  z[i] = isfinite(zz) ? zz : INFINITY;
   idx[i] = i;
 }
 

@@ -766,11 +766,8 @@ __global__ void __launch_bounds__(kMtThreads) k_mt19937_chunks(const unsigned* k
 // key_in = mt_key[0 .. 624) (or the previous final state), key_out = mt_key[1248 .. 1872)
 static void launch_mt19937(fofb_handle* h, cudaStream_t st, const unsigned* key_in, unsigned* key_out, int pos, int first,
                            unsigned* head, long long nblocks, unsigned* out) {
-  static bool configured = false;
-  if (!configured) {
-    FOFB_CUDA(cudaFuncSetAttribute(k_mt19937_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMtSmemBytes));
-    configured = true;
-  }
+  // per device, so set on every launch (a handle may live on any device of the process)
+  FOFB_CUDA(cudaFuncSetAttribute(k_mt19937_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMtSmemBytes));
   long long nchunks = (nblocks + kMtChunkBlocks - 1) / kMtChunkBlocks;
   nchunks = std::min<long long>(std::max<long long>(nchunks, 1), 1ll << kMtJumpTables);
   k_mt19937_chunks<<<(unsigned)nchunks, kMtThreads, kMtSmemBytes, st>>>(key_in, key_out, pos, first, head, nblocks, out);

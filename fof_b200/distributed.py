@@ -357,7 +357,8 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     lids = torch.empty(max(tot_loc, 1), dtype=f64, device=dev)[:tot_loc]
     if K_loc:
         h.check(L.fofb_dist_local_clusters_dev(h.h, lc.data_ptr(), ls.data_ptr(), lids.data_ptr()))
-    meta = torch.cat([loc_rows[lc.long()], key[lc.long()].to(f64).unsqueeze(1), ls.to(f64).unsqueeze(1)], dim=1)  # K x 10
+    # the int64 priority key travels as its bit pattern (N * 2^40 exceeds 2^53 for N >= 8192)
+    meta = torch.cat([loc_rows[lc.long()], key[lc.long()].view(f64).unsqueeze(1), ls.to(f64).unsqueeze(1)], dim=1)  # K x 10
     g_meta = comm.allgatherv_t(meta)
     g_ids = comm.allgatherv_t(lids)
     kcounts = [len(x) for x in g_meta]
@@ -368,7 +369,7 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     cl_owner = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(kcounts)]) if K_glob else \
         torch.zeros(0, dtype=torch.int32, device=dev)
     if K_glob:
-        corder = torch.argsort(M_all[:, 8], descending=True)  # priority order = the order fof.py:232 appends clusters
+        corder = torch.argsort(M_all[:, 8].contiguous().view(i64), descending=True)  # priority order = the order fof.py:232 appends clusters
         sizes_all = M_all[:, 9].to(i64)
         starts = torch.cumsum(sizes_all, 0) - sizes_all
         sizes_s = sizes_all[corder]
@@ -409,14 +410,14 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
 
     # ---- the global catalogue, in priority order -------------------------------------------------------------
     cidx_t = cidx32.long()
-    fmeta = torch.cat([key[cidx_t].to(f64).unsqueeze(1), loc_grow[cidx_t].to(f64).unsqueeze(1),
+    fmeta = torch.cat([key[cidx_t].view(f64).unsqueeze(1), loc_grow[cidx_t].to(f64).unsqueeze(1),
                        (off_t[1:] - off_t[:-1]).to(f64).unsqueeze(1), N_t.unsqueeze(1), D_t.unsqueeze(1), props_t],
                       dim=1) if Kf else torch.zeros((0, 13), dtype=f64, device=dev)
     f_meta = cat0(comm.allgatherv_t(fmeta))
     f_rows = cat0(comm.allgatherv_t(grow_t[rows_t.long()] if total else torch.zeros(0, dtype=i64, device=dev)))
     Kt = len(f_meta)
     if Kt:
-        fo = torch.argsort(f_meta[:, 0], descending=True)
+        fo = torch.argsort(f_meta[:, 0].contiguous().view(i64), descending=True)
         fs_all = f_meta[:, 2].to(i64)
         fstarts = torch.cumsum(fs_all, 0) - fs_all
         fs = fs_all[fo]

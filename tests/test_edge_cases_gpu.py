@@ -95,6 +95,13 @@ def test_unsupported_inputs_are_refused(lib):
     with pytest.raises(_lib.FofbError) as e:
         h.fof_run(dup, cand, _lib.default_params())
     assert e.value.code == -5
-    # (c) bad shapes
+    # (c) non-finite coordinates / redshifts, declinations off the sphere
+    for col, val in ((0, np.nan), (1, np.nan), (2, np.nan), (0, np.inf), (2, -np.inf), (1, 91.0)):
+        broken = arr.copy()
+        broken[17, col] = val
+        with pytest.raises(_lib.FofbError) as e:
+            h.number_counts(broken, _lib.default_params())
+        assert e.value.code == -1, (col, val)
+    # (d) bad shapes
     with pytest.raises(_lib.FofbError):
         h.fof_run(main_arr[:, :5], cand[:, :5], _lib.default_params())
