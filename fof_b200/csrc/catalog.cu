@@ -6,9 +6,13 @@
 namespace fofb {
 
 // ---- K1a: pull (ra, dec, z) out of the strided row matrix; NaN rows are refused later ----------
-__global__ void k_extract(View rows, int n, double* ra, double* dec, double* z, int* idx) {
+__global__ void k_extract(View rows, int n, double* ra, double* dec, double* z, int* idx, int* unsorted) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (i > 0) {  // the reference's pipeline hands over rows ordered by redshift (pipeline.py:47,56): detect that
+    const double prev = rows.at(i - 1, 2);
+    if (!((isfinite(prev) ? prev : INFINITY) <= (isfinite(rows.at(i, 2)) ? rows.at(i, 2) : INFINITY))) *unsorted = 1;
+  }
   // NaN would slip through the min/max reductions of the bounding box: store +inf so that Catalog::build refuses it
   const double a = rows.at(i, 0), d = rows.at(i, 1), zz = rows.at(i, 2);
   ra[i] = isfinite(a) ? a : INFINITY;
@@ -113,15 +117,25 @@ void Catalog::build(fofb_handle* h, const View& rows_in) {
   double* dec = dec_row.alloc(n);
   double* z = z_row.alloc(n);
   int* idx = idx_tmp.alloc(n);
-  FOFB_PROFILED(h, "k_extract", k_extract<<<grid_for(n, B), B, 0, st>>>(rows, ni, ra, dec, z, idx));
+  int* unsorted = sorted_flag.alloc(1);
+  FOFB_CUDA(cudaMemsetAsync(unsorted, 0, sizeof(int), st));
+  FOFB_PROFILED(h, "k_extract", k_extract<<<grid_for(n, B), B, 0, st>>>(rows, ni, ra, dec, z, idx, unsorted));
+  int host_unsorted = 0;
+  FOFB_CUDA(cudaMemcpyAsync(&host_unsorted, unsorted, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
 
-  // K2a: stable radix sort by redshift
+  // K2a: stable radix sort by redshift -- the identity when the rows already come in redshift order
   double* zs_p = zs.alloc(n);
   int* zorder_p = zorder.alloc(n);
   size_t bytes = 0;
-  FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, z, zs_p, idx, zorder_p, ni, 0, 64, st));
-  FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, z, zs_p, idx, zorder_p, ni, 0, 64, st));
-  count_launch(h, 8);
+  if (host_unsorted) {
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, z, zs_p, idx, zorder_p, ni, 0, 64, st));
+    FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, z, zs_p, idx, zorder_p, ni, 0, 64, st));
+    count_launch(h, 8);
+  } else {
+    FOFB_CUDA(cudaMemcpyAsync(zs_p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    FOFB_CUDA(cudaMemcpyAsync(zorder_p, idx, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+  }
   double* zra_p = zra.alloc(n);
   double* zdec_p = zdec.alloc(n);
   int* rank_p = rank.alloc(n);

@@ -29,7 +29,7 @@ struct Catalog {
 
   DBuf<double> ra_row, dec_row, z_row;  // row order
   DBuf<double> zs, zra, zdec;           // z-rank order
-  DBuf<int> zorder, rank, idx_tmp;
+  DBuf<int> zorder, rank, idx_tmp, sorted_flag;
   DBuf<double4> pre, suf, levels, gbox_dev;
 
   void build(fofb_handle* h, const View& rows);  // z sort + range-bbox tables

@@ -75,6 +75,16 @@ def test_random_small_catalogues(lib, seed):
              D=float(rng.choice([-1e9, 0.0, 2.0])), seed=seed)
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_rows_not_sorted_by_redshift(lib, seed):
+    """The reference's pipeline hands over rows ordered by redshift, and the device path skips its redshift sort when it
+    sees that; shuffled rows must take the sorting path and still match the oracle (row order enters D1 / D2)."""
+    arr = make_catalog(2500, seed=31 + seed, as_frame=False)
+    arr = arr[np.random.default_rng(seed).permutation(len(arr))]
+    assert np.any(np.diff(arr[:, 2]) < 0)
+    assert len(_compare(arr, rich=8, D=0.0)) > 0
+
+
 def test_unsupported_inputs_are_refused(lib):
     """Degenerate inputs the device path documents as unsupported fail loudly instead of diverging."""
     from fof_b200 import _lib
