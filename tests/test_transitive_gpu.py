@@ -33,6 +33,13 @@ def test_percolating_blobs_deep_chains(lib):
     assert counts.max() > 1500  # the blobs percolate
     want, _ = T.labels(arr, 1.0)
     assert np.array_equal(got, want)
+    runs, n_groups_r, _ = transitive.friends_of_friends(arr, linking_length=1.0, count_links=False)   # run-based kernel
+    assert np.array_equal(runs, want) and n_groups_r == n_groups
+    # pair-by-pair kernel and run-based kernel agree on a blob catalogue the oracle cannot reach
+    mid = make_catalog(300000, seed=12, kind="dense", n_blobs=5, as_frame=False)
+    a, ga, _ = transitive.friends_of_friends(mid, linking_length=1.0)
+    b, gb, _ = transitive.friends_of_friends(mid, linking_length=1.0, count_links=False)
+    assert np.array_equal(a, b) and ga == gb
     # the same at a size the oracle cannot reach: size-independent invariants only
     big = make_catalog(2000000, seed=10, kind="dense", n_blobs=12, as_frame=False)
     lab, n_groups, links = transitive.friends_of_friends(big, linking_length=1.0, count_links=False)
