@@ -42,10 +42,11 @@ __device__ __forceinline__ double np_pairwise_leaf(F get, long long lo, long lon
   return res;
 }
 
-template <class F>
-__device__ double np_pairwise_sum(F get, long long lo, long long n) {
-  if (n <= 128) return np_pairwise_leaf(get, lo, n);
-  // numpy recurses on halves (n2 = n/2 rounded down to a multiple of 8); explicit post-order stack
+// numpy's recursion on halves (n2 = n/2 rounded down to a multiple of 8) as an explicit post-order stack; `leaf`
+// evaluates a block of <= 128 elements.
+template <class L>
+__device__ double np_pairwise_tree(L leaf, long long lo, long long n) {
+  if (n <= 128) return leaf(lo, n);
   long long s_lo[40], s_n[40];
   double s_left[40];
   int s_state[40];
@@ -55,7 +56,7 @@ __device__ double np_pairwise_sum(F get, long long lo, long long n) {
   while (sp >= 0) {
     const long long cl = s_lo[sp], cn = s_n[sp];
     if (cn <= 128) {
-      ret = np_pairwise_leaf(get, cl, cn);
+      ret = leaf(cl, cn);
       --sp;
       continue;
     }
@@ -76,6 +77,52 @@ __device__ double np_pairwise_sum(F get, long long lo, long long n) {
     }
   }
   return ret;
+}
+
+template <class F>
+__device__ double np_pairwise_sum(F get, long long lo, long long n) {
+  return np_pairwise_tree([&](long long l, long long c) -> double { return np_pairwise_leaf(get, l, c); }, lo, n);
+}
+
+// The same sum by a whole CTA, bit for bit: thread 0 lists the leaves of the recursion, the threads evaluate them
+// (each leaf is serial, as in numpy), thread 0 adds them up along the same tree.  Falls back to the serial walk when
+// the leaf table is too small.  All threads of the block must call it; the result is returned to every thread.
+constexpr int kPwLeaves = 2048;
+struct PairwiseScratch {
+  int lo[kPwLeaves];
+  short cnt[kPwLeaves];
+  double sum[kPwLeaves];
+  int nleaves;
+  double result;
+};
+
+template <class F>
+__device__ double cta_pairwise_sum(F get, long long n, PairwiseScratch& sc) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) {
+    int nl = 0;
+    np_pairwise_tree([&](long long l, long long c) -> double {
+      if (nl < kPwLeaves) { sc.lo[nl] = (int)l; sc.cnt[nl] = (short)c; }
+      ++nl;
+      return 0.0;
+    }, 0, n);
+    sc.nleaves = nl;
+  }
+  __syncthreads();
+  const int nl = sc.nleaves;
+  if (nl > kPwLeaves) {
+    if (tid == 0) sc.result = np_pairwise_sum(get, 0, n);
+  } else {
+    for (int t = tid; t < nl; t += blockDim.x) sc.sum[t] = np_pairwise_leaf(get, sc.lo[t], sc.cnt[t]);
+    __syncthreads();
+    if (tid == 0) {
+      int next = 0;
+      sc.result = np_pairwise_tree([&](long long, long long) -> double { return sc.sum[next++]; }, 0, n);
+    }
+  }
+  __syncthreads();
+  return sc.result;
 }
 
 // ---- K12a: per member velocity and projected radius (fof.py:418-431) ---------------------------------
@@ -150,14 +197,20 @@ __global__ void k_bin_members(int K, const long long* off, const double* rad, in
 }
 
 // ---- K12c: iterative 3-sigma clipping of one radial bin, one thread per (cluster, bin) (fof.py:439-492)
+// Bins longer than kBigBin are left to the batched path (k_big_*); clusters of at most n_smem members belong to
+// k_clip_bins_smem.
+constexpr int kBigBin = 256;
+
 __global__ void k_clip_bins(int K, int nbins, const long long* off, const double* vel, const double* rad, int* perm,
-                            const int* bin_start, double* dev, int* kept) {
+                            const int* bin_start, double* dev, int* kept, int n_smem) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)K * nbins) return;
   const int k = (int)(g / nbins), b = (int)(g % nbins) + 1;
   const long long s0 = off[k];
+  if (off[k + 1] - s0 <= n_smem) return;
   const int* bs = bin_start + (long long)k * (nbins + 2);
   const int lo = bs[b], hi = (b == nbins) ? bs[nbins + 1] : bs[b + 1];
+  if (hi - lo > kBigBin) return;
   int* p = perm + s0 + lo;   // this bin's members (positions inside the cluster), reordered in place
   double* d = dev + s0 + lo;
   int len = hi - lo;
@@ -206,12 +259,13 @@ __global__ void k_clip_bins(int K, int nbins, const long long* off, const double
 // cluster, lane b-1 owns radial bin b.  The serial chains of dependent loads then cost ~30 cycles instead of an L2
 // round trip each.  Dynamic shared memory: n_max * 21 bytes (launched only when that fits).
 __global__ void __launch_bounds__(32) k_clip_bins_smem(int K, int nbins, const long long* off, const double* vel, const double* rad,
-                                                       int* perm, const int* bin_start, int* kept) {
+                                                       int* perm, const int* bin_start, int* kept, int n_smem) {
   extern __shared__ double smem_d[];
   const int k = blockIdx.x;
   if (k >= K) return;
   const long long s0 = off[k];
   const int n = (int)(off[k + 1] - s0);
+  if (n > n_smem) return;
   const int lane = threadIdx.x;
   double* sv = smem_d;                                       // velocity by position in the cluster
   double* sd = sv + n;                                       // deviation scratch, by slot
@@ -226,6 +280,7 @@ __global__ void __launch_bounds__(32) k_clip_bins_smem(int K, int nbins, const l
   const int* bs = bin_start + (long long)k * (nbins + 2);
   for (int b = lane + 1; b <= nbins; b += 32) {
     const int lo = bs[b], hi = (b == nbins) ? bs[nbins + 1] : bs[b + 1];
+    if (hi - lo > kBigBin) continue;
     int* p = sp + lo;
     double* d = sd + lo;
     int len = hi - lo;
@@ -272,6 +327,122 @@ __global__ void __launch_bounds__(32) k_clip_bins_smem(int K, int nbins, const l
   for (int i = lane; i < n; i += 32) perm[s0 + i] = sp[i];
 }
 
+// ---- K12d: long bins, all of them together, one clipping iteration per round of launches -------------------------
+// A bin of 10^4..10^5 members cannot be clipped by one thread (the insertion sort alone is quadratic).  The batched
+// path keeps the arithmetic of fof.py:439-492 bit for bit -- numpy's pairwise means over the members in their current
+// order, the stable argsort by deviation -- but spreads it: a CTA per bin for the exact means, one segmented stable
+// sort over all long bins, a CTA per bin for the 3-sigma decision.  Only the dispersion, a sequential builtin sum()
+// in the reference, is reduced in parallel; it decides a comparison, and when the two sides are within 1e-9 of each
+// other thread 0 repeats it in the reference's order.
+__global__ void k_big_list(int K, int nbins, const long long* off, const int* bin_start, int* count, int* big_begin, int* big_len,
+                           int* big_slot) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)K * nbins) return;
+  const int k = (int)(g / nbins), b = (int)(g % nbins) + 1;
+  const int* bs = bin_start + (long long)k * (nbins + 2);
+  const int lo = bs[b], hi = (b == nbins) ? bs[nbins + 1] : bs[b + 1];
+  if (hi - lo <= kBigBin) return;
+  const int i = atomicAdd(count, 1);
+  big_begin[i] = (int)(off[k] + lo);   // position of the bin inside perm / dev (total < 2^31)
+  big_len[i] = hi - lo;
+  big_slot[i] = (int)g;                // where its kept count goes
+}
+
+// exact mean of the bin in its current order, deviations, and the segment [begin, end) for the sort
+__global__ void __launch_bounds__(256) k_big_mean_dev(int nb, const int* big_begin, const int* big_len, const int* big_active,
+                                                      const long long* cl_off_of_pos, const double* vel, const int* perm,
+                                                      double* dev, int* seg_begin, int* seg_end) {
+  __shared__ PairwiseScratch sc;
+  const int i = blockIdx.x;
+  if (i >= nb) return;
+  const int begin = big_begin[i], len = big_len[i];
+  const bool act = big_active[i] && len > 2;
+  if (threadIdx.x == 0) {
+    seg_begin[i] = begin;
+    seg_end[i] = act ? begin + len : begin;
+  }
+  if (!act) return;
+  const long long s0 = cl_off_of_pos[i];
+  const int* p = perm + begin;
+  auto getv = [&](long long t) -> double { return vel[s0 + p[t]]; };
+  const double mean = __ddiv_rn(cta_pairwise_sum(getv, len, sc), (double)len);
+  for (int t = threadIdx.x; t < len; t += blockDim.x) dev[begin + t] = fabs(__dsub_rn(vel[s0 + p[t]], mean));
+}
+
+__global__ void __launch_bounds__(256) k_big_decide(int nb, const int* big_begin, int* big_len, int* big_active,
+                                                    const long long* cl_off_of_pos, const double* vel, const double* rad,
+                                                    int* perm, const int* perm_sorted, int* any_changed) {
+  __shared__ PairwiseScratch sc;
+  typedef cub::BlockReduce<double, 256> Reduce;
+  __shared__ typename Reduce::TempStorage rtmp;
+  __shared__ double s_acc;
+  const int i = blockIdx.x;
+  if (i >= nb) return;
+  const int begin = big_begin[i], len = big_len[i];
+  if (!big_active[i]) return;
+  if (len <= 2) {
+    if (threadIdx.x == 0) big_active[i] = 0;
+    return;
+  }
+  const long long s0 = cl_off_of_pos[i];
+  int* p = perm + begin;
+  for (int t = threadIdx.x; t < len; t += blockDim.x) p[t] = perm_sorted[begin + t];
+  __syncthreads();
+  const int last = p[len - 1];
+  bool removed = false;
+  if (rad[s0 + last] != 0.0) {  // the largest deviation is not the cluster centre itself
+    const int m = len - 1;
+    if (m > 1) {
+      auto getv = [&](long long t) -> double { return vel[s0 + p[t]]; };
+      const double bin_mean = __ddiv_rn(cta_pairwise_sum(getv, m, sc), (double)m);
+      double part = 0.0;
+      for (int t = threadIdx.x; t < m; t += blockDim.x) {
+        const double x = vel[s0 + p[t]] - bin_mean;
+        part += x * x;
+      }
+      double acc = Reduce(rtmp).Sum(part);
+      if (threadIdx.x == 0) {
+        const double lhs = fabs(__dsub_rn(vel[s0 + last], bin_mean));
+        double rhs = __dmul_rn(3.0, sqrt(__ddiv_rn(acc, (double)(m - 1))));
+        if (fabs(lhs - rhs) <= 1e-9 * rhs) {  // too close to call: builtin sum(), sequential, as the reference
+          acc = 0.0;
+          for (int t = 0; t < m; ++t) {
+            const double x = __dsub_rn(vel[s0 + p[t]], bin_mean);
+            acc = __dadd_rn(acc, __dmul_rn(x, x));
+          }
+          rhs = __dmul_rn(3.0, sqrt(__ddiv_rn(acc, (double)(m - 1))));
+        }
+        s_acc = lhs > rhs ? 1.0 : 0.0;
+      }
+      __syncthreads();
+      removed = s_acc != 0.0;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (removed) {
+      big_len[i] = len - 1;
+      *any_changed = 1;
+    } else {
+      big_active[i] = 0;
+    }
+  }
+}
+
+__global__ void k_fill_i32(int n, int* out, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+__global__ void k_big_finish(int nb, const int* big_len, const int* big_slot, int* kept) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) kept[big_slot[i]] = big_len[i];
+}
+
+__global__ void k_big_cluster_off(int nb, int K, const long long* off, const int* big_slot, int nbins, long long* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) out[i] = off[big_slot[i] / nbins];
+}
+
 __global__ void k_max_cluster_len(int K, const long long* off, int* out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < K) atomicMax(out, (int)(off[k + 1] - off[k]));
@@ -299,6 +470,53 @@ __global__ void k_emit_cleaned(int K, int nbins, const long long* off, const int
     for (int t = lane; t < len; t += 32) out_index[dst + t] = perm[s0 + lo + t];
     dst += len;
   }
+}
+
+// Long bins (more than kBigBin members): see K12d above.
+void CleanState::clip_big_bins(fofb_handle* h, int K, int nbins, const long long* off, long long total, const double* vel,
+                               const double* rad, double* dev, int* perm, const int* bstart, int* kept) {
+  cudaStream_t st = h->stream;
+  FOFB_REQUIRE(total < (1ll << 31), "three_sigma: more than 2^31 members");
+  const size_t cap = (size_t)(total / kBigBin) + 1;  // at most this many long bins
+  int* cnt = d_big_count.alloc(2);
+  int* bb = d_big_begin.alloc(cap);
+  int* bl = d_big_len.alloc(cap);
+  int* bsl = d_big_slot.alloc(cap);
+  FOFB_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(int), st));
+  k_big_list<<<grid_for((int64_t)K * nbins, 256), 256, 0, st>>>(K, nbins, off, bstart, cnt, bb, bl, bsl);
+  FOFB_LAUNCH_CHECK(h);
+  int nb = 0;
+  FOFB_CUDA(cudaMemcpyAsync(&nb, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FOFB_CUDA(cudaStreamSynchronize(st));
+  if (nb == 0) return;
+  int* act = d_big_active.alloc(nb);
+  int* sb = d_big_seg.alloc((size_t)nb * 2);
+  int* se = sb + nb;
+  long long* coff = d_big_off.alloc(nb);
+  double* dev_s = d_big_dev.alloc((size_t)total);
+  int* perm_s = d_big_perm.alloc((size_t)total);
+  int* changed = cnt + 1;
+  k_fill_i32<<<grid_for(nb, 256), 256, 0, st>>>(nb, act, 1);
+  FOFB_LAUNCH_CHECK(h);
+  k_big_cluster_off<<<grid_for(nb, 256), 256, 0, st>>>(nb, K, off, bsl, nbins, coff);
+  FOFB_LAUNCH_CHECK(h);
+  size_t bytes = 0;
+  FOFB_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, bytes, dev, dev_s, perm, perm_s, total, nb, sb, se, st));
+  unsigned char* tmp = cub_tmp(h, bytes);
+  for (int iter = 0;; ++iter) {
+    FOFB_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+    FOFB_PROFILED(h, "k_big_mean_dev", k_big_mean_dev<<<nb, 256, 0, st>>>(nb, bb, bl, act, coff, vel, perm, dev, sb, se));
+    FOFB_CUDA(cub::DeviceSegmentedSort::StableSortPairs(tmp, bytes, dev, dev_s, perm, perm_s, total, nb, sb, se, st));
+    count_launch(h, 4);
+    FOFB_PROFILED(h, "k_big_decide", k_big_decide<<<nb, 256, 0, st>>>(nb, bb, bl, act, coff, vel, rad, perm, perm_s, changed));
+    int any = 0;
+    FOFB_CUDA(cudaMemcpyAsync(&any, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    if (!any) break;
+    FOFB_REQUIRE(iter < (1 << 24), "three_sigma: clipping did not terminate");
+  }
+  k_big_finish<<<grid_for(nb, 256), 256, 0, st>>>(nb, bl, bsl, kept);
+  FOFB_LAUNCH_CHECK(h);
 }
 
 long long CleanState::three_sigma_core(fofb_handle* h, const fofb_params& p, int K, const long long* off, long long total,
@@ -329,16 +547,18 @@ long long CleanState::three_sigma_core(fofb_handle* h, const fofb_params& p, int
   int nmax = 0;
   FOFB_CUDA(cudaMemcpyAsync(&nmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
-  const size_t smem = (size_t)nmax * 21 + 64;
-  if (smem <= 200 * 1024) {
-    if (smem > 48 * 1024 && smem > clip_smem_set) {
-      FOFB_CUDA(cudaFuncSetAttribute(k_clip_bins_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      clip_smem_set = 200 * 1024;
-    }
-    FOFB_PROFILED(h, "k_clip_bins", k_clip_bins_smem<<<K, 32, smem, st>>>(K, nbins, off, vel, rad, perm, bstart, kept));
-  } else {
-    FOFB_PROFILED(h, "k_clip_bins", k_clip_bins<<<grid_for((int64_t)K * nbins, 64), 64, 0, st>>>(K, nbins, off, vel, rad, perm, bstart, dev, kept));
+  const int smem_cap = 200 * 1024;
+  const int n_smem = (smem_cap - 64) / 21;  // clusters up to this many members are clipped in shared memory
+  const size_t smem = (size_t)std::min(nmax, n_smem) * 21 + 64;
+  if (smem > 48 * 1024 && smem > clip_smem_set) {
+    FOFB_CUDA(cudaFuncSetAttribute(k_clip_bins_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+    clip_smem_set = smem_cap;
   }
+  FOFB_PROFILED(h, "k_clip_bins", k_clip_bins_smem<<<K, 32, smem, st>>>(K, nbins, off, vel, rad, perm, bstart, kept, n_smem));
+  if (nmax > n_smem) {
+    FOFB_PROFILED(h, "k_clip_bins_global", k_clip_bins<<<grid_for((int64_t)K * nbins, 64), 64, 0, st>>>(K, nbins, off, vel, rad, perm, bstart, dev, kept, n_smem));
+  }
+  if (nmax > kBigBin) clip_big_bins(h, K, nbins, off, total, vel, rad, dev, perm, bstart, kept);
   long long* len = d_len.alloc((size_t)K + 1);
   long long* ooff = d_out_off.alloc((size_t)K + 1);
   k_kept_per_cluster<<<grid_for(K, B), B, 0, st>>>(K, nbins, kept, len);
@@ -409,9 +629,69 @@ constexpr int kVirialThreads = 256;
 constexpr int kBootNum = 100;
 
 // One CTA per cluster.
+// ---- pair sum of a giant cluster, spread over the grid ----------------------------------------------------------
+// k_virial_mass gives a cluster one CTA; its O(n^2) separations are the whole cost once n reaches 10^4..10^5.  For
+// clusters above kBigCluster members the sum over i < j of 1 / sep_ij [rad] is taken by one CTA per 64 rows i, then
+// added up per cluster in tile order (deterministic).
+constexpr int kBigCluster = 4096;
+constexpr int kPairRows = 64;
+
+__global__ void k_big_clusters(int K, const long long* off, int* count, int* list) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  if (off[k + 1] - off[k] > kBigCluster) list[atomicAdd(count, 1)] = k;
+}
+
+__global__ void __launch_bounds__(256) k_pair_sum_big(const int* list, const long long* off, View M, const double4* trig,
+                                                      int tiles_max, double* partial) {
+  const int k = list[blockIdx.y];
+  const long long s0 = off[k];
+  const int n = (int)(off[k + 1] - s0);
+  const int i0 = blockIdx.x * kPairRows;
+  double* dst = partial + (long long)blockIdx.y * tiles_max + blockIdx.x;
+  if (i0 >= n - 1) {
+    if (threadIdx.x == 0) *dst = 0.0;
+    return;
+  }
+  const int i1 = min(i0 + kPairRows, n - 1);
+  __shared__ double4 rows[kPairRows];
+  if (threadIdx.x < i1 - i0) rows[threadIdx.x] = trig[s0 + i0 + threadIdx.x];
+  __syncthreads();
+  double psum = 0.0;
+  for (int j = i0 + 1 + threadIdx.x; j < n; j += 256) {
+    const double4 b = trig[s0 + j];
+    const int top = min(i1, j);  // rows i < j
+    for (int i = i0; i < top; ++i) {
+      const double4 a = rows[i - i0];
+      const double sdlon = b.x * a.y - b.y * a.x, cdlon = b.y * a.y + b.x * a.x;
+      const double num1 = b.w * sdlon;
+      const double num2 = a.w * b.z - a.z * b.w * cdlon;
+      const double den = a.z * b.z + a.w * b.w * cdlon;
+      double sep = atan2(sqrt(num1 * num1 + num2 * num2), den);
+      if (sep < 1e-6)
+        sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
+                           __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
+      psum += 1.0 / sep;
+    }
+  }
+  typedef cub::BlockReduce<double, 256> Reduce;
+  __shared__ typename Reduce::TempStorage rtmp;
+  const double t = Reduce(rtmp).Sum(psum);
+  if (threadIdx.x == 0) *dst = t;
+}
+
+__global__ void k_pair_sum_finish(int nbig, const int* list, int tiles_max, const double* partial, double* big_psum) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbig) return;
+  double acc = 0.0;
+  for (int t = 0; t < tiles_max; ++t) acc += partial[(long long)b * tiles_max + t];
+  big_psum[list[b]] = acc;
+}
+
 __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const long long* off, View M, const double4* trig,
                                                                 Cosmo cosmo, const unsigned* mt, long long mt_len,
-                                                                double mass_unit, double* out, int* status) {
+                                                                double mass_unit, double* out, int* status,
+                                                                const double* big_psum) {
   const int k = blockIdx.x;
   if (k >= K) return;
   const long long s0 = off[k];
@@ -473,7 +753,7 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   // pair sum over i < j of 1 / (sep_deg * d_A * pi/180 * h)
   const double dA = cosmo_angular_diameter_distance(cosmo, zbar);
   double psum = 0.0;
-  {
+  if (n <= kBigCluster) {
     // pairs (i, j), i < j, in row-major order of the upper triangle, strided over the block.  Vincenty's
     // formula with the angle-difference identities on the precomputed sines and cosines; pairs closer than
     // 1e-6 rad (where the identities lose digits) are recomputed from the angles themselves.
@@ -499,7 +779,8 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
       j += kVirialThreads;
     }
   }
-  const double total_sep = Reduce(rtmp).Sum(psum);
+  double total_sep = Reduce(rtmp).Sum(psum);
+  if (n > kBigCluster) total_sep = big_psum[k] / (kRad2Deg * dA * kDeg2Rad * cosmo.h);  // summed by k_pair_sum_big
   __syncthreads();
   // bootstrap: 100 resamples of n-1 indices from the masked MT19937 stream.  Every thread owns a contiguous span of
   // the raw stream: one counting pass, one block scan for the ordinal of its first accepted word, then a second
@@ -690,7 +971,26 @@ void CleanState::virial_core(fofb_handle* h, const fofb_params& p, int K, const 
     k_member_trig<<<grid_for(M.rows, 256), 256, 0, st>>>(M.rows, M, trig);
     FOFB_LAUNCH_CHECK(h);
   }
-  FOFB_PROFILED(h, "k_virial_mass", k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, trig, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status));
+  double* big_psum = d_big_psum.alloc((size_t)K);
+  if (nmax > kBigCluster) {
+    int* cnt = d_big_count.alloc(2);
+    int* list = d_big_slot.alloc((size_t)K);
+    FOFB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+    k_big_clusters<<<grid_for(K, 256), 256, 0, st>>>(K, off, cnt, list);
+    FOFB_LAUNCH_CHECK(h);
+    int nbig = 0;
+    FOFB_CUDA(cudaMemcpyAsync(&nbig, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    if (nbig > 0) {
+      FOFB_REQUIRE(nbig <= 65535, "virial: more than 65535 clusters above 4096 members");
+      const int tiles = (nmax + kPairRows - 1) / kPairRows;
+      double* partial = d_big_dev.alloc((size_t)nbig * tiles);
+      FOFB_PROFILED(h, "k_pair_sum_big", k_pair_sum_big<<<dim3(tiles, nbig), 256, 0, st>>>(list, off, M, trig, tiles, partial));
+      k_pair_sum_finish<<<grid_for(nbig, 64), 64, 0, st>>>(nbig, list, tiles, partial, big_psum);
+      FOFB_LAUNCH_CHECK(h);
+    }
+  }
+  FOFB_PROFILED(h, "k_virial_mass", k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, trig, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status, big_psum));
   int bad = 0;
   FOFB_CUDA(cudaMemcpyAsync(&bad, status, sizeof(int), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
