@@ -504,6 +504,16 @@ __global__ void k_hop2_novel(long long total, const int* owner, const long long*
 }
 
 constexpr int kHop2Threads = 256;
+constexpr int kHop2BitonicAbove = 1024;  // candidate count above which hop 2 sorts instead of ranking by counting
+
+// FOFB_HOP2_SORT_ABOVE=<n> overrides the threshold (the parity tests are also run with 0 to cover the sorting path)
+static int hop2_sort_above() {
+  static const int v = [] {
+    const char* e = getenv("FOFB_HOP2_SORT_ABOVE");
+    return e ? atoi(e) : kHop2BitonicAbove;
+  }();
+  return v;
+}
 
 // (d) one CTA per centre: the surviving candidates are decided batch by batch.
 __global__ void __launch_bounds__(kHop2Threads) k_hop2(
@@ -511,7 +521,7 @@ __global__ void __launch_bounds__(kHop2Threads) k_hop2(
     const long long* hcap, unsigned long long* htab, View G, const double* v2ra, const double* v2dec, const double* v2cos,
     const unsigned char* novel, const double* LLin, const double4* bbox2, fofb_params p, const int* v2row, int* mrows,
     int* nm_list, int* first_batch, int* nm_sorted, int* nM, int* pass, const int* kill_target, unsigned char* alive,
-    unsigned char* decided) {
+    unsigned char* decided, unsigned long long* sort_scratch, int sort_above) {
   const int w = blockIdx.x;
   if (w >= nr) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -571,7 +581,30 @@ __global__ void __launch_bounds__(kHop2Threads) k_hop2(
           }
         }
         __syncthreads();
-        // candidates ordered by (first batch, V2 position): rank by all-pairs counting
+        // candidates ordered by (first batch, V2 position): rank by all-pairs counting -- or, for the tens of
+        // thousands of candidates of a giant bubble, a bitonic sort of the unique keys (first batch, position) in
+        // scratch memory (flip / disperse network: every exchange is ascending, so the virtual +inf padding up to
+        // the next power of two never moves and out-of-range partners are simply skipped)
+        if (n_nm > sort_above) {
+          unsigned long long* key = sort_scratch + off;
+          for (int q = tid; q < n_nm; q += kHop2Threads)
+            key[q] = ((unsigned long long)(unsigned)first_batch[off + q] << 32) | (unsigned)q;
+          __syncthreads();
+          for (int k = 2; (k >> 1) < n_nm; k <<= 1) {
+            for (int j = k; j > 1; j >>= 1) {
+              const int mask = j == k ? k - 1 : (j >> 1);  // flip on the first step of a merge, disperse after
+              for (int i = tid; i < n_nm; i += kHop2Threads) {
+                const int l = i ^ mask;
+                if (l > i && l < n_nm) {
+                  const unsigned long long a = key[i], b = key[l];
+                  if (a > b) { key[i] = b; key[l] = a; }
+                }
+              }
+              __syncthreads();
+            }
+          }
+          for (int q = tid; q < n_nm; q += kHop2Threads) nm_sorted[off + q] = (int)(unsigned)(key[q] & 0xffffffffull);
+        } else
         for (int q = tid; q < n_nm; q += kHop2Threads) {
           const int fq = first_batch[off + q];
           int rank = 0;
@@ -1005,7 +1038,7 @@ void FofState::round_evaluate(fofb_handle* h) {
       }
       FOFB_PROFILED(h, "k_hop2", k_hop2<<<nr, kHop2Threads, 0, st>>>(nr, rb, nv_p, nF_p, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p,
                                       ismember.p, LLp, bb2, p, v2, mr, nml, fbatch, nm_sorted.alloc(tv), nM_p, pass_p, kill_target.p, alive.p,
-                                      decided.p));
+                                      decided.p, k1, hop2_sort_above()));
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse
       long long* dst = ho;    // reuse
