@@ -50,6 +50,7 @@ __device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int lo
 
 __global__ void __launch_bounds__(256) k_count(CellListView cl, int n, const QueryRec* __restrict__ rec,
                                                int* __restrict__ N_row) {
+  __shared__ int run_lo[9][256], run_hi[9][256];  // per thread: the runs of its (at most 3 x 3) neighbour cells
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const QueryRec qr = rec[cl.zrank[q]];
@@ -61,19 +62,34 @@ __global__ void __launch_bounds__(256) k_count(CellListView cl, int n, const Que
     const int cx = cl.cx_of(ra), cy = cl.cy_of(dec);
     const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < cl.ncx - 1 ? cx + 1 : cl.ncx - 1;
     const int y0 = cy > 0 ? cy - 1 : 0, y1 = cy < cl.ncy - 1 ? cy + 1 : cl.ncy - 1;
+    // pass 1: the in-window run of every neighbour cell (uniform work: two binary searches per cell);
+    // pass 2: ONE loop over the runs back to back, so that a warp iterates max-over-lanes of the TOTAL number of
+    // candidates instead of the sum over cells of the per-cell maxima (the runs are 0-3 long for field galaxies).
+    int nrun = 0;
     for (int yy = y0; yy <= y1; ++yy) {
       int s = __ldg(cl.cell_start + yy * cl.ncx + x0);
       for (int xx = x0; xx <= x1; ++xx) {
         const int e = __ldg(cl.cell_start + yy * cl.ncx + xx + 1);
         const int a = lower_bound_i32(cl.zrank, s, e, qr.wlo);
         const int b = lower_bound_i32(cl.zrank, a, e, qr.whi);
-        for (int j = a; j < b; ++j) {
-          const double pra = __ldg(cl.ra + j), pdec = __ldg(cl.dec + j);
-          if (pra >= qr.ra_lo && pra <= qr.ra_hi && pdec >= qr.dec_lo && pdec <= qr.dec_hi &&
-              bt.inside(pra, pdec, __ldg(cl.cosdec + j)))
-            ++count;
+        if (b > a) {
+          run_lo[nrun][threadIdx.x] = a;
+          run_hi[nrun][threadIdx.x] = b;
+          ++nrun;
         }
         s = e;
+      }
+    }
+    int c = 0;
+    int j = nrun ? run_lo[0][threadIdx.x] : 0, end = nrun ? run_hi[0][threadIdx.x] : 0;
+    while (c < nrun) {
+      const double pra = __ldg(cl.ra + j), pdec = __ldg(cl.dec + j);
+      if (pra >= qr.ra_lo && pra <= qr.ra_hi && pdec >= qr.dec_lo && pdec <= qr.dec_hi &&
+          bt.inside(pra, pdec, __ldg(cl.cosdec + j)))
+        ++count;
+      if (++j == end && ++c < nrun) {
+        j = run_lo[c][threadIdx.x];
+        end = run_hi[c][threadIdx.x];
       }
     }
   }

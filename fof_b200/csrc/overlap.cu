@@ -594,9 +594,12 @@ __global__ void k_od_keys(long long total, CellListView cl, const double* rra, c
 }
 
 // one thread per (cluster, random point): galaxies of the centre's velocity window within theta_0.5
-__global__ void k_od_count(long long total, int npts, const int* order, const int* centre, CellListView cl, const int* c_wlo,
+constexpr int kOdThreads = 128, kOdRuns = 9;
+
+__global__ void __launch_bounds__(kOdThreads) k_od_count(long long total, int npts, const int* order, const int* centre, CellListView cl, const int* c_wlo,
                            const int* c_whi, const double* c_th05, const double4* bbox, const int* all_oof,
                            const double* rra, const double* rdec, int grid_cells, int* counts) {
+  __shared__ int run_lo[kOdRuns][kOdThreads], run_hi[kOdRuns][kOdThreads];
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const long long q = order[t];
@@ -615,6 +618,9 @@ __global__ void k_od_count(long long total, int npts, const int* order, const in
     const double reach = ra_reach(r, dec);
     const int x0 = cl.cx_of(ra - reach), x1 = cl.cx_of(ra + reach);
     const int y0 = cl.cy_of(dec - r * 1.000001), y1 = cl.cy_of(dec + r * 1.000001);
+    // runs first, then one loop over all of them (see k_count): neighbouring threads belong to different clusters,
+    // their runs are 0-2 long, and a loop per cell would run with three lanes of a warp active
+    int nrun = 0;
     for (int yy = y0; yy <= y1; ++yy)
       for (int xx = x0; xx <= x1; ++xx) {
         const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
@@ -623,11 +629,28 @@ __global__ void k_od_count(long long total, int npts, const int* order, const in
         const int first = a;
         bnd = e;
         while (a < bnd) { const int mid = (a + bnd) >> 1; if (cl.zrank[mid] < whi) a = mid + 1; else bnd = mid; }
-        for (int j = first; j < a; ++j) {
-          const double pra = cl.ra[j], pdec = cl.dec[j];
-          if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
+        if (a == first) continue;
+        if (nrun < kOdRuns) {
+          run_lo[nrun][threadIdx.x] = first;
+          run_hi[nrun][threadIdx.x] = a;
+          ++nrun;
+        } else {  // more cells than the table holds (cells smaller than the bubble): count this one directly
+          for (int j = first; j < a; ++j) {
+            const double pra = cl.ra[j], pdec = cl.dec[j];
+            if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
+          }
         }
       }
+    int cur = 0;
+    int j = nrun ? run_lo[0][threadIdx.x] : 0, end = nrun ? run_hi[0][threadIdx.x] : 0;
+    while (cur < nrun) {
+      const double pra = cl.ra[j], pdec = cl.dec[j];
+      if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
+      if (++j == end && ++cur < nrun) {
+        j = run_lo[cur][threadIdx.x];
+        end = run_hi[cur][threadIdx.x];
+      }
+    }
   }
   counts[q] = cnt;
 }

@@ -1,0 +1,43 @@
+"""Summarise `ncu -i <rep> --page raw --csv` (a --set full capture) into a small JSON list: one entry per profiled
+launch with duration, DRAM traffic, cache hit rates, SM utilisation, occupancy, registers and instruction count.
+    ncu -i gpurun_out/x.ncu-rep --page raw --csv > /tmp/raw.csv && python scripts/ncu_full_summary.py /tmp/raw.csv"""
+import csv
+import json
+import sys
+
+WANT = {
+    "gpu__time_duration.sum": "duration",
+    "dram__bytes_read.sum": "dram_read",
+    "dram__bytes_write.sum": "dram_write",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
+    "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+    "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct_of_peak",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+    "launch__registers_per_thread": "regs",
+    "launch__grid_size": "grid",
+    "launch__block_size": "block",
+    "smsp__inst_executed.sum": "warp_insts",
+    "smsp__thread_inst_executed_per_inst_executed.ratio": "active_threads_per_inst",
+}
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    names, units = rows[hdr], rows[hdr + 1]
+    out = []
+    for r in rows[hdr + 2:]:
+        if len(r) != len(names):
+            continue
+        e = {"kernel": r[names.index("Kernel Name")][:70]}
+        for col, key in WANT.items():
+            if col in names:
+                i = names.index(col)
+                e[key] = f"{r[i]} {units[i]}".strip()
+        out.append(e)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
