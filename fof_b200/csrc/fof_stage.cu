@@ -271,25 +271,46 @@ __global__ void k_virial(int nr, const int* ready, CatalogView cat, CellListView
       GridAxis gx, gy;
       gx.init(bb.ra_min, bb.ra_max, grid_cells);
       gy.init(bb.dec_min, bb.dec_max, grid_cells);
-      for (int t = lane; t < ncells; t += 32) {
-        const int yy = y0 + t / nx, xx = x0 + t % nx;
-        const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
-        int a = s, b = e;
-        while (a < b) { const int mid = (a + b) >> 1; if (cl.zrank[mid] < wlo) a = mid + 1; else b = mid; }
-        const int first = a;
-        b = e;
-        while (a < b) { const int mid = (a + b) >> 1; if (cl.zrank[mid] < whi) a = mid + 1; else b = mid; }
-        for (int j = first; j < a; ++j) {
-          const double pra = cl.ra[j], pdec = cl.dec[j];
-          if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) {
+      // the lanes first find the in-window run of one neighbour cell each (the cells are few), then the whole warp
+      // strides over the candidates of every run: a loop per lane over its own cell would keep 3 of 32 lanes busy
+      for (int base = 0; base < ncells; base += 32) {
+        const int t = base + lane;
+        int first = 0, last = 0;
+        if (t < ncells) {
+          const int yy = y0 + t / nx, xx = x0 + t % nx;
+          const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
+          int a = s, b = e;
+          while (a < b) { const int mid = (a + b) >> 1; if (cl.zrank[mid] < wlo) a = mid + 1; else b = mid; }
+          first = a;
+          b = e;
+          while (a < b) { const int mid = (a + b) >> 1; if (cl.zrank[mid] < whi) a = mid + 1; else b = mid; }
+          last = a;
+        }
+        const int here = ncells - base < 32 ? ncells - base : 32;
+        for (int k = 0; k < here; ++k) {
+          const int f = __shfl_sync(0xffffffffu, first, k), e = __shfl_sync(0xffffffffu, last, k);
+          for (int j0 = f; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            double pra = 0.0, pdec = 0.0;
+            if (j < e) {
+              pra = cl.ra[j];
+              pdec = cl.dec[j];
+              hit = box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j]);
+            }
             if (MODE == 0) {
-              ++count;
+              count += hit ? 1 : 0;
             } else {
-              const unsigned long long key =
-                  ((unsigned long long)(unsigned)(gy.digit_clamped(pdec) * grid_cells + gx.digit_clamped(pra)) << 32) |
-                  (unsigned)cl.row[j];
-              const int pos = atomicAdd(cursor + w, 1);
-              keys[voff[w] + pos] = key;
+              const unsigned mh = __ballot_sync(0xffffffffu, hit);
+              if (mh) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(cursor + w, __popc(mh));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (hit)
+                  keys[voff[w] + pos + __popc(mh & ((1u << lane) - 1u))] =
+                      ((unsigned long long)(unsigned)(gy.digit_clamped(pdec) * grid_cells + gx.digit_clamped(pra)) << 32) |
+                      (unsigned)cl.row[j];
+              }
             }
           }
         }
