@@ -629,6 +629,17 @@ constexpr int kVirialThreads = 256;
 constexpr int kBootNum = 100;
 
 // One CTA per cluster.
+// atan2(y, x) for y >= 0: members of one cluster are arc-minutes apart, so t = y / x is tiny and four terms of the
+// alternating series are exact to the last bit (t < 0.02: the next term is below 1e-17 relative); otherwise the library
+// function.  Vincenty's numerator and denominator are what astropy feeds to arctan2 (App. B.2).
+__device__ __forceinline__ double small_atan2(double y, double x) {
+  if (x > 0.0 && y < 0.02 * x) {
+    const double t = y / x, t2 = t * t;
+    return t * (1.0 + t2 * (-1.0 / 3.0 + t2 * (1.0 / 5.0 + t2 * (-1.0 / 7.0))));
+  }
+  return atan2(y, x);
+}
+
 // ---- pair sum of a giant cluster, spread over the grid ----------------------------------------------------------
 // k_virial_mass gives a cluster one CTA; its O(n^2) separations are the whole cost once n reaches 10^4..10^5.  For
 // clusters above kBigCluster members the sum over i < j of 1 / sep_ij [rad] is taken by one CTA per 64 rows i, then
@@ -667,7 +678,7 @@ __global__ void __launch_bounds__(256) k_pair_sum_big(const int* list, const lon
       const double num1 = b.w * sdlon;
       const double num2 = a.w * b.z - a.z * b.w * cdlon;
       const double den = a.z * b.z + a.w * b.w * cdlon;
-      double sep = atan2(sqrt(num1 * num1 + num2 * num2), den);
+      double sep = small_atan2(sqrt(num1 * num1 + num2 * num2), den);
       if (sep < 1e-6)
         sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
                            __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
@@ -771,7 +782,7 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
       const double num1 = b.w * sdlon;
       const double num2 = a.w * b.z - a.z * b.w * cdlon;
       const double den = a.z * b.z + a.w * b.w * cdlon;
-      double sep = atan2(sqrt(num1 * num1 + num2 * num2), den);
+      double sep = small_atan2(sqrt(num1 * num1 + num2 * num2), den);
       if (sep < 1e-6)
         sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
                            __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));

@@ -138,7 +138,8 @@ struct CentreCells {
 __global__ void k_ready(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
                         const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
                         const unsigned char* alive, const unsigned char* decided, const int* t_row, const double* ra_row, const double* dec_row,
-                        const double* cos_row, const double* z_row, double vmax, double R1max, int* ready_flag) {
+                        const double* cos_row, const double* z_row, double vmax, double R1max, int* ready_flag,
+                        int* resume_cell, int* resume_k) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= na) return;
   const int i = active[t];
@@ -155,20 +156,32 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
       y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
   x0 = max(x0, 0); y0 = max(y0, 0);
   x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
+  // A candidate that does not block now never will again (alive only falls, decided only rises), so the scan resumes
+  // where the previous round found its blocker instead of starting over: one pass per centre over all rounds.
+  const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
+  const int c0 = resume_cell[i], k0 = resume_k[i];
   bool blocked = false;
-  for (int yy = y0; yy <= y1 && !blocked; ++yy) {
-    for (int xx = x0; xx <= x1 && !blocked; ++xx) {
-      int lo = cc.start[yy * cc.ncx + xx];
-      const int e = cc.start[yy * cc.ncx + xx + 1];
+  for (int cidx = c0 > 0 ? c0 : 0; cidx < ncells && !blocked; ++cidx) {
+    const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
+    int lo = cc.start[yy * cc.ncx + xx];
+    const int e = cc.start[yy * cc.ncx + xx + 1];
+    if (cidx == c0) {
+      lo = k0;
+    } else {
       int hi = e;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
-      for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
-        const int j = cc.idx[k];
-        if (j >= i || !alive[j] || decided[j]) continue;
-        if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
-        BubbleTest bt;
-        bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
-        if (bt.inside(ra, dec, cs)) { blocked = true; break; }
+    }
+    for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
+      const int j = cc.idx[k];
+      if (j >= i || !alive[j] || decided[j]) continue;
+      if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+      BubbleTest bt;
+      bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
+      if (bt.inside(ra, dec, cs)) {
+        blocked = true;
+        resume_cell[i] = cidx;
+        resume_k[i] = k;
+        break;
       }
     }
   }
@@ -921,6 +934,8 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
     FOFB_LAUNCH_CHECK(h);
   }
   // ---- priority rounds: initial active list -------------------------------------------------------
+  FOFB_CUDA(cudaMemsetAsync(resume_cell.alloc(mm), 0xff, sizeof(int) * mm, st));  // -1: no scan position yet
+  FOFB_CUDA(cudaMemsetAsync(resume_k.alloc(mm), 0xff, sizeof(int) * mm, st));
   int* act = active_a.alloc(mm);
   active_b.alloc(mm);
   act_in_a = true;
@@ -958,6 +973,8 @@ void FofState::restart_rounds(fofb_handle* h, double linking_length_factor, int 
   if (m == 0) return;
   FOFB_CUDA(cudaMemsetAsync(alive.p, 1, (size_t)m, st));
   FOFB_CUDA(cudaMemsetAsync(decided.p, 0, (size_t)m, st));
+  FOFB_CUDA(cudaMemsetAsync(resume_cell.p, 0xff, sizeof(int) * (size_t)m, st));
+  FOFB_CUDA(cudaMemsetAsync(resume_k.p, 0xff, sizeof(int) * (size_t)m, st));
   FOFB_CUDA(cudaMemcpyAsync(active_a.p, cc_idx.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToDevice, st));
   act_in_a = true;
   na = m;
@@ -981,7 +998,7 @@ void FofState::round_evaluate(fofb_handle* h) {
     if (na > 8192) {
       FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
                                                t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
-                                               p.max_velocity, R1max, fl));
+                                               p.max_velocity, R1max, fl, resume_cell.p, resume_k.p));
     } else {
       FOFB_PROFILED(h, "k_ready", k_ready_warp<<<grid_for((int64_t)na * 32, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
                                                t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
