@@ -347,7 +347,7 @@ __global__ void k_alloc_sizes(int nr, const int* nv, int min_virial, long long* 
 __global__ void k_hop1(int nr, const int* ready, const int* nv, const long long* voff, const unsigned long long* keys1,
                        const double* ra_row, const double* dec_row, const double* cos_row, const double* c_ra,
                        const double* c_dec, const double* c_cos, const double* c_z, Cosmo cosmo, fofb_params p,
-                       double* LLout, double4* bbox2, int* nF, unsigned long long* keys2) {
+                       double* LLout, double4* bbox2, int* nF, unsigned long long* keys2, int key_bits) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nr) return;
@@ -390,7 +390,11 @@ __global__ void k_hop1(int nr, const int* ready, const int* nv, const long long*
     const bool fr = !oof && box.contains(pra, pdec) && bt.inside(pra, pdec, cos_row[row]);
     cnt += fr ? 1 : 0;
     const unsigned long long cellkey = (unsigned)(gy.digit_clamped(pdec) * p.grid_cells + gx.digit_clamped(pra));
-    keys2[off + k] = (fr ? 0ull : (1ull << 63)) | (cellkey << 32) | (unsigned)k;
+    // key_bits == 0: keys1 is in virial order and k is the tie-break inside a cell of the friends' grid.
+    // key_bits  > 0: keys1 is unsorted; its own (cell of the virial grid, row) is that tie-break, so ONE sort by
+    //                (friend flag, friends' cell, virial cell, row) gives the same order without sorting keys1 first.
+    keys2[off + k] = key_bits ? (fr ? 0ull : (1ull << 63)) | (cellkey << (32 + key_bits)) | keys1[off + k]
+                              : (fr ? 0ull : (1ull << 63)) | (cellkey << 32) | (unsigned)k;
   }
   for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) {
@@ -486,7 +490,7 @@ __device__ __forceinline__ bool hash_contains_owner(const unsigned long long* ta
 __global__ void k_hop2_setup(int nr, const int* nv, const int* nF, const long long* voff, const unsigned long long* keys1,
                              const unsigned long long* keys2, const double* ra_row, const double* dec_row,
                              const double* cos_row, int min_virial, int* v2row, int* owner, double* v2ra, double* v2dec,
-                             double* v2cos, int* mrows) {
+                             double* v2cos, int* mrows, int key_bits) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nr) return;
@@ -496,8 +500,8 @@ __global__ void k_hop2_setup(int nr, const int* nv, const int* nF, const long lo
   const int n_f = nF[w];
   // V2 order: friends first (in f_gsp's return order), then the rest in f_gsp cell order
   for (int t = lane; t < n_v; t += 32) {
-    const int k = (int)(unsigned)(keys2[off + t] & 0xffffffffull);
-    const int row = (int)(unsigned)(keys1[off + k] & 0xffffffffull);
+    const int low = (int)(unsigned)(keys2[off + t] & 0xffffffffull);  // the row itself, or the position in virial order
+    const int row = key_bits ? low : (int)(unsigned)(keys1[off + low] & 0xffffffffull);
     v2row[off + t] = row;
     owner[off + t] = w;
     v2ra[off + t] = ra_row[row];
@@ -1040,14 +1044,20 @@ void FofState::round_evaluate(fofb_handle* h) {
       unsigned long long* k2 = keys2.alloc(tv);
       unsigned long long* k2s = keys2b.alloc(tv);
       long long total_h = 0;
+      // (friend flag, friends' cell, virial cell, row) fits one 64-bit key up to 181 grid cells per axis: then the
+      // virial points need no sort of their own
+      int key_bits = 1;
+      while ((1ll << key_bits) < (long long)p.grid_cells * p.grid_cells) ++key_bits;
+      if (1 + 2 * key_bits + 32 > 64) key_bits = 0;
       if (total_v > 0) {
         int* cur = cursor.alloc(nr);
         FOFB_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * nr, st));
         FOFB_PROFILED(h, "k_virial_fill", k_virial<1><<<wblocks, 128, 0, st>>>(nr, rb, cv, clbig, c_ra.p, c_dec.p, c_cos.p, c_R1.p, c_wlo.p, c_whi.p,
                                              p.grid_cells, p.min_virial, nv_p, bb1, vo, cur, k1));
-        segmented_sort(h, k1, k1s, total_v, nr, vo);
-        FOFB_PROFILED(h, "k_hop1", k_hop1<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, vo, k1s, cat.ra_row.p, cat.dec_row.p, cos_row.p, c_ra.p, c_dec.p,
-                                        c_cos.p, c_z.p, cosmo, p, LLp, bb2, nF_p, k2));
+        if (!key_bits) segmented_sort(h, k1, k1s, total_v, nr, vo);
+        const unsigned long long* k1v = key_bits ? k1 : k1s;
+        FOFB_PROFILED(h, "k_hop1", k_hop1<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, vo, k1v, cat.ra_row.p, cat.dec_row.p, cos_row.p, c_ra.p, c_dec.p,
+                                        c_cos.p, c_z.p, cosmo, p, LLp, bb2, nF_p, k2, key_bits));
         segmented_sort(h, k2, k2s, total_v, nr, vo);
         k_hash_sizes<<<grid_for(nr, B), B, 0, st>>>(nr, nv_p, nF_p, p.min_virial, need);
         FOFB_LAUNCH_CHECK(h);
@@ -1067,7 +1077,7 @@ void FofState::round_evaluate(fofb_handle* h) {
         double* v2c = v2cos.alloc(tv);
         unsigned char* nov = ismember.alloc(tv);
         k_hop2_setup<<<wblocks, 128, 0, st>>>(nr, nv_p, nF_p, vo, k1s, k2s, cat.ra_row.p, cat.dec_row.p, cos_row.p, p.min_virial,
-                                              v2, own, v2a, v2d, v2c, mr);
+                                              v2, own, v2a, v2d, v2c, mr, key_bits);
         FOFB_LAUNCH_CHECK(h);
         if (total_h > 0) {
           FOFB_PROFILED(h, "k_hop2_insert", k_hop2_insert<<<grid_for(total_v, B), B, 0, st>>>(total_v, own, vo, nF_p, ho, need, htab.p, G, v2));
