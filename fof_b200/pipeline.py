@@ -53,10 +53,11 @@ class Catalogue:
 
 
 def find_clusters(galaxy_data, max_velocity=None, linking_length_factor=None, virial_radius=None, richness=None,
-                  overdensity=None, min_redshift=None, max_redshift=None, device=0, uniforms=None):
+                  overdensity=None, min_redshift=None, max_redshift=None, device=0, uniforms=None, grid_cells=None):
     """Run the whole cluster-finding path on ``galaxy_data`` (DataFrame or (n, 7) array in the column order
     of pipeline.py:51-53).  Defaults come from ``fof_b200.params``.  The overdensity sample points consume
-    ``np.random`` (legacy global generator) exactly as the reference does."""
+    ``np.random`` (legacy global generator) exactly as the reference does.  ``grid_cells``: GriSPy's N_cells (64, the
+    library default the reference runs with)."""
     g = _as_matrix(galaxy_data)
     h = _lib.get_handle(device)
     p = _lib.default_params(
@@ -66,6 +67,8 @@ def find_clusters(galaxy_data, max_velocity=None, linking_length_factor=None, vi
         virial_radius=as_float(P.max_radius if virial_radius is None else virial_radius),
         richness=int(P.richness if richness is None else richness),
         overdensity=float(P.D if overdensity is None else overdensity))
+    if grid_cells is not None:
+        p.grid_cells = int(grid_cells)
     zmin = P.min_redshift if min_redshift is None else min_redshift
     zmax = P.max_redshift if max_redshift is None else max_redshift
     if uniforms is None:

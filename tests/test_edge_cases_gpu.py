@@ -8,14 +8,17 @@ from oracle import fof_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _compare(arr, b=0.2, rich=12, D=2.0, seed=5):
+def _compare(arr, b=0.2, rich=12, D=2.0, seed=5, grid_cells=None):
     from fof_b200 import _lib, pipeline
     op = O.Params(linking_length_factor=b, richness=rich, overdensity=D)
     ref = O.run_pipeline(arr, op, mode="fast", seed=seed)
     np.random.seed(seed)
-    cat = pipeline.find_clusters(arr, linking_length_factor=b, richness=rich, overdensity=D)
+    cat = pipeline.find_clusters(arr, linking_length_factor=b, richness=rich, overdensity=D, grid_cells=grid_cells)
     h = _lib.get_handle(0)
-    N, rows = h.number_counts(arr, _lib.default_params())
+    lp = _lib.default_params()
+    if grid_cells is not None:
+        lp.grid_cells = grid_cells
+    N, rows = h.number_counts(arr, lp)
     assert np.array_equal(N.astype(float), ref["main_arr"][:, 7])
     assert np.array_equal(arr[rows, 6], ref["candidate_centers"][:, 6])
     assert len(cat) == len(ref["virial"])
@@ -83,6 +86,15 @@ def test_rows_not_sorted_by_redshift(lib, seed):
     arr = arr[np.random.default_rng(seed).permutation(len(arr))]
     assert np.any(np.diff(arr[:, 2]) < 0)
     assert len(_compare(arr, rich=8, D=0.0)) > 0
+
+
+@pytest.mark.parametrize("cells", [16, 128, 256])
+def test_other_grid_sizes(lib, cells, monkeypatch):
+    """GriSPy's N_cells other than 64: 16 and 128 keep the single-key ordering of the virial points, 256 cells per axis
+    no longer fit one 64-bit key and take the two-sort path."""
+    monkeypatch.setattr(O, "N_CELLS", cells)
+    arr = make_catalog(2500, seed=41, as_frame=False)
+    assert len(_compare(arr, rich=8, D=0.0, grid_cells=cells)) > 0
 
 
 def test_unsupported_inputs_are_refused(lib):
