@@ -629,15 +629,20 @@ constexpr int kVirialThreads = 256;
 constexpr int kBootNum = 100;
 
 // One CTA per cluster.
-// atan2(y, x) for y >= 0: members of one cluster are arc-minutes apart, so t = y / x is tiny and four terms of the
-// alternating series are exact to the last bit (t < 0.02: the next term is below 1e-17 relative); otherwise the library
-// function.  Vincenty's numerator and denominator are what astropy feeds to arctan2 (App. B.2).
-__device__ __forceinline__ double small_atan2(double y, double x) {
-  if (x > 0.0 && y < 0.02 * x) {
-    const double t = y / x, t2 = t * t;
-    return t * (1.0 + t2 * (-1.0 / 3.0 + t2 * (1.0 / 5.0 + t2 * (-1.0 / 7.0))));
-  }
-  return atan2(y, x);
+// 1 / separation [rad] of two members from Vincenty's numerator^2 (s = num1^2 + num2^2) and denominator
+// (den = cos(sep)), the two quantities astropy feeds to arctan2 (App. B.2).  Members of one cluster are arc-minutes
+// apart, so t = sqrt(s) / den is tiny: with eps = 1 - den, 1/den = 1 + eps + eps^2 + ...; atan t = t (1 - a),
+// a = t^2/3 - t^4/5 + t^6/7; 1/(1 - a) = 1 + a + a^2 + a^3.  For t < 0.02 every truncated term is below 1e-15
+// relative, and the pair costs one reciprocal square root instead of a square root, two divisions and an atan2.
+// Returns a negative number when the shortcut does not apply (wide pair, or closer than 1e-6 rad where the
+// angle-difference identities lose digits): the caller then evaluates the formula itself.
+__device__ __forceinline__ double inv_small_separation(double s, double den) {
+  if (!(den > 0.0 && s < 4.0e-4 * den * den && s >= 1.0e-12)) return -1.0;
+  const double eps = 1.0 - den;
+  const double inv_den = 1.0 + eps * (1.0 + eps * (1.0 + eps * (1.0 + eps)));
+  const double t2 = s * inv_den * inv_den;
+  const double a = t2 * (1.0 / 3.0 - t2 * (1.0 / 5.0 - t2 * (1.0 / 7.0)));
+  return den * rsqrt(s) * (1.0 + a * (1.0 + a * (1.0 + a)));
 }
 
 // ---- pair sum of a giant cluster, spread over the grid ----------------------------------------------------------
@@ -678,11 +683,16 @@ __global__ void __launch_bounds__(256) k_pair_sum_big(const int* list, const lon
       const double num1 = b.w * sdlon;
       const double num2 = a.w * b.z - a.z * b.w * cdlon;
       const double den = a.z * b.z + a.w * b.w * cdlon;
-      double sep = small_atan2(sqrt(num1 * num1 + num2 * num2), den);
-      if (sep < 1e-6)
-        sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
-                           __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
-      psum += 1.0 / sep;
+      const double ss = num1 * num1 + num2 * num2;
+      double inv = inv_small_separation(ss, den);
+      if (inv < 0.0) {
+        double sep = atan2(sqrt(ss), den);
+        if (sep < 1e-6)
+          sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
+                             __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
+        inv = 1.0 / sep;
+      }
+      psum += inv;
     }
   }
   typedef cub::BlockReduce<double, 256> Reduce;
@@ -768,7 +778,6 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
     // pairs (i, j), i < j, in row-major order of the upper triangle, strided over the block.  Vincenty's
     // formula with the angle-difference identities on the precomputed sines and cosines; pairs closer than
     // 1e-6 rad (where the identities lose digits) are recomputed from the angles themselves.
-    const double scale = kRad2Deg * dA * kDeg2Rad * cosmo.h;
     int i = 0;
     long long j = 1 + tid;
     while (i < n - 1) {
@@ -782,15 +791,21 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
       const double num1 = b.w * sdlon;
       const double num2 = a.w * b.z - a.z * b.w * cdlon;
       const double den = a.z * b.z + a.w * b.w * cdlon;
-      double sep = small_atan2(sqrt(num1 * num1 + num2 * num2), den);
-      if (sep < 1e-6)
-        sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
-                           __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
-      psum += 1.0 / (sep * scale);
+      const double ss = num1 * num1 + num2 * num2;
+      double inv = inv_small_separation(ss, den);
+      if (inv < 0.0) {
+        double sep = atan2(sqrt(ss), den);
+        if (sep < 1e-6)
+          sep = vincenty_rad(__dmul_rn(M.at(s0 + i, 0), kDeg2Rad), __dmul_rn(M.at(s0 + i, 1), kDeg2Rad),
+                             __dmul_rn(M.at(s0 + j, 0), kDeg2Rad), __dmul_rn(M.at(s0 + j, 1), kDeg2Rad));
+        inv = 1.0 / sep;
+      }
+      psum += inv;
       j += kVirialThreads;
     }
   }
-  double total_sep = Reduce(rtmp).Sum(psum);
+  // sum over pairs of 1 / sep [rad]  ->  sum of 1 / (sep_deg * d_A * pi/180 * h)
+  double total_sep = Reduce(rtmp).Sum(psum) / (kRad2Deg * dA * kDeg2Rad * cosmo.h);
   if (n > kBigCluster) total_sep = big_psum[k] / (kRad2Deg * dA * kDeg2Rad * cosmo.h);  // summed by k_pair_sum_big
   __syncthreads();
   // bootstrap: 100 resamples of n-1 indices from the masked MT19937 stream.  Every thread owns a contiguous span of
