@@ -347,7 +347,7 @@ __global__ void k_alloc_sizes(int nr, const int* nv, int min_virial, long long* 
 __global__ void k_hop1(int nr, const int* ready, const int* nv, const long long* voff, const unsigned long long* keys1,
                        const double* ra_row, const double* dec_row, const double* cos_row, const double* c_ra,
                        const double* c_dec, const double* c_cos, const double* c_z, Cosmo cosmo, fofb_params p,
-                       double* LLout, double4* bbox2, int* nF, unsigned long long* keys2, int key_bits) {
+                       double* LLout, double4* bbox2, int* nF, unsigned long long* keys2, int key_bits, int* seg_of) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nr) return;
@@ -395,6 +395,7 @@ __global__ void k_hop1(int nr, const int* ready, const int* nv, const long long*
     //                (friend flag, friends' cell, virial cell, row) gives the same order without sorting keys1 first.
     keys2[off + k] = key_bits ? (fr ? 0ull : (1ull << 63)) | (cellkey << (32 + key_bits)) | keys1[off + k]
                               : (fr ? 0ull : (1ull << 63)) | (cellkey << 32) | (unsigned)k;
+    if (seg_of) seg_of[off + k] = w;
   }
   for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) {
@@ -539,6 +540,16 @@ __global__ void k_hop2_novel(long long total, const int* owner, const long long*
     nov = ok ? 1 : 0;
   }
   novel[g] = nov;
+}
+
+// FOFB_RADIX_ABOVE=<n> overrides the number of virial points above which a round orders them with two device-wide
+// radix sorts instead of one segmented sort (the parity tests are also run with 0 to cover that path)
+static long long radix_sort_above() {
+  static const long long v = [] {
+    const char* e = getenv("FOFB_RADIX_ABOVE");
+    return e ? atoll(e) : (1ll << 17);
+  }();
+  return v;
 }
 
 constexpr int kHop2Threads = 256;
@@ -1049,6 +1060,10 @@ void FofState::round_evaluate(fofb_handle* h) {
       int key_bits = 1;
       while ((1ll << key_bits) < (long long)p.grid_cells * p.grid_cells) ++key_bits;
       if (1 + 2 * key_bits + 32 > 64) key_bits = 0;
+      const bool radix = key_bits > 0 && total_v > radix_sort_above();
+      int* seg_a = radix ? seg_of_a.alloc(tv) : nullptr;
+      int* seg_b = radix ? seg_of_b.alloc(tv) : nullptr;
+      const unsigned long long* k2sorted = radix ? k2 : k2s;
       if (total_v > 0) {
         int* cur = cursor.alloc(nr);
         FOFB_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * nr, st));
@@ -1057,8 +1072,21 @@ void FofState::round_evaluate(fofb_handle* h) {
         if (!key_bits) segmented_sort(h, k1, k1s, total_v, nr, vo);
         const unsigned long long* k1v = key_bits ? k1 : k1s;
         FOFB_PROFILED(h, "k_hop1", k_hop1<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, vo, k1v, cat.ra_row.p, cat.dec_row.p, cos_row.p, c_ra.p, c_dec.p,
-                                        c_cos.p, c_z.p, cosmo, p, LLp, bb2, nF_p, k2, key_bits));
-        segmented_sort(h, k2, k2s, total_v, nr, vo);
+                                        c_cos.p, c_z.p, cosmo, p, LLp, bb2, nF_p, k2, key_bits, radix ? seg_a : nullptr));
+        if (radix) {
+          // two stable device-wide radix sorts (by key, then by centre) instead of one segmented sort: at millions of
+          // keys in segments of a few hundred the onesweep passes are several times faster
+          size_t bytes = 0;
+          FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k2, k2s, seg_a, seg_b, total_v, 0, 64, st));
+          FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, k2, k2s, seg_a, seg_b, total_v, 0, 64, st));
+          int seg_bits = 1;
+          while ((1 << seg_bits) < nr) ++seg_bits;
+          FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, seg_b, seg_a, k2s, k2, total_v, 0, seg_bits, st));
+          FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, seg_b, seg_a, k2s, k2, total_v, 0, seg_bits, st));
+          count_launch(h, 12);
+        } else {
+          segmented_sort(h, k2, k2s, total_v, nr, vo);
+        }
         k_hash_sizes<<<grid_for(nr, B), B, 0, st>>>(nr, nv_p, nF_p, p.min_virial, need);
         FOFB_LAUNCH_CHECK(h);
         total_h = scan_offsets(h, need, ho, nr);
@@ -1076,7 +1104,7 @@ void FofState::round_evaluate(fofb_handle* h) {
         double* v2d = v2dec.alloc(tv);
         double* v2c = v2cos.alloc(tv);
         unsigned char* nov = ismember.alloc(tv);
-        k_hop2_setup<<<wblocks, 128, 0, st>>>(nr, nv_p, nF_p, vo, k1s, k2s, cat.ra_row.p, cat.dec_row.p, cos_row.p, p.min_virial,
+        k_hop2_setup<<<wblocks, 128, 0, st>>>(nr, nv_p, nF_p, vo, k1s, k2sorted, cat.ra_row.p, cat.dec_row.p, cos_row.p, p.min_virial,
                                               v2, own, v2a, v2d, v2c, mr, key_bits);
         FOFB_LAUNCH_CHECK(h);
         if (total_h > 0) {

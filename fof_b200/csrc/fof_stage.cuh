@@ -41,7 +41,7 @@ struct FofState {
   double R1max = 0;
 
   // round scratch
-  DBuf<int> active_a, active_b, ready, flags, counts, nv, nF, nM, cursor, pass, resume_cell, resume_k;
+  DBuf<int> active_a, active_b, ready, flags, counts, nv, nF, nM, cursor, pass, resume_cell, resume_k, seg_of_a, seg_of_b;
   DBuf<long long> voff, hoff, hcap, moff;
   DBuf<unsigned long long> keys1, keys1b, keys2, keys2b, htab;
   DBuf<int> v2row, mrows, nm_list, first_batch;

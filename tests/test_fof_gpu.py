@@ -110,3 +110,34 @@ def test_helper_functions_match_the_oracle(lib):
     got = helper.center_overdensity(cl, g, 2000.0)
     assert got == want
     assert np.array_equal(helper.setdiff2d(g[:10], g[5:20]), g[:5])
+
+
+def test_round_sort_paths_agree(tmp_path):
+    """The virial points of a round are ordered by one segmented sort or, above 2^17 points, by two device-wide radix
+    sorts; FOFB_RADIX_ABOVE moves the threshold, and both orderings must give the same catalogue."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from fof_b200 import pipeline\n"
+        "from fof_b200.mock import make_catalog\n"
+        "arr = make_catalog(60000, seed=17, as_frame=False)\n"
+        "np.random.seed(5)\n"
+        "cat = pipeline.find_clusters(arr)\n"
+        "np.savez(sys.argv[1], off=cat.offsets, rows=cat.member_rows, centre=cat.centre_row, N=cat.N, D=cat.D, props=cat.props)\n"
+    ) % root
+    outs = []
+    for tag, above in (("segmented", str(1 << 40)), ("radix", "0")):
+        out = str(tmp_path / (tag + ".npz"))
+        env = dict(os.environ, FOFB_RADIX_ABOVE=above)
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root)
+        outs.append(np.load(out))
+    a, b = outs
+    assert len(a["centre"]) > 50
+    for key in ("off", "rows", "centre", "N", "D"):
+        assert np.array_equal(a[key], b[key]), key
+    # the bootstrap error accumulates with shared-memory atomics: equal to rounding, not bit for bit, between two runs
+    assert np.allclose(a["props"], b["props"], rtol=1e-12, atol=0)
