@@ -53,3 +53,29 @@ def test_stream_continues_identically_after_device_draws():
     np.random.seed(99)
     np.random.bytes(4 * (2 * CHUNK_WORDS + 17))
     assert np.array_equal(after_device, np.random.random_sample(5))
+
+
+def test_speculation_shortfall_continues_the_stream():
+    """The whole-job call starts the generator early for a guessed number of clusters; when the guess is too small the
+    stream is continued from the state the first launch left behind.  Force that with a one-cluster guess."""
+    from fof_b200.mock import make_catalog
+    arr = make_catalog(6000, seed=12, as_frame=False)
+    h = _lib.get_handle(0)
+    p = _lib.default_params(richness=5, overdensity=-1e9)
+    np.random.seed(3)
+    Kf, total = h.pipeline_run_np_random(arr, p, 0.5, 2.52, 2.5)
+    want = h.pipeline_fetch(Kf, total)
+    want_state = np.random.get_state()
+    assert Kf > 4                                              # several 1200-word blocks of the stream are needed
+    np.random.seed(3)
+    state = np.random.get_state()
+    key = np.ascontiguousarray(state[1], dtype=np.uint32)
+    h.pipeline_begin(arr, p, 0.5, 2.52, 2.5)
+    h.check(h.lib.fofb_dist_prefetch_mt(h.h, key.ctypes.data, int(state[2]), 1))   # stream for ONE cluster only
+    Kf2, total2, nkey, npos = h.pipeline_finish_mt(key, state[2])
+    got = h.pipeline_fetch(Kf2, total2)
+    assert (Kf2, total2) == (Kf, total)
+    for a, b in zip(got[:5], want[:5]):
+        assert np.array_equal(a, b)
+    assert np.allclose(got[5], want[5], rtol=1e-12, atol=0)
+    assert npos == want_state[2] and np.array_equal(nkey, want_state[1])
