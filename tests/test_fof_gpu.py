@@ -130,14 +130,18 @@ def test_round_sort_paths_agree(tmp_path):
         "np.savez(sys.argv[1], off=cat.offsets, rows=cat.member_rows, centre=cat.centre_row, N=cat.N, D=cat.D, props=cat.props)\n"
     ) % root
     outs = []
-    for tag, above in (("segmented", str(1 << 40)), ("radix", "0")):
+    # (virial points: segmented sort | two radix sorts) x (hop-2 candidates: ranking by counting | bitonic sort, which
+    # FOFB_HOP2_SORT_ABOVE moves the same way)
+    for tag, radix_above, hop2_above in (("segmented", str(1 << 40), str(1 << 30)), ("radix", "0", str(1 << 30)),
+                                         ("bitonic", str(1 << 40), "0")):
         out = str(tmp_path / (tag + ".npz"))
-        env = dict(os.environ, FOFB_RADIX_ABOVE=above)
+        env = dict(os.environ, FOFB_RADIX_ABOVE=radix_above, FOFB_HOP2_SORT_ABOVE=hop2_above)
         subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root)
         outs.append(np.load(out))
-    a, b = outs
+    a = outs[0]
     assert len(a["centre"]) > 50
-    for key in ("off", "rows", "centre", "N", "D"):
-        assert np.array_equal(a[key], b[key]), key
-    # the bootstrap error accumulates with shared-memory atomics: equal to rounding, not bit for bit, between two runs
-    assert np.allclose(a["props"], b["props"], rtol=1e-12, atol=0)
+    for b in outs[1:]:
+        for key in ("off", "rows", "centre", "N", "D"):
+            assert np.array_equal(a[key], b[key]), key
+        # the bootstrap error accumulates with shared-memory atomics: equal to rounding, not bit for bit, between runs
+        assert np.allclose(a["props"], b["props"], rtol=1e-12, atol=0)
