@@ -45,3 +45,28 @@ def test_shim_cosmology_known_answers():
     for n, want in ((12, 6.893), (100, 3.400), (1000, 1.578), (10000, 0.733)):
         got = 0.2 * ms(n, 1.0, 0.1 * u.deg, 2000 * u.km / u.s, survey_area=1.7).value
         assert abs(got - want) < 2e-3
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_live_compare_clusters_matches_oracle(seed):
+    """catalog_matching.compare_clusters, unmodified, on random samples against the oracle restatement."""
+    import importlib
+    import logging
+    import os
+    import sys
+    ref = RR.load_reference()
+    cwd = os.getcwd()
+    os.chdir(ref.scratch)  # logging.basicConfig at catalog_matching.py:12 opens a file relative to the cwd
+    try:
+        cm = importlib.import_module("catalog_matching")
+    finally:
+        os.chdir(cwd)
+    logging.disable(logging.CRITICAL)
+    u = sys.modules["astropy"].units
+    from oracle.make_golden_matching import SampleCluster, make_case
+    sample, cat = make_case(100 + seed, 150 + 40 * seed, 120 + 60 * seed, zero_richness=(seed == 2))
+    clusters = [SampleCluster(*row) for row in sample]
+    matched, idx = cm.compare_clusters(clusters, cat, 0.5 * u.Mpc / u.littleh, richness_plot=False)
+    got_m, got_idx = O.compare_clusters(sample, cat, 0.5)
+    assert np.array_equal(idx, got_idx) and np.array_equal(matched, got_m)
+    assert idx.sum() > 10
