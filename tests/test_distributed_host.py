@@ -89,3 +89,47 @@ def test_torch_comm_under_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_thread_comm_collectives_world3():
+    """ThreadComm (the ranks-as-threads communicator the slab parity tests use) implements the same collectives as the
+    torch one: ragged all-gathers, sum/min/max all-reduce, and the MIN / MAX merge of the tracker state bytes."""
+    import threading
+    import torch
+    from fof_b200.distributed import ThreadComm
+    world = 3
+    comms = ThreadComm.group(world)
+    results = [None] * world
+    errors = []
+
+    def worker(r):
+        try:
+            c = comms[r]
+            rows = np.arange(r * 2 + 1, dtype=np.float64).reshape(-1, 1) + 10 * r       # ragged: 1, 3, 5 rows
+            g = c.allgatherv(rows)
+            t = c.allgatherv_t(torch.arange(r + 1, dtype=torch.int64) + 100 * r)          # ragged tensors
+            s = c.allreduce(np.array([r + 1.0, -r]), "sum")
+            mn = c.allreduce(np.array([r + 1.0, -r]), "min")
+            mx = c.allreduce(np.array([r + 1.0, -r]), "max")
+            alive = torch.tensor([1, 1, 1, 1], dtype=torch.uint8)
+            decided = torch.tensor([0, 0, 0, 0], dtype=torch.uint8)
+            alive[r] = 0                                                                   # rank r kills centre r
+            decided[3 - r] = 1                                                             # and decides centre 3 - r
+            c.allreduce_bytes(alive, decided)
+            c.barrier()
+            results[r] = (g, t, s, mn, mx, alive.clone(), decided.clone())
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    assert not errors, errors
+    for r in range(world):
+        g, t, s, mn, mx, alive, decided = results[r]
+        assert [len(x) for x in g] == [1, 3, 5] and g[2][0, 0] == 20.0
+        assert [x.tolist() for x in t] == [[0], [100, 101], [200, 201, 202]]
+        assert s.tolist() == [6.0, -3.0] and mn.tolist() == [1.0, -2.0] and mx.tolist() == [3.0, 0.0]
+        assert alive.tolist() == [0, 0, 0, 1] and decided.tolist() == [0, 1, 1, 1]
