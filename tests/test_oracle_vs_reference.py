@@ -70,3 +70,18 @@ def test_live_compare_clusters_matches_oracle(seed):
     got_m, got_idx = O.compare_clusters(sample, cat, 0.5)
     assert np.array_equal(idx, got_idx) and np.array_equal(matched, got_m)
     assert idx.sum() > 10
+
+
+def test_parameter_defaults_equal_the_reference_module():
+    """fof_b200.params against params.py:16-27 as imported live (names and values), and the C ABI defaults."""
+    ref = RR.load_reference()
+    from fof_b200 import params as ours
+    rp = ref.params
+    for name in ("min_redshift", "max_redshift", "linking_length_factor", "richness", "D", "runname"):
+        assert getattr(ours, name) == getattr(rp, name), name
+    assert float(ours.max_velocity) == float(rp.max_velocity.value)
+    assert float(ours.max_radius) == float(rp.max_radius.value)
+    assert (ours.cosmo.H0, ours.cosmo.Om0, ours.cosmo.Ode0) == (float(rp.cosmo.H0.value), rp.cosmo.Om0, rp.cosmo.Ode0)
+    op = O.Params()
+    assert (op.max_velocity, op.linking_length_factor, op.virial_radius, op.richness, op.overdensity) == \
+        (float(rp.max_velocity.value), rp.linking_length_factor, float(rp.max_radius.value), rp.richness, float(rp.D))
