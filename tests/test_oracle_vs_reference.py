@@ -85,3 +85,36 @@ def test_parameter_defaults_equal_the_reference_module():
     op = O.Params()
     assert (op.max_velocity, op.linking_length_factor, op.virial_radius, op.richness, op.overdensity) == \
         (float(rp.max_velocity.value), rp.linking_length_factor, float(rp.max_radius.value), rp.richness, float(rp.D))
+
+
+@pytest.mark.parametrize("n,seed,kw,b,rich,D", [
+    (1200, 51, {}, 0.05, 5, -5.0),
+    (1500, 52, {"density": 200000.0}, 0.3, 8, 0.0),
+    (1800, 53, {"kind": "wide"}, 0.2, 8, 0.5),
+    (900, 54, {"cluster_fraction": 0.6, "richness_range": (10, 60)}, 0.1, 5, 2.0),
+])
+def test_live_reference_parameter_sweep(n, seed, kw, b, rich, D):
+    """More live runs of the unmodified reference with other catalogues and parameters, against both oracle modes."""
+    import logging
+    logging.disable(logging.CRITICAL)
+    ref = RR.load_reference()
+    df = make_catalog(n, seed=seed, **kw)
+    R = RR.run_pipeline(ref, df, richness=rich, overdensity=D, linking_length_factor=b, seed=seed)
+    p = O.Params(linking_length_factor=b, richness=rich, overdensity=D)
+    for mode in ("fast", "literal"):
+        main_arr, _ = O.candidate_center_search(df.values, p, mode)
+        assert np.array_equal(main_arr, R["main_arr"])
+        g = main_arr[(main_arr[:, 2] >= 0.5) & (main_arr[:, 2] <= 2.52)]
+        c = R["candidate_centers"]
+        c = c[(c[:, 2] >= 0.5) & (c[:, 2] <= 2.5)]
+        np.random.seed(seed)
+        cl = O.FoF(g, c, p, mode)
+        assert len(cl) == len(R["clusters"])
+        for x, (attrs, members, N, Dv) in zip(cl, R["clusters"]):
+            assert np.array_equal(x.galaxies, members) and x.N == N
+            assert x.D == Dv or (np.isnan(x.D) and np.isnan(Dv))
+        cleaned, removed = O.interloper_removal(cl, p)
+        assert removed == R["number_removed"]
+        assert len(cleaned) == len(R["cleaned"])
+        for x, (attrs, members) in zip(cleaned, R["cleaned"]):
+            assert np.array_equal(x.galaxies, members)
