@@ -109,6 +109,7 @@ def load():
         "fofb_pipeline_finish": (C.c_int, [vp, vp, i32, P(i64), P(i64)]),
         "fofb_pipeline_fetch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "fofb_pipeline_stats": (C.c_int, [vp, vp]),
+        "fofb_pipeline_fetch_counts": (C.c_int, [vp, vp, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -348,6 +349,12 @@ class Handle:
                                                 N.ctypes.data, D.ctypes.data, props.ctypes.data))
         return off, rows, cen, N, D, props
 
+    def pipeline_fetch_counts(self, n_rows):
+        """N(0.5) of every input row of the last pipeline run (int32, host)."""
+        N = np.empty(int(n_rows), dtype=np.int32)
+        self.check(self.lib.fofb_pipeline_fetch_counts(self.h, N.ctypes.data, 0))
+        return N
+
     def pipeline_fetch_torch(self, K, total, device):
         """The same as pipeline_fetch into torch tensors on ``device`` (no host round trip)."""
         import torch
@@ -376,7 +383,7 @@ class Handle:
         pos = C.c_int32(int(st[2]))
         out = np.empty(int(n_words), dtype=np.uint32)
         self.check(self.lib.fofb_mt19937_words(self.h, key.ctypes.data, C.byref(pos), int(n_words), out.ctypes.data, 0))
-        new_state = ("MT19937", key, pos.value, 0, 0.0)
+        new_state = ("MT19937", key, pos.value, st[3], st[4])  # a pending cached Gaussian is not the uniforms' business
         if use_global:
             np.random.set_state(new_state)
         return out, new_state

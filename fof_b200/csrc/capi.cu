@@ -333,8 +333,9 @@ int fofb_fof_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxi
   if (!h->fof) h->fof = new FofState();
   h->fof->ran = h->fof->finished = false;
   Timed timer(h);
-  const View G = to_device(h, *galaxies, h->upload);
-  const View Cn = to_device(h, *centres, h->upload2);
+  // the state owns its copies: other entry points on this handle reuse h->upload between run / finish / fetch
+  const View G = to_device(h, *galaxies, h->fof->g_store);
+  const View Cn = to_device(h, *centres, h->fof->c_store);
   FOFB_REQUIRE(G.rows > 0, "galaxy_data is empty");
   h->fof->run(h, *p, G, Cn);
   timer.stop();
@@ -626,6 +627,19 @@ int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, 
   if (D) FOFB_CUDA(cudaMemcpyAsync(D, P.out_D.p, sizeof(double) * K, cudaMemcpyDefault, st));
   if (props) FOFB_CUDA(cudaMemcpyAsync(props, P.props.p, sizeof(double) * K * 8, cudaMemcpyDefault, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_pipeline_fetch_counts(fofb_handle* h, int32_t* N_row, int32_t mem) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  if (!h->pipe || !h->pipe->s0.valid) throw fofb::Error(FOFB_ERR_STATE, "fofb_pipeline_fetch_counts called before a pipeline run");
+  FOFB_REQUIRE(N_row, "N_row is null");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  FOFB_CUDA(cudaMemcpyAsync(N_row, h->pipe->s0.N_row.p, sizeof(int32_t) * h->pipe->n_in,
+                            mem == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
   return FOFB_OK;
   FOFB_CATCH(h)
 }

@@ -79,8 +79,8 @@ __global__ void k_col4_keys(View Cn, int m, double* key, int* val) {
   val[i] = i;
 }
 
-__global__ void k_kill_targets(View G, int n, int m, const double* skey, const int* sval, int* target, int* t_row,
-                               int* t_count, int* dup) {
+__global__ void k_kill_targets(View G, int n, int m, const double* skey, const int* sval, int* target, int* t_count,
+                               int* dup) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
   const double v = G.at(g, 4) + 0.0;
@@ -91,10 +91,22 @@ __global__ void k_kill_targets(View G, int n, int m, const double* skey, const i
   }
   const int tgt = (lo < m && skey[lo] == v) ? sval[lo] : -1;  // stable sort => smallest centre index first
   target[g] = tgt;
-  if (tgt >= 0) {
-    if (atomicAdd(t_count + tgt, 1) > 0) atomicAdd(dup, 1);
-    t_row[tgt] = g;
-  }
+  if (tgt >= 0 && atomicAdd(t_count + tgt, 1) > 0) atomicAdd(dup, 1);
+}
+
+// Every galaxy row that carries centre i's column-4 value switches i off when it joins a cluster (np.intersect1d
+// matches by VALUE, fof.py:238-246): t_rows[t_off[i] .. t_off[i+1]) lists those rows.  With unique column-4 values the
+// list has one entry; photo-z catalogues quote z_upper to a few decimals and have hundreds.
+__global__ void k_kill_rows(int n, const int* target, const long long* t_off, int* cursor, int* t_rows) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int tgt = target[g];
+  if (tgt >= 0) t_rows[t_off[tgt] + atomicAdd(cursor + tgt, 1)] = g;
+}
+
+__global__ void k_i32_to_ll(int n, const int* in, long long* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
 }
 
 // ---- centre cell list for the blocking test ----------------------------------------------------------------
@@ -137,53 +149,61 @@ struct CentreCells {
 // centres whose window can contain the galaxy are visited.
 __global__ void k_ready(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
                         const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
-                        const unsigned char* alive, const unsigned char* decided, const int* t_row, const double* ra_row, const double* dec_row,
+                        const unsigned char* alive, const unsigned char* decided, const long long* t_off, const int* t_rows,
+                        const double* ra_row, const double* dec_row,
                         const double* cos_row, const double* z_row, double vmax, double R1max, int* ready_flag,
-                        int* resume_cell, int* resume_k) {
+                        int* resume_row, int* resume_cell, int* resume_k) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= na) return;
   const int i = active[t];
-  // centre i is switched off when the galaxy row carrying its column-4 value joins a cluster (Q3)
-  const int g = t_row[i];
-  if (g < 0) { ready_flag[t] = 1; return; }
-  const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+  // centre i is switched off when a galaxy row carrying its column-4 value joins a cluster (Q3)
+  const int nrows = (int)(t_off[i + 1] - t_off[i]);
+  if (nrows == 0) { ready_flag[t] = 1; return; }
+  const int* rows = t_rows + t_off[i];
   // |v(z; z_j)| <= vmax  =>  (z - beta)/(1 + beta) <= z_j <= (z + beta)/(1 - beta), beta = vmax/c (+ margin)
   const double beta = vmax / kCkms;
-  const double zlo = (z - beta) / (1.0 + beta) - 1e-9, zhi = (z + beta) / (1.0 - beta) + 1e-9;
-  const double reach = ra_reach(R1max, dec);
-  int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
-  int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
-      y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
-  x0 = max(x0, 0); y0 = max(y0, 0);
-  x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
   // A candidate that does not block now never will again (alive only falls, decided only rises), so the scan resumes
-  // where the previous round found its blocker instead of starting over: one pass per centre over all rounds.
-  const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
-  const int c0 = resume_cell[i], k0 = resume_k[i];
+  // where the previous round found its blocker instead of starting over: one pass per centre over all rounds.  The
+  // rows are walked in list order; a row whose scan ended without a blocker is done for good.
+  int c0 = resume_cell[i], k0 = resume_k[i];
   bool blocked = false;
-  for (int cidx = c0 > 0 ? c0 : 0; cidx < ncells && !blocked; ++cidx) {
-    const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
-    int lo = cc.start[yy * cc.ncx + xx];
-    const int e = cc.start[yy * cc.ncx + xx + 1];
-    if (cidx == c0) {
-      lo = k0;
-    } else {
-      int hi = e;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
-    }
-    for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
-      const int j = cc.idx[k];
-      if (j >= i || !alive[j] || decided[j]) continue;
-      if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
-      BubbleTest bt;
-      bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
-      if (bt.inside(ra, dec, cs)) {
-        blocked = true;
-        resume_cell[i] = cidx;
-        resume_k[i] = k;
-        break;
+  for (int r = resume_row[i]; r < nrows && !blocked; ++r) {
+    const int g = rows[r];
+    const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+    const double zlo = (z - beta) / (1.0 + beta) - 1e-9, zhi = (z + beta) / (1.0 - beta) + 1e-9;
+    const double reach = ra_reach(R1max, dec);
+    int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
+    int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
+        y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
+    x0 = max(x0, 0); y0 = max(y0, 0);
+    x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
+    const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
+    for (int cidx = c0 > 0 ? c0 : 0; cidx < ncells && !blocked; ++cidx) {
+      const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
+      int lo = cc.start[yy * cc.ncx + xx];
+      const int e = cc.start[yy * cc.ncx + xx + 1];
+      if (cidx == c0) {
+        lo = k0;
+      } else {
+        int hi = e;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
+      }
+      for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
+        const int j = cc.idx[k];
+        if (j >= i || !alive[j] || decided[j]) continue;
+        if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+        BubbleTest bt;
+        bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
+        if (bt.inside(ra, dec, cs)) {
+          blocked = true;
+          resume_row[i] = r;
+          resume_cell[i] = cidx;
+          resume_k[i] = k;
+          break;
+        }
       }
     }
+    c0 = -1;  // the stored scan position belongs to the row it was found on
   }
   ready_flag[t] = blocked ? 0 : 1;
 }
@@ -192,45 +212,45 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
 // serial chain of dependent loads of a single thread is what the round waits for.
 __global__ void k_ready_warp(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
                              const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
-                             const unsigned char* alive, const unsigned char* decided, const int* t_row,
-                             const double* ra_row, const double* dec_row, const double* cos_row, const double* z_row,
-                             double vmax, double R1max, int* ready_flag) {
+                             const unsigned char* alive, const unsigned char* decided, const long long* t_off,
+                             const int* t_rows, const double* ra_row, const double* dec_row, const double* cos_row,
+                             const double* z_row, double vmax, double R1max, int* ready_flag) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= na) return;
   const int i = active[t];
-  const int g = t_row[i];
-  if (g < 0) {
-    if (lane == 0) ready_flag[t] = 1;
-    return;
-  }
-  const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+  const int nrows = (int)(t_off[i + 1] - t_off[i]);
+  const int* rows = t_rows + t_off[i];
   const double beta = vmax / kCkms;
-  const double zlo = (z - beta) / (1.0 + beta) - 1e-9, zhi = (z + beta) / (1.0 - beta) + 1e-9;
-  const double reach = ra_reach(R1max, dec);
-  int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
-  int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
-      y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
-  x0 = max(x0, 0); y0 = max(y0, 0);
-  x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
-  const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
   bool blocked = false;
-  for (int cidx = lane; cidx < ncells && !blocked; cidx += 32) {
-    const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
-    int lo = cc.start[yy * cc.ncx + xx];
-    const int e = cc.start[yy * cc.ncx + xx + 1];
-    int hi = e;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
-    for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
-      const int j = cc.idx[k];
-      if (j >= i || !alive[j] || decided[j]) continue;
-      if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
-      BubbleTest bt;
-      bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
-      if (bt.inside(ra, dec, cs)) { blocked = true; break; }
+  for (int r = 0; r < nrows && !blocked; ++r) {
+    const int g = rows[r];
+    const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+    const double zlo = (z - beta) / (1.0 + beta) - 1e-9, zhi = (z + beta) / (1.0 - beta) + 1e-9;
+    const double reach = ra_reach(R1max, dec);
+    int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
+    int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
+        y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
+    x0 = max(x0, 0); y0 = max(y0, 0);
+    x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
+    const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
+    for (int cidx = lane; cidx < ncells && !blocked; cidx += 32) {
+      const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
+      int lo = cc.start[yy * cc.ncx + xx];
+      const int e = cc.start[yy * cc.ncx + xx + 1];
+      int hi = e;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
+      for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
+        const int j = cc.idx[k];
+        if (j >= i || !alive[j] || decided[j]) continue;
+        if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+        BubbleTest bt;
+        bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
+        if (bt.inside(ra, dec, cs)) { blocked = true; break; }
+      }
     }
+    blocked = __any_sync(0xffffffffu, blocked);
   }
-  blocked = __any_sync(0xffffffffu, blocked);
   if (lane == 0) ready_flag[t] = blocked ? 0 : 1;
 }
 
@@ -890,15 +910,27 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
     FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, val_in, val_out, m, 0, 64, st));
     FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, key_in, key_out, val_in, val_out, m, 0, 64, st));
     count_launch(h, 8);
-    int* trow = t_row.alloc(mm);
-    int* tcnt = t_count.alloc(mm + 1);
-    FOFB_CUDA(cudaMemsetAsync(trow, 0xff, sizeof(int) * mm, st));
-    FOFB_CUDA(cudaMemsetAsync(tcnt, 0, sizeof(int) * (mm + 1), st));
-    FOFB_PROFILED(h, "k_kill_targets", k_kill_targets<<<grid_for(n, B), B, 0, st>>>(G, n, m, key_out, val_out, kill_target.alloc(n), trow, tcnt, tcnt + mm));
-    if (d2h_scalar(h, tcnt + mm) != 0)
+    int* tcnt = t_count.alloc(mm + 2);
+    FOFB_CUDA(cudaMemsetAsync(tcnt, 0, sizeof(int) * (mm + 2), st));
+    FOFB_PROFILED(h, "k_kill_targets", k_kill_targets<<<grid_for(n, B), B, 0, st>>>(G, n, m, key_out, val_out, kill_target.alloc(n), tcnt, tcnt + mm));
+    long long* tlen = hcap.alloc(mm + 1);
+    long long* toff = t_off.alloc(mm + 1);
+    k_i32_to_ll<<<grid_for(m, B), B, 0, st>>>(m, tcnt, tlen);
+    FOFB_LAUNCH_CHECK(h);
+    const int n_dup = d2h_scalar(h, tcnt + mm);
+    // A slab run sees only its own rows: a value shared with a row of another slab would need the tracker state of
+    // centres far outside the halo.  Single-process runs reproduce the by-value rule exactly.
+    if (n_dup != 0 && owned)
       throw Error(FOFB_ERR_UNSUPPORTED,
-                  "two galaxy rows share a column-4 (z_upper) value with the same candidate centre; the tracker of "
-                  "fof.py:238-246 keys on that column and the device path requires it to identify a galaxy uniquely");
+                  "slab-decomposed runs need column-4 (z_upper) values that identify a galaxy row uniquely: the tracker of "
+                  "fof.py:238-246 matches by value, so duplicated values couple centres across slabs; run this "
+                  "catalogue on one GPU (fofb_pipeline_run / fofb_fof_run reproduce the by-value rule)");
+    const long long n_trows = scan_offsets(h, tlen, toff, m);
+    int* trows = t_rows.alloc((size_t)std::max<long long>(n_trows, 1));
+    FOFB_CUDA(cudaMemsetAsync(tcnt, 0, sizeof(int) * mm, st));
+    k_kill_rows<<<grid_for(n, B), B, 0, st>>>(n, kill_target.p, toff, tcnt, trows);
+    FOFB_LAUNCH_CHECK(h);
+    duplicated_keys = n_dup;
   }
   // centre cell list
   {
@@ -949,6 +981,7 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
     FOFB_LAUNCH_CHECK(h);
   }
   // ---- priority rounds: initial active list -------------------------------------------------------
+  FOFB_CUDA(cudaMemsetAsync(resume_row.alloc(mm), 0, sizeof(int) * mm, st));
   FOFB_CUDA(cudaMemsetAsync(resume_cell.alloc(mm), 0xff, sizeof(int) * mm, st));  // -1: no scan position yet
   FOFB_CUDA(cudaMemsetAsync(resume_k.alloc(mm), 0xff, sizeof(int) * mm, st));
   int* act = active_a.alloc(mm);
@@ -988,6 +1021,7 @@ void FofState::restart_rounds(fofb_handle* h, double linking_length_factor, int 
   if (m == 0) return;
   FOFB_CUDA(cudaMemsetAsync(alive.p, 1, (size_t)m, st));
   FOFB_CUDA(cudaMemsetAsync(decided.p, 0, (size_t)m, st));
+  FOFB_CUDA(cudaMemsetAsync(resume_row.p, 0, sizeof(int) * (size_t)m, st));
   FOFB_CUDA(cudaMemsetAsync(resume_cell.p, 0xff, sizeof(int) * (size_t)m, st));
   FOFB_CUDA(cudaMemsetAsync(resume_k.p, 0xff, sizeof(int) * (size_t)m, st));
   FOFB_CUDA(cudaMemcpyAsync(active_a.p, cc_idx.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToDevice, st));
@@ -1012,11 +1046,11 @@ void FofState::round_evaluate(fofb_handle* h) {
     int* fl = flags.alloc((size_t)na);
     if (na > 8192) {
       FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
-                                               t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
-                                               p.max_velocity, R1max, fl, resume_cell.p, resume_k.p));
+                                               t_off.p, t_rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
+                                               p.max_velocity, R1max, fl, resume_row.p, resume_cell.p, resume_k.p));
     } else {
       FOFB_PROFILED(h, "k_ready", k_ready_warp<<<grid_for((int64_t)na * 32, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
-                                               t_row.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
+                                               t_off.p, t_rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
                                                p.max_velocity, R1max, fl));
     }
     int* rdy = ready.alloc((size_t)na);

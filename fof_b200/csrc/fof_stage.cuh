@@ -19,6 +19,7 @@ struct FofState {
   bool ran = false, finished = false;
   int n = 0, m = 0;
   View G, Cn;
+  DBuf<double> g_store, c_store;  // fofb_fof_run: host matrices are staged here, not in the handle's shared buffers
   Catalog cat;
   CellList big;    // sized for the stage-1 virial search radius
   CellList small;  // sized for theta_0.5 (overdensity counts)
@@ -28,7 +29,9 @@ struct FofState {
   DBuf<double> c_ra, c_dec, c_cos, c_z, c_R1, c_T1, c_thvir, c_th05, c_mag, c_N, c_id;
   DBuf<int> c_wlo, c_whi;
   DBuf<unsigned char> alive, decided;
-  DBuf<int> t_row, t_count;  // per centre: the galaxy row whose membership switches it off (-1: none)
+  DBuf<long long> t_off;     // per centre: its slice of t_rows
+  DBuf<int> t_rows, t_count; // the galaxy rows whose membership switches a centre off (they carry its column-4 value)
+  int duplicated_keys = 0;   // rows beyond the first that share a kill target (0 for unique column-4 values)
   DBuf<int> kill_target;   // per galaxy row: first centre whose column 4 equals the row's column 4, or -1
   DBuf<double> cos_row;
 
@@ -41,7 +44,7 @@ struct FofState {
   double R1max = 0;
 
   // round scratch
-  DBuf<int> active_a, active_b, ready, flags, counts, nv, nF, nM, cursor, pass, resume_cell, resume_k, seg_of_a, seg_of_b;
+  DBuf<int> active_a, active_b, ready, flags, counts, nv, nF, nM, cursor, pass, resume_row, resume_cell, resume_k, seg_of_a, seg_of_b;
   DBuf<long long> voff, hoff, hcap, moff;
   DBuf<unsigned long long> keys1, keys1b, keys2, keys2b, htab;
   DBuf<int> v2row, mrows, nm_list, first_batch;

@@ -8,9 +8,14 @@ from .params import cosmo
 from .units import Q
 
 
-def find_masses(data, estimator, device=0):
+def find_masses(data, estimator, device=0, keep_flags=True):
     """mass_analysis.py:8-44: wrap every cluster in a CleanedCluster carrying its virial mass, velocity
-    dispersion (a variance, km^2/s^2), projected radius and total absolute magnitude."""
+    dispersion (a variance, km^2/s^2), projected radius and total absolute magnitude.
+
+    ``keep_flags``: the reference rebuilds each object through ``Cluster.__init__`` (cluster.py:40-41), so its
+    CleanedClusters come back with ``D = 0`` and ``flag_poor = False`` whatever FoF() and the flagging step set
+    (``properties[8:10]`` lose them).  True (default) carries the input's D / flag_poor over -- a documented
+    deviation; False reproduces the reference's reset bit for bit."""
     if estimator not in ("virial", "projected"):
         raise ValueError("estimator must be 'virial' or 'projected'")
     if not len(data):
@@ -24,8 +29,9 @@ def find_masses(data, estimator, device=0):
         for k, c in enumerate(data):
             new_c = CleanedCluster(c.center_attributes, c.galaxies, Q(pm[k, 0], "Msun/littleh"), Q(pm[k, 1], "km2/s2"),
                                    None, None, None, None)
-            new_c.D = c.D
-            new_c.flag_poor = c.flag_poor
+            if keep_flags:
+                new_c.D = c.D
+                new_c.flag_poor = c.flag_poor
             out.append(new_c)
         return out
     props = h.virial(off, members, p)
@@ -34,8 +40,9 @@ def find_masses(data, estimator, device=0):
         m, me, vd, vde, r, absmag = props[k, :6]
         new_c = CleanedCluster(c.center_attributes, c.galaxies, Q(m, "Msun/littleh"), Q(me, "Msun/littleh"),
                                Q(vd, "km2/s2"), Q(vde, "km2/s2"), Q(r, "Mpc/littleh"), float(absmag))
-        new_c.D = c.D
-        new_c.flag_poor = c.flag_poor
+        if keep_flags:
+            new_c.D = c.D
+            new_c.flag_poor = c.flag_poor
         assert new_c.gal_id == c.gal_id, "Different cluster has been added"
         new_cs.append(new_c)
     return new_cs

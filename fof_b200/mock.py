@@ -33,7 +33,7 @@ def _sample_z(rng, n, zmin, zmax):
 
 def make_catalog(n, seed=20260101, kind="cosmos", density=50000.0, zmin=0.5, zmax=2.0,
                  cluster_fraction=0.2, richness_range=(20, 300), ra0=150.1, dec0=2.2,
-                 n_blobs=None, as_frame=True):
+                 n_blobs=None, as_frame=True, photoz_decimals=None):
     """Build one mock catalogue.
 
     kind = "cosmos"  : footprint sized for ``density`` galaxies/deg^2 around (ra0, dec0);
@@ -43,6 +43,9 @@ def make_catalog(n, seed=20260101, kind="cosmos", density=50000.0, zmin=0.5, zma
                         GriSPy RA cell-box truncation).
     kind = "dense"   : all cluster members in ``n_blobs`` (<= 20) giant Plummer blobs plus a 20 %
                         background (configs[4], percolation stress).
+    photoz_decimals  : round z_lower / z_upper to that many decimals, as published photo-z catalogues quote them.
+                        Thousands of rows then share a column-4 value, which is what the reference's tracker keys on
+                        (fof.py:238-246); None keeps the continuous (unique) values.
     """
     rng = np.random.default_rng(seed)
     n = int(n)
@@ -110,6 +113,9 @@ def make_catalog(n, seed=20260101, kind="cosmos", density=50000.0, zmin=0.5, zma
 
     z_lower = z - np.abs(rng.normal(0.0, 0.02 * (1 + z)))
     z_upper = z + np.abs(rng.normal(0.0, 0.02 * (1 + z)))
+    if photoz_decimals is not None:  # after every draw, so the other columns do not depend on it
+        z_lower = np.round(z_lower, int(photoz_decimals))
+        z_upper = np.round(z_upper, int(photoz_decimals))
     rmag = rng.normal(-21.0, 1.0, n)
     gid = np.arange(n, dtype=np.float64)
 

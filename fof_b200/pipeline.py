@@ -15,10 +15,11 @@ from .units import Q, as_float
 class Catalogue:
     """Final cluster catalogue in CSR form, indexing rows of the input table."""
 
-    def __init__(self, galaxy_arr, offsets, member_rows, centre_row, N, D, props):
+    def __init__(self, galaxy_arr, offsets, member_rows, centre_row, N, D, props, N_row=None):
         self.galaxy_arr = galaxy_arr
         self.offsets, self.member_rows, self.centre_row = offsets, member_rows, centre_row
         self.N, self.D, self.props = N, D, props
+        self.N_row = N_row   # N(0.5) per input row (column 7 of main_arr, fof.py:61-74); None: not fetched
 
     def __len__(self):
         return len(self.centre_row)
@@ -41,7 +42,10 @@ class Catalogue:
     def cluster(self, k):
         g = self.galaxy_arr
         center = np.append(g[self.centre_row[k]], self.N[k])
-        rows = np.column_stack([g[self.members(k)], np.zeros(len(self.members(k)))])
+        if self.N_row is None:
+            raise RuntimeError("this Catalogue was built without the per-row N(0.5) column (find_clusters(..., "
+                               "with_counts=False)); Cluster.galaxies rows carry it in the reference")
+        rows = np.column_stack([g[self.members(k)], self.N_row[self.members(k)].astype(np.float64)])
         m, me, vd, vde, r, absmag = self.props[k, :6]
         c = CleanedCluster(center, rows, Q(m, "Msun/littleh"), Q(me, "Msun/littleh"), Q(vd, "km2/s2"),
                            Q(vde, "km2/s2"), Q(r, "Mpc/littleh"), float(absmag))
@@ -53,11 +57,13 @@ class Catalogue:
 
 
 def find_clusters(galaxy_data, max_velocity=None, linking_length_factor=None, virial_radius=None, richness=None,
-                  overdensity=None, min_redshift=None, max_redshift=None, device=0, uniforms=None, grid_cells=None):
+                  overdensity=None, min_redshift=None, max_redshift=None, device=0, uniforms=None, grid_cells=None,
+                  with_counts=True):
     """Run the whole cluster-finding path on ``galaxy_data`` (DataFrame or (n, 7) array in the column order
     of pipeline.py:51-53).  Defaults come from ``fof_b200.params``.  The overdensity sample points consume
     ``np.random`` (legacy global generator) exactly as the reference does.  ``grid_cells``: GriSPy's N_cells (64, the
-    library default the reference runs with)."""
+    library default the reference runs with).  ``with_counts``: also read back N(0.5) of every row (4 bytes per row), so that
+    ``Catalogue.cluster(k).galaxies`` has the reference's 8 columns."""
     g = _as_matrix(galaxy_data)
     h = _lib.get_handle(device)
     p = _lib.default_params(
@@ -76,7 +82,7 @@ def find_clusters(galaxy_data, max_velocity=None, linking_length_factor=None, vi
     else:
         h.pipeline_begin(g, p, zmin, zmax + 0.02, zmax)
         Kf, total = h.pipeline_finish(uniforms)
-    return Catalogue(g, *h.pipeline_fetch(Kf, total))
+    return Catalogue(g, *h.pipeline_fetch(Kf, total), N_row=h.pipeline_fetch_counts(len(g)) if with_counts else None)
 
 
 def sweep(galaxy_data, linking_length_factors, richness=None, overdensity=None, max_velocity=None, virial_radius=None,
@@ -101,5 +107,7 @@ def sweep(galaxy_data, linking_length_factors, richness=None, overdensity=None, 
             Kf, total = h.pipeline_run_np_random(g, p, zmin, zmax + 0.02, zmax)
         else:
             Kf, total = h.pipeline_rerun_np_random(b, rich, od)
-        out[float(b)] = Catalogue(g, *h.pipeline_fetch(Kf, total))
+        if i == 0:
+            N_row = h.pipeline_fetch_counts(len(g))   # stage 0 does not depend on the swept parameters
+        out[float(b)] = Catalogue(g, *h.pipeline_fetch(Kf, total), N_row=N_row)
     return out

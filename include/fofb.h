@@ -195,6 +195,9 @@ int fofb_pipeline_rerun(fofb_handle* h, double linking_length_factor, int32_t ri
                         int32_t* mt_pos, int64_t* n_final, int64_t* n_members);
 int fofb_pipeline_fetch(fofb_handle* h, int64_t* offsets, int32_t* member_rows, int32_t* centre_row, double* N, double* D,
                         double* props);
+/* N(0.5) of every INPUT row of the last pipeline run (column 7 of main_arr, fof.py:61-74): what the reference's
+ * Cluster.galaxies rows carry in their last column.  N_row[n_input_rows], host (mem 0) or device (mem 1). */
+int fofb_pipeline_fetch_counts(fofb_handle* h, int32_t* N_row, int32_t mem);
 /* sizes seen by the last pipeline run: galaxies after the z cut, candidate centres, stage-1 candidate clusters,
  * total stage-1 members, priority rounds, centres evaluated, clusters entering stage 4 */
 int fofb_pipeline_stats(fofb_handle* h, int64_t* stats7);

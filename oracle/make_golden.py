@@ -25,6 +25,10 @@ CASES = {
     "cosmos_4000_b005": (4000, 4, {}, 0.05, 8, 0.5, 2468),
     "dense_2500_b002": (2500, 6, {"density": 200000.0}, 0.02, 5, -5.0, 1357),
     "wide_3000_default": (3000, 7, {"kind": "wide"}, 0.2, 12, 2.0, 97531),
+    # z_lower / z_upper quoted to 3 (2) decimals: dozens (hundreds) of rows share each column-4 value, the key of the
+    # reference's tracker (fof.py:238-246: np.intersect1d switches off the FIRST candidate row carrying the value)
+    "photoz3_4000_default": (4000, 12, {"photoz_decimals": 3}, 0.2, 12, 2.0, 4321),
+    "photoz2_4000_b01": (4000, 13, {"photoz_decimals": 2, "density": 100000.0}, 0.1, 10, 1.0, 8642),
 }
 
 
@@ -61,7 +65,8 @@ def main():
             cleaned_centre_ids=np.array([c[0][6] for c in R["cleaned"]]),
             number_removed=np.array(R["number_removed"], dtype=np.int64),
             virial=np.array([[v[k] for k in keys] for v in R["virial"]]).reshape(-1, len(keys)),
-            projected=np.array(R["projected"]).reshape(-1, 2))
+            projected=np.array(R["projected"]).reshape(-1, 2),
+            r200=np.array([[v["r200"], v["r500"]] for v in R["virial"]]).reshape(-1, 2))
         print(name, "clusters", len(R["clusters"]), "cleaned", len(R["cleaned"]), "candidates", len(R["candidate_centers"]))
 
 

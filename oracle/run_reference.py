@@ -95,7 +95,9 @@ def run_pipeline(ref, df, richness=None, overdensity=None, linking_length_factor
             dict(center=v.center_attributes.copy(), galaxies=v.galaxies.copy(),
                  cluster_mass=float(v.cluster_mass.value), mass_err=float(v.mass_err.value),
                  vel_disp=float(v.vel_disp.value), vel_disp_err=float(v.vel_disp_err.value),
-                 projected_radius=float(v.projected_radius.value), total_absmag=float(v.total_absmag))
+                 projected_radius=float(v.projected_radius.value), total_absmag=float(v.total_absmag),
+                 # cluster.py:111-118 with the reference's own cosmology object, delta = 200 and 500
+                 r200=float(v.r200(p.cosmo, 200).value), r500=float(v.r200(p.cosmo, 500).value))
             for v in virial]
         proj = ref.mass_analysis.find_masses(cleaned, "projected")
         out["projected"] = [(float(v.cluster_mass.value), float(getattr(v.mass_err, "value", v.mass_err))) for v in proj]

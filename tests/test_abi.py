@@ -107,7 +107,11 @@ def test_cluster_types_mirror_the_reference():
     cc = CleanedCluster(center, np.zeros((13, 8)), Q(1e14, "Msun/littleh"), Q(1e13), Q(5e5), Q(1e4), Q(0.7), -26.0)
     assert cc.properties.shape == (11,) and cc.properties[3] == 1e14
     from fof_b200.params import cosmo
-    assert 0.1 < float(cc.r200(cosmo, 200)) < 5.0
+    # known answer from the unmodified reference (tests/golden/cosmos_3000_default.npz holds the per-cluster values):
+    # r200 = (3 M / (4 pi 200 rho_c(z)))^(1/3); at z = 2, M = 1e14 Msun/h, H0 = 70, Om0 = 0.3 -> 0.4425 Mpc/h
+    r = float(cc.r200(cosmo, 200))
+    rho_c = 2.77536627e11 * (0.3 * 27 + 0.7)   # h^2 Msun / Mpc^3 at z = 2
+    assert abs(r - (3 * 1e14 / (4 * np.pi * 200 * rho_c)) ** (1 / 3)) < 2e-6 * r
 
 
 def test_cluster_objects_pickle_like_the_reference_pipeline():
@@ -139,3 +143,22 @@ def test_units_accept_plain_numbers_and_quantity_likes():
     from fof_b200 import params
     assert (params.min_redshift, params.max_redshift, float(params.max_velocity), params.linking_length_factor,
             float(params.max_radius), params.richness, params.D) == (0.5, 2.5, 2000.0, 0.2, 1.5, 12, 2)
+
+
+def test_r200_matches_the_unmodified_reference():
+    """CleanedCluster.r200 (cluster.py:111-118) is host arithmetic: with the golden masses and centre redshifts it must
+    give the radii the unmodified reference computed under the shims (delta = 200 and 500), to 1e-9."""
+    from golden_util import fixtures, load
+    from fof_b200.cluster import CleanedCluster
+    from fof_b200.params import cosmo
+    from fof_b200.units import Q
+    checked = 0
+    for path in fixtures():
+        g = load(path)
+        z_of_id = dict(zip(g["table"][:, 6].tolist(), g["table"][:, 2].tolist()))
+        for cid, v, want in zip(g["cleaned_centre_ids"], g["virial"], g["r200"]):
+            center = np.array([0.0, 0.0, z_of_id[cid], 0, 0, 0, cid, 0])
+            cc = CleanedCluster(center, np.zeros((12, 8)), Q(v[0], "Msun/littleh"), Q(v[1]), Q(v[2]), Q(v[3]), Q(v[4]), v[5])
+            np.testing.assert_allclose([float(cc.r200(cosmo, 200)), float(cc.r200(cosmo, 500))], want, rtol=1e-9)
+            checked += 1
+    assert checked > 50

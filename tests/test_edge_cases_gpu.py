@@ -110,20 +110,50 @@ def test_unsupported_inputs_are_refused(lib):
     with pytest.raises(_lib.FofbError) as e:
         h.fof_run(bad, cb, _lib.default_params())
     assert e.value.code == -5
-    # (b) two galaxy rows sharing a candidate centre's z_upper
-    dup = main_arr.copy()
-    r0 = int(np.nonzero(dup[:, 6] == cand[0, 6])[0][0])
-    dup[(r0 + 1) % len(dup), 4] = dup[r0, 4]
-    with pytest.raises(_lib.FofbError) as e:
-        h.fof_run(dup, cand, _lib.default_params())
-    assert e.value.code == -5
-    # (c) non-finite coordinates / redshifts, declinations off the sphere
+    # (b) non-finite coordinates / redshifts, declinations off the sphere
     for col, val in ((0, np.nan), (1, np.nan), (2, np.nan), (0, np.inf), (2, -np.inf), (1, 91.0)):
         broken = arr.copy()
         broken[17, col] = val
         with pytest.raises(_lib.FofbError) as e:
             h.number_counts(broken, _lib.default_params())
         assert e.value.code == -1, (col, val)
-    # (d) bad shapes
+    # (c) bad shapes
     with pytest.raises(_lib.FofbError):
         h.fof_run(main_arr[:, :5], cand[:, :5], _lib.default_params())
+
+
+@pytest.mark.parametrize("decimals,n,seed,b,rich,D", [(3, 6000, 21, 0.2, 12, 2.0), (2, 6000, 22, 0.1, 10, 1.0),
+                                                       (4, 20000, 23, 0.2, 12, 2.0), (1, 3000, 24, 0.2, 8, 0.0)])
+def test_duplicated_column4_values_follow_the_reference_tracker(lib, decimals, n, seed, b, rich, D):
+    """z_lower / z_upper quoted to a few decimals: many rows share a column-4 value.  The reference's tracker matches by
+    VALUE (np.intersect1d, fof.py:238-246): a passing cluster switches off the FIRST candidate row carrying any member's
+    column-4 value, and only that one.  Whole path against the oracle (which is pinned to the unmodified reference on
+    such tables by tests/golden/photoz*.npz)."""
+    arr = make_catalog(n, seed=seed, photoz_decimals=decimals, as_frame=False)
+    assert len(np.unique(arr[:, 4])) < 0.8 * len(arr)
+    assert len(_compare(arr, b=b, rich=rich, D=D)) > 0
+
+
+def test_single_shared_value_switches_off_the_first_centre_only(lib, handle):
+    """Two candidate centres share one column-4 value: members carrying it switch off the first of them, never the
+    second (np.intersect1d returns first-occurrence indices)."""
+    arr = make_catalog(3000, seed=2, as_frame=False)
+    main_arr, cand = O.candidate_center_search(arr, O.Params(), mode="fast")
+    g = np.ascontiguousarray(main_arr[(main_arr[:, 2] >= 0.5) & (main_arr[:, 2] <= 2.52)])
+    c = np.ascontiguousarray(cand[(cand[:, 2] >= 0.5) & (cand[:, 2] <= 2.5)])
+    rng = np.random.default_rng(1)
+    for _ in range(3):  # give random pairs of neighbouring centres (and their galaxy rows) a common value
+        i = int(rng.integers(0, len(c) - 5))
+        for j in (i + 1, i + 3):
+            v = c[i, 4]
+            g[g[:, 6] == c[j, 6], 4] = v
+            c[j, 4] = v
+    stages = {}
+    np.random.seed(11)
+    final = O.FoF(g, c, O.Params(), mode="fast", stages=stages)
+    K, _ = handle.fof_run(g, c, lib.default_params())
+    off, mem, cen, N, _ = handle.fof_fetch(0)
+    assert len(cen) == len(stages["candidates"])
+    for k, (attrs, members) in enumerate(stages["candidates"]):
+        assert np.array_equal(c[cen[k]], attrs)
+        assert np.array_equal(g[mem[off[k]:off[k + 1]]], members)

@@ -35,6 +35,9 @@ def test_gpu_reproduces_reference_golden(lib, path):
     vir = mass_analysis.find_masses(cleaned, "virial")
     got = np.array([[float(getattr(v, k)) for k in KEYS] for v in vir]).reshape(-1, len(KEYS))
     np.testing.assert_allclose(got, g["virial"], rtol=1e-9)
+    # CleanedCluster.r200 (cluster.py:111-118) at delta = 200 and 500, from the unmodified reference under the shims
+    r = np.array([[float(v.r200(params.cosmo, 200)), float(v.r200(params.cosmo, 500))] for v in vir]).reshape(-1, 2)
+    np.testing.assert_allclose(r, g["r200"], rtol=1e-9)
     proj = mass_analysis.find_masses(cleaned, "projected")
     gotp = np.array([[float(v.cluster_mass), float(v.mass_err)] for v in proj]).reshape(-1, 2)
     np.testing.assert_allclose(gotp, g["projected"], rtol=1e-9)

@@ -72,7 +72,8 @@ def test_properties_table_equals_per_object_properties():
     off = np.concatenate([[0], np.cumsum(sizes)])
     rows = rng.integers(0, n, off[-1])
     cat = Catalogue(g, off, rows, rng.integers(0, n, K), rng.integers(8, 40, K).astype(float), rng.uniform(2, 9, K),
-                    rng.uniform(1, 10, (K, 6)))
+                    rng.uniform(1, 10, (K, 6)), N_row=rng.integers(0, 30, n).astype(np.int32))
+    assert np.array_equal(cat.cluster(1).galaxies[:, 7], cat.N_row[cat.members(1)])   # rows carry their own N(0.5)
     table = fio.properties_table(cat)
     want = np.array([c.properties for c in cat.clusters()])
     assert np.array_equal(table, want)

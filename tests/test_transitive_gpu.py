@@ -46,3 +46,17 @@ def test_percolating_blobs_deep_chains(lib):
     assert (lab <= np.arange(len(big))).all() and (lab[lab] == lab).all()
     assert n_groups == len(np.unique(lab))
     assert np.unique(lab, return_counts=True)[1].max() > 50000
+
+
+def test_pair_and_run_kernels_agree_at_10M(lib):
+    """BASELINE configs[2] size: the pair-by-pair kernel (with the link count) and the run-based kernel must label the
+    same 10M-galaxy catalogue identically (round 1 recorded different group counts for this pair of runs)."""
+    from fof_b200 import transitive
+    arr = make_catalog(10_000_000, seed=20260103, as_frame=False)
+    a, ga, links = transitive.friends_of_friends(arr, linking_length=0.3)
+    b, gb, _ = transitive.friends_of_friends(arr, linking_length=0.3, count_links=False)
+    assert ga == gb
+    assert np.array_equal(a, b)
+    n = len(arr)
+    assert (a <= np.arange(n)).all() and (a[a] == a).all() and ga == int((a == np.arange(n)).sum())
+    assert links > 0
