@@ -584,162 +584,346 @@ static int hop2_sort_above() {
   return v;
 }
 
-// (d) one CTA per centre: the surviving candidates are decided batch by batch.
-__global__ void __launch_bounds__(kHop2Threads) k_hop2(
-    int nr, const int* ready, const int* nv, const int* nF, const long long* voff, const long long* hoff,
-    const long long* hcap, unsigned long long* htab, View G, const double* v2ra, const double* v2dec, const double* v2cos,
-    const unsigned char* novel, const double* LLin, const double4* bbox2, fofb_params p, const int* v2row, int* mrows,
-    int* nm_list, int* first_batch, int* nm_sorted, int* nM, int* pass, const int* kill_target, unsigned char* alive,
-    unsigned char* decided, unsigned long long* sort_scratch, int sort_above) {
-  const int w = blockIdx.x;
-  if (w >= nr) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kWarps = kHop2Threads / 32;
-  const int c = ready[w];
-  const int n_v = nv[w];
-  __shared__ int s_nnm, s_members, s_warp_cnt[kWarps];
-  int n_members = 0;
-  if (n_v >= p.min_virial) {
-    const long long off = voff[w];
-    const int n_f = nF[w];
-    n_members = n_f;
-    const long long cap = hcap[w];
-    if (cap > 0) {
-      unsigned long long* tab = htab + hoff[w];
-      // candidates: the novel non-members, kept in V2 order (block-wide ordered compaction)
-      int n_nm = 0;
-      for (int base = n_f; base < n_v; base += kHop2Threads) {
-        const int t = base + tid;
-        const bool nov = t < n_v && novel[off + t];
-        const unsigned mk = __ballot_sync(0xffffffffu, nov);
-        if (lane == 0) s_warp_cnt[warp] = __popc(mk);
-        __syncthreads();
-        int before = 0, all = 0;
-        for (int k = 0; k < kWarps; ++k) {
-          before += k < warp ? s_warp_cnt[k] : 0;
-          all += s_warp_cnt[k];
-        }
-        if (nov) nm_list[off + n_nm + before + __popc(mk & ((1u << lane) - 1u))] = t;
-        n_nm += all;
-        __syncthreads();
-      }
-      if (n_nm > 0) {
-        const double LL = LLin[w];
-        const double4 b4 = bbox2[w];
-        const BBox b2{b4.x, b4.y, b4.z, b4.w};
-        const double sh = sin(0.5 * LL * kDeg2Rad);
-        const double T = sh * sh;
-        // first friend (in order) whose bubble contains each candidate.  Friends sit in the lanes, 32 per warp
-        // step; the candidates stream past them; atomicMin merges the warps' findings.
-        for (int q = tid; q < n_nm; q += kHop2Threads) first_batch[off + q] = 0x7fffffff;
-        __syncthreads();
-        for (int base = warp * 32; base < n_f; base += kHop2Threads) {
-          const int fi = base + lane;
-          const bool have = fi < n_f;
-          const double fra = have ? v2ra[off + fi] : 0.0, fdec = have ? v2dec[off + fi] : 0.0;
-          BubbleTest bt;
-          bt.init_T(fra, fdec, have ? v2cos[off + fi] : 1.0, LL, T);
-          const Box fbox = grid_box(b2, p.grid_cells, fra, fdec, LL);  // the friend's cell box: once per friend
-          for (int q = 0; q < n_nm; ++q) {
-            if (*(volatile int*)(first_batch + off + q) <= base) continue;  // an earlier friend already has it
-            const int vp = nm_list[off + q];
-            const double pra = v2ra[off + vp], pdec = v2dec[off + vp];
-            const bool hit = have && fbox.contains(pra, pdec) && bt.inside(pra, pdec, v2cos[off + vp]);
-            const unsigned mh = __ballot_sync(0xffffffffu, hit);
-            if (mh && lane == 0) atomicMin(first_batch + off + q, base + __ffs(mh) - 1);
-          }
-        }
-        __syncthreads();
-        // candidates ordered by (first batch, V2 position): rank by all-pairs counting -- or, for the tens of
-        // thousands of candidates of a giant bubble, a bitonic sort of the unique keys (first batch, position) in
-        // scratch memory (flip / disperse network: every exchange is ascending, so the virtual +inf padding up to
-        // the next power of two never moves and out-of-range partners are simply skipped)
-        if (n_nm > sort_above) {
-          unsigned long long* key = sort_scratch + off;
-          for (int q = tid; q < n_nm; q += kHop2Threads)
-            key[q] = ((unsigned long long)(unsigned)first_batch[off + q] << 32) | (unsigned)q;
-          __syncthreads();
-          for (int k = 2; (k >> 1) < n_nm; k <<= 1) {
-            for (int j = k; j > 1; j >>= 1) {
-              const int mask = j == k ? k - 1 : (j >> 1);  // flip on the first step of a merge, disperse after
-              for (int i = tid; i < n_nm; i += kHop2Threads) {
-                const int l = i ^ mask;
-                if (l > i && l < n_nm) {
-                  const unsigned long long a = key[i], b = key[l];
-                  if (a > b) { key[i] = b; key[l] = a; }
-                }
-              }
-              __syncthreads();
-            }
-          }
-          for (int q = tid; q < n_nm; q += kHop2Threads) nm_sorted[off + q] = (int)(unsigned)(key[q] & 0xffffffffull);
-        } else
-        for (int q = tid; q < n_nm; q += kHop2Threads) {
-          const int fq = first_batch[off + q];
-          int rank = 0;
-          for (int r = 0; r < n_nm; ++r) {
-            const int fr = first_batch[off + r];
-            rank += (fr < fq || (fr == fq && r < q)) ? 1 : 0;
-          }
-          nm_sorted[off + rank] = q;
-        }
-        __syncthreads();
-        // one pass over the batches in friend order; every candidate is decided in its first batch, against the
-        // member matrix as it stood before that batch.
-        const int cols = G.cols;
-        int s0 = 0;
-        while (s0 < n_nm) {
-          const int fb = first_batch[off + nm_sorted[off + s0]];
-          if (fb == 0x7fffffff) break;  // no friend's bubble contains the remaining rows
-          int s1 = s0 + 1;
-          while (s1 < n_nm && first_batch[off + nm_sorted[off + s1]] == fb) ++s1;
-          __syncthreads();
-          // pass 1: every row of the batch against the value set as it stands BEFORE the batch (a warp per row)
-          for (int j = s0 + warp; j < s1; j += kWarps) {
-            const int q = nm_sorted[off + j];
-            const int row = v2row[off + nm_list[off + q]];
-            bool found = false;
-            for (int col = lane; col < cols && !found; col += 32) found = hash_contains_owner(tab, cap, G.at(row, col));
-            const bool adm = !__any_sync(0xffffffffu, found);
-            if (lane == 0 && adm) first_batch[off + q] = -1;
-          }
-          __syncthreads();
-          // pass 2: append the admitted rows in order and extend the value set (warp 0)
-          if (warp == 0) {
-            int nm = n_members;
-            for (int j = s0; j < s1; ++j) {
-              const int q = nm_sorted[off + j];
-              if (first_batch[off + q] != -1) continue;
-              const int row = v2row[off + nm_list[off + q]];
-              if (lane == 0) {  // one thread inserts: plain stores, no two writers
-                mrows[off + nm] = row;
-                for (int col = 0; col < cols; ++col) hash_insert_owner(tab, cap, G.at(row, col));
-              }
-              ++nm;
-            }
-            if (lane == 0) s_members = nm;
-            __threadfence_block();
-          }
-          __syncthreads();
-          n_members = s_members;
-          s0 = s1;
-        }
-      }
-    }
-  }
+// FOFB_HOP2_SMEM_ROWS=<n> caps the number of hop-2 candidates the shared-memory path takes (the parity tests also run
+// with 0, which sends every centre through the global-memory path)
+static int hop2_smem_rows() {
+  static const int v = [] {
+    const char* e = getenv("FOFB_HOP2_SMEM_ROWS");
+    return e ? atoi(e) : (1 << 30);
+  }();
+  return v;
+}
+
+// The richness gate and the tracker for one centre (fof.py:230-246): members that are candidate centres never seed a
+// cluster later.  Called by all `nthreads` threads that share the centre (a warp or a CTA).
+__device__ __forceinline__ void hop2_finalize(int w, int c, int n_members, long long off, int tid, int nthreads,
+                                              const fofb_params& p, const int* mrows, const int* kill_target,
+                                              unsigned char* alive, unsigned char* decided, int* nM, int* pass) {
   const bool ok = n_members >= p.richness;
   if (tid == 0) {
     nM[w] = n_members;
     pass[w] = ok ? 1 : 0;
     decided[c] = 1;
   }
-  if (ok) {  // tracker: members that are candidate centres never seed a cluster later (fof.py:238-246)
-    const long long off = voff[w];
-    __syncthreads();
-    for (int t = tid; t < n_members; t += kHop2Threads) {
+  if (ok)
+    for (int t = tid; t < n_members; t += nthreads) {
       const int tgt = kill_target[mrows[off + t]];
       if (tgt > c) alive[tgt] = 0;
     }
+}
+
+// (d1) one warp per centre: the novel non-members in V2 order (the hop-2 candidates).  Centres without candidates are
+// finished here -- the common case: below ~100 virial points the linking length exceeds the virial radius and hop 1
+// already holds every point.  The others are queued by size class for k_hop2_heavy.
+__global__ void k_hop2_front(int nr, const int* ready, const int* nv, const int* nF, const long long* voff,
+                             const long long* hcap, const unsigned char* novel, fofb_params p, int* nm_list, int* n_nm_out,
+                             const int* mrows, int* nM, int* pass, const int* kill_target, unsigned char* alive,
+                             unsigned char* decided, int small_rows, int large_rows, int* qcount, int* qlist) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nr) return;
+  const int c = ready[w];
+  const int n_v = nv[w];
+  int n_members = 0, n_nm = 0;
+  long long off = 0;
+  if (n_v >= p.min_virial) {
+    off = voff[w];
+    const int n_f = nF[w];
+    n_members = n_f;
+    if (hcap[w] > 0) {
+      for (int base = n_f; base < n_v; base += 32) {
+        const int t = base + lane;
+        const bool nov = t < n_v && novel[off + t];
+        const unsigned mk = __ballot_sync(0xffffffffu, nov);
+        if (nov) nm_list[off + n_nm + __popc(mk & ((1u << lane) - 1u))] = t;
+        n_nm += __popc(mk);
+      }
+    }
+  }
+  if (lane == 0) n_nm_out[w] = n_nm;
+  if (n_nm == 0) {
+    hop2_finalize(w, c, n_members, off, lane, 32, p, mrows, kill_target, alive, decided, nM, pass);
+  } else if (lane == 0) {
+    const int cls = n_nm <= small_rows ? 0 : (n_nm <= large_rows ? 1 : 2);
+    qlist[(size_t)cls * nr + atomicAdd(qcount + cls, 1)] = w;
+  }
+}
+
+// Global-memory path of one centre for a 256-thread CTA (candidate sets that do not fit shared memory: the percolating
+// blobs of the dense stress configuration).  Returns the member count.
+__device__ int hop2_global_path(int w, int n_f, int n_nm, long long off, long long cap, unsigned long long* tab, View G,
+                                const double* v2ra, const double* v2dec, const double* v2cos, double LL, double4 b4,
+                                const fofb_params& p, const int* v2row, int* mrows, const int* nm_list, int* first_batch,
+                                int* nm_sorted, unsigned long long* sort_scratch, int sort_above) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kHop2Threads / 32;
+  __shared__ int s_members;
+  int n_members = n_f;
+  const BBox b2{b4.x, b4.y, b4.z, b4.w};
+  const double sh = sin(0.5 * LL * kDeg2Rad);
+  const double T = sh * sh;
+  // first friend (in order) whose bubble contains each candidate.  Friends sit in the lanes, 32 per warp
+  // step; the candidates stream past them; atomicMin merges the warps' findings.
+  for (int q = tid; q < n_nm; q += kHop2Threads) first_batch[off + q] = 0x7fffffff;
+  __syncthreads();
+  for (int base = warp * 32; base < n_f; base += kHop2Threads) {
+    const int fi = base + lane;
+    const bool have = fi < n_f;
+    const double fra = have ? v2ra[off + fi] : 0.0, fdec = have ? v2dec[off + fi] : 0.0;
+    BubbleTest bt;
+    bt.init_T(fra, fdec, have ? v2cos[off + fi] : 1.0, LL, T);
+    const Box fbox = grid_box(b2, p.grid_cells, fra, fdec, LL);  // the friend's cell box: once per friend
+    for (int q = 0; q < n_nm; ++q) {
+      if (*(volatile int*)(first_batch + off + q) <= base) continue;  // an earlier friend already has it
+      const int vp = nm_list[off + q];
+      const double pra = v2ra[off + vp], pdec = v2dec[off + vp];
+      const bool hit = have && fbox.contains(pra, pdec) && bt.inside(pra, pdec, v2cos[off + vp]);
+      const unsigned mh = __ballot_sync(0xffffffffu, hit);
+      if (mh && lane == 0) atomicMin(first_batch + off + q, base + __ffs(mh) - 1);
+    }
+  }
+  __syncthreads();
+  // candidates ordered by (first batch, V2 position): rank by all-pairs counting -- or, for the tens of
+  // thousands of candidates of a giant bubble, a bitonic sort of the unique keys (first batch, position) in
+  // scratch memory (flip / disperse network: every exchange is ascending, so the virtual +inf padding up to
+  // the next power of two never moves and out-of-range partners are simply skipped)
+  if (n_nm > sort_above) {
+    unsigned long long* key = sort_scratch + off;
+    for (int q = tid; q < n_nm; q += kHop2Threads)
+      key[q] = ((unsigned long long)(unsigned)first_batch[off + q] << 32) | (unsigned)q;
+    __syncthreads();
+    for (int k = 2; (k >> 1) < n_nm; k <<= 1) {
+      for (int j = k; j > 1; j >>= 1) {
+        const int mask = j == k ? k - 1 : (j >> 1);  // flip on the first step of a merge, disperse after
+        for (int i = tid; i < n_nm; i += kHop2Threads) {
+          const int l = i ^ mask;
+          if (l > i && l < n_nm) {
+            const unsigned long long a = key[i], b = key[l];
+            if (a > b) { key[i] = b; key[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int q = tid; q < n_nm; q += kHop2Threads) nm_sorted[off + q] = (int)(unsigned)(key[q] & 0xffffffffull);
+  } else
+  for (int q = tid; q < n_nm; q += kHop2Threads) {
+    const int fq = first_batch[off + q];
+    int rank = 0;
+    for (int r = 0; r < n_nm; ++r) {
+      const int fr = first_batch[off + r];
+      rank += (fr < fq || (fr == fq && r < q)) ? 1 : 0;
+    }
+    nm_sorted[off + rank] = q;
+  }
+  __syncthreads();
+  // one pass over the batches in friend order; every candidate is decided in its first batch, against the
+  // member matrix as it stood before that batch.
+  const int cols = G.cols;
+  int s0 = 0;
+  while (s0 < n_nm) {
+    const int fb = first_batch[off + nm_sorted[off + s0]];
+    if (fb == 0x7fffffff) break;  // no friend's bubble contains the remaining rows
+    int s1 = s0 + 1;
+    while (s1 < n_nm && first_batch[off + nm_sorted[off + s1]] == fb) ++s1;
+    __syncthreads();
+    // pass 1: every row of the batch against the value set as it stands BEFORE the batch (a warp per row)
+    for (int j = s0 + warp; j < s1; j += kWarps) {
+      const int q = nm_sorted[off + j];
+      const int row = v2row[off + nm_list[off + q]];
+      bool found = false;
+      for (int col = lane; col < cols && !found; col += 32) found = hash_contains_owner(tab, cap, G.at(row, col));
+      const bool adm = !__any_sync(0xffffffffu, found);
+      if (lane == 0 && adm) first_batch[off + q] = -1;
+    }
+    __syncthreads();
+    // pass 2: append the admitted rows in order and extend the value set (warp 0)
+    if (warp == 0) {
+      int nm = n_members;
+      for (int j = s0; j < s1; ++j) {
+        const int q = nm_sorted[off + j];
+        if (first_batch[off + q] != -1) continue;
+        const int row = v2row[off + nm_list[off + q]];
+        if (lane == 0) {  // one thread inserts: plain stores, no two writers
+          mrows[off + nm] = row;
+          for (int col = 0; col < cols; ++col) hash_insert_owner(tab, cap, G.at(row, col));
+        }
+        ++nm;
+      }
+      if (lane == 0) s_members = nm;
+      __threadfence_block();
+    }
+    __syncthreads();
+    n_members = s_members;
+    s0 = s1;
+  }
+  __syncthreads();
+  return n_members;
+}
+
+// (d2) the centres that have hop-2 candidates, one CTA at a time from the queue of a size class (persistent CTAs).
+// Only collisions BETWEEN candidates are still open (every candidate is already novel against the hop-1 members), so
+// the value set that matters is the candidates' own: their CAP x 8 values get a slot each in a shared-memory hash
+// table (parallel insert), and the batch loop -- sequential by nature: a batch sees what earlier batches admitted --
+// only reads and sets one byte per value.  Warp 0 walks the batches, four rows (x 8 columns) per step.
+//   shared memory per candidate row: ra, dec, cos (24) + 16 table slots (128) + first batch, order, row (12)
+//                                    + 8 slot ids (16) + 16 taken bytes = 196 bytes
+constexpr int kHop2SmallRows = 256, kHop2LargeRows = 1024;
+constexpr size_t hop2_smem_bytes(int cap_rows) { return (size_t)cap_rows * 196; }
+constexpr unsigned long long kSlotEmpty = ~0ull;
+
+template <int CAP>
+__global__ void __launch_bounds__(kHop2Threads) k_hop2_heavy(
+    int cls, int nr, const int* qcount, const int* qlist, const int* ready, const int* nF, const int* n_nm_in,
+    const long long* voff, const long long* hoff, const long long* hcap, unsigned long long* htab, View G,
+    const double* v2ra, const double* v2dec, const double* v2cos, const double* LLin, const double4* bbox2, fofb_params p,
+    const int* v2row, int* mrows, const int* nm_list, int* first_batch, int* nm_sorted, int* nM, int* pass,
+    const int* kill_target, unsigned char* alive, unsigned char* decided, unsigned long long* sort_scratch, int sort_above) {
+  extern __shared__ __align__(16) unsigned char hop2_smem[];
+  double* s_ra = reinterpret_cast<double*>(hop2_smem);
+  double* s_dec = s_ra + CAP;
+  double* s_cos = s_dec + CAP;
+  unsigned long long* s_tab = reinterpret_cast<unsigned long long*>(s_cos + CAP);  // 16 * CAP slots
+  int* s_fb = reinterpret_cast<int*>(s_tab + 16 * CAP);
+  int* s_sorted = s_fb + CAP;
+  int* s_row = s_sorted + CAP;
+  unsigned short* s_slot = reinterpret_cast<unsigned short*>(s_row + CAP);  // 8 per row; 0xffff: NaN, matches nothing
+  unsigned char* s_taken = reinterpret_cast<unsigned char*>(s_slot + 8 * CAP);
+  __shared__ int s_nmem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = qcount[cls];
+  for (int it = blockIdx.x; it < total; it += gridDim.x) {
+    const int w = qlist[(size_t)cls * nr + it];
+    const int c = ready[w];
+    const long long off = voff[w];
+    const int n_f = nF[w], n_nm = n_nm_in[w];
+    const double LL = LLin[w];
+    const double4 b4 = bbox2[w];
+    int n_members;
+    if (CAP == 0 || n_nm > CAP || G.cols != 8) {
+      n_members = hop2_global_path(w, n_f, n_nm, off, hcap[w], htab + hoff[w], G, v2ra, v2dec, v2cos, LL, b4, p, v2row, mrows,
+                                   nm_list, first_batch, nm_sorted, sort_scratch, sort_above);
+    } else {
+      const BBox b2{b4.x, b4.y, b4.z, b4.w};
+      const double sh = sin(0.5 * LL * kDeg2Rad);
+      const double T = sh * sh;
+      int tcap = 64;
+      while (tcap < 16 * n_nm) tcap <<= 1;
+      __syncthreads();  // the previous centre of this CTA is done with the shared arrays
+      for (int q = tid; q < n_nm; q += kHop2Threads) {
+        const int vp = nm_list[off + q];
+        s_ra[q] = v2ra[off + vp];
+        s_dec[q] = v2dec[off + vp];
+        s_cos[q] = v2cos[off + vp];
+        s_row[q] = v2row[off + vp];
+        s_fb[q] = 0x7fffffff;
+      }
+      for (int t = tid; t < tcap; t += kHop2Threads) {
+        s_tab[t] = kSlotEmpty;
+        s_taken[t] = 0;
+      }
+      __syncthreads();
+      // every candidate value gets its slot (row q, column col <-> thread stride)
+      for (int t = tid; t < 8 * n_nm; t += kHop2Threads) {
+        unsigned long long bits;
+        unsigned short slot = 0xffff;
+        if (value_bits(G.at(s_row[t >> 3], t & 7), &bits)) {
+          int sl = (int)(hash_mix(bits) & (unsigned long long)(tcap - 1));
+          for (;;) {
+            const unsigned long long old = atomicCAS(s_tab + sl, kSlotEmpty, bits);
+            if (old == kSlotEmpty || old == bits) break;
+            sl = (sl + 1) & (tcap - 1);
+          }
+          slot = (unsigned short)sl;
+        }
+        s_slot[t] = slot;
+      }
+      // first friend (in order) whose bubble contains each candidate: friends in the lanes, 32 per warp step, the
+      // candidates stream past them out of shared memory
+      for (int base = warp * 32; base < n_f; base += kHop2Threads) {
+        const int fi = base + lane;
+        const bool have = fi < n_f;
+        const double fra = have ? v2ra[off + fi] : 0.0, fdec = have ? v2dec[off + fi] : 0.0;
+        BubbleTest bt;
+        bt.init_T(fra, fdec, have ? v2cos[off + fi] : 1.0, LL, T);
+        const Box fbox = grid_box(b2, p.grid_cells, fra, fdec, LL);
+        for (int q = 0; q < n_nm; ++q) {
+          if (*(volatile int*)(s_fb + q) <= base) continue;  // an earlier friend already has it
+          const double pra = s_ra[q], pdec = s_dec[q];
+          const bool hit = have && fbox.contains(pra, pdec) && bt.inside(pra, pdec, s_cos[q]);
+          const unsigned mh = __ballot_sync(0xffffffffu, hit);
+          if (mh && lane == 0) atomicMin(s_fb + q, base + __ffs(mh) - 1);
+        }
+      }
+      __syncthreads();
+      // order by (first batch, V2 position)
+      for (int q = tid; q < n_nm; q += kHop2Threads) {
+        const int fq = s_fb[q];
+        int rank = 0;
+        for (int r = 0; r < n_nm; ++r) {
+          const int fr = s_fb[r];
+          rank += (fr < fq || (fr == fq && r < q)) ? 1 : 0;
+        }
+        s_sorted[rank] = q;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int nm = n_f;
+        int s0 = 0;
+        const int sub = lane >> 3, col = lane & 7;
+        while (s0 < n_nm) {
+          const int fb = s_fb[s_sorted[s0]];
+          if (fb == 0x7fffffff) break;  // no friend's bubble contains the remaining rows
+          int s1 = s0 + 1;
+          for (;;) {  // end of the batch
+            const int j = s1 + lane;
+            const bool differs = j >= n_nm || s_fb[s_sorted[j]] != fb;
+            const unsigned mk = __ballot_sync(0xffffffffu, differs);
+            if (mk) { s1 += __ffs(mk) - 1; break; }
+            s1 += 32;
+          }
+          // every row of the batch against the admitted values as they stand BEFORE the batch
+          for (int j0 = s0; j0 < s1; j0 += 4) {
+            const int j = j0 + sub;
+            bool blocked = false;
+            int q = 0;
+            if (j < s1) {
+              q = s_sorted[j];
+              const unsigned short sl = s_slot[8 * q + col];
+              blocked = sl != 0xffff && s_taken[sl];
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, blocked);
+            if (j < s1 && col == 0 && ((mk >> (lane & 24)) & 0xffu) == 0) s_fb[q] = -1;
+          }
+          __syncwarp();
+          // append the admitted rows in order; their values join the set
+          for (int j0 = s0; j0 < s1; j0 += 4) {
+            const int j = j0 + sub;
+            bool adm = false;
+            int q = 0;
+            if (j < s1) {
+              q = s_sorted[j];
+              adm = s_fb[q] == -1;
+            }
+            if (adm) {
+              const unsigned short sl = s_slot[8 * q + col];
+              if (sl != 0xffff) s_taken[sl] = 1;
+            }
+            const unsigned amk = __ballot_sync(0xffffffffu, adm && col == 0);
+            if (adm && col == 0) mrows[off + nm + __popc(amk & ((1u << lane) - 1u))] = s_row[q];
+            nm += __popc(amk);
+          }
+          __syncwarp();
+          s0 = s1;
+        }
+        if (lane == 0) s_nmem = nm;
+      }
+      __syncthreads();
+      n_members = s_nmem;
+    }
+    __threadfence_block();
+    __syncthreads();  // mrows of this centre are complete before the tracker pass reads them
+    hop2_finalize(w, c, n_members, off, tid, kHop2Threads, p, mrows, kill_target, alive, decided, nM, pass);
   }
 }
 
@@ -1146,9 +1330,35 @@ void FofState::round_evaluate(fofb_handle* h) {
           FOFB_PROFILED(h, "k_hop2_novel", k_hop2_novel<<<grid_for(total_v, B), B, 0, st>>>(total_v, own, vo, nF_p, ho, need, htab.p, G, v2, nov));
         }
       }
-      FOFB_PROFILED(h, "k_hop2", k_hop2<<<nr, kHop2Threads, 0, st>>>(nr, rb, nv_p, nF_p, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p,
-                                      ismember.p, LLp, bb2, p, v2, mr, nml, fbatch, nm_sorted.alloc(tv), nM_p, pass_p, kill_target.p, alive.p,
-                                      decided.p, k1, hop2_sort_above()));
+      {
+        int* qc = hop2_qcount.alloc(4);
+        int* ql = hop2_qlist.alloc((size_t)nr * 3);
+        int* nnm = hop2_nnm.alloc(nr);
+        int* nms = nm_sorted.alloc(tv);
+        FOFB_CUDA(cudaMemsetAsync(qc, 0, sizeof(int) * 4, st));
+        const int cap_rows = hop2_smem_rows();
+        const int small_rows = std::min(kHop2SmallRows, cap_rows), large_rows = std::min(kHop2LargeRows, cap_rows);
+        FOFB_PROFILED(h, "k_hop2_front", k_hop2_front<<<wblocks, 128, 0, st>>>(nr, rb, nv_p, nF_p, vo, need, ismember.p, p, nml, nnm, mr, nM_p,
+                                                    pass_p, kill_target.p, alive.p, decided.p, small_rows, large_rows, qc, ql));
+        static bool attr_set[64] = {};
+        if (!attr_set[h->device & 63]) {
+          FOFB_CUDA(cudaFuncSetAttribute(k_hop2_heavy<kHop2SmallRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hop2_smem_bytes(kHop2SmallRows)));
+          FOFB_CUDA(cudaFuncSetAttribute(k_hop2_heavy<kHop2LargeRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hop2_smem_bytes(kHop2LargeRows)));
+          attr_set[h->device & 63] = true;
+        }
+        // persistent CTAs over the three queues: <= 256 candidates (4 CTAs per SM), <= 1024 (one per SM), the rest
+        // (global-memory path).  The queues are usually short or empty; an empty queue costs one launch.
+        const int g0 = std::min(nr, h->sm_count * 4), g1 = std::min(nr, h->sm_count), g2 = std::min(nr, h->sm_count * 2);
+        FOFB_PROFILED(h, "k_hop2", k_hop2_heavy<kHop2SmallRows><<<g0, kHop2Threads, hop2_smem_bytes(kHop2SmallRows), st>>>(
+            0, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
+            pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above()));
+        FOFB_PROFILED(h, "k_hop2", k_hop2_heavy<kHop2LargeRows><<<g1, kHop2Threads, hop2_smem_bytes(kHop2LargeRows), st>>>(
+            1, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
+            pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above()));
+        FOFB_PROFILED(h, "k_hop2", k_hop2_heavy<0><<<g2, kHop2Threads, 0, st>>>(
+            2, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
+            pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above()));
+      }
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse
       long long* dst = ho;    // reuse

@@ -49,7 +49,7 @@ struct FofState {
   DBuf<unsigned long long> keys1, keys1b, keys2, keys2b, htab;
   DBuf<int> v2row, mrows, nm_list, first_batch;
   DBuf<double> cc_z, v2ra, v2dec, v2cos;
-  DBuf<int> owner, nm_sorted;
+  DBuf<int> owner, nm_sorted, hop2_qcount, hop2_qlist, hop2_nnm;
   DBuf<unsigned char> ismember;
   DBuf<double> LL;
   DBuf<double4> bbox1, bbox2;

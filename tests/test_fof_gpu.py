@@ -130,12 +130,15 @@ def test_round_sort_paths_agree(tmp_path):
         "np.savez(sys.argv[1], off=cat.offsets, rows=cat.member_rows, centre=cat.centre_row, N=cat.N, D=cat.D, props=cat.props)\n"
     ) % root
     outs = []
-    # (virial points: segmented sort | two radix sorts) x (hop-2 candidates: ranking by counting | bitonic sort, which
-    # FOFB_HOP2_SORT_ABOVE moves the same way)
-    for tag, radix_above, hop2_above in (("segmented", str(1 << 40), str(1 << 30)), ("radix", "0", str(1 << 30)),
-                                         ("bitonic", str(1 << 40), "0")):
+    # (virial points: segmented sort | two radix sorts) x (hop-2 candidates: shared-memory path | global-memory path with
+    # ranking by counting | global-memory path with the bitonic sort, which FOFB_HOP2_SORT_ABOVE moves)
+    for tag, radix_above, hop2_above, smem_rows in (("segmented", str(1 << 40), str(1 << 30), str(1 << 30)),
+                                                    ("radix", "0", str(1 << 30), str(1 << 30)),
+                                                    ("global", str(1 << 40), str(1 << 30), "0"),
+                                                    ("small-class-only", str(1 << 40), str(1 << 30), "8"),
+                                                    ("bitonic", str(1 << 40), "0", "0")):
         out = str(tmp_path / (tag + ".npz"))
-        env = dict(os.environ, FOFB_RADIX_ABOVE=radix_above, FOFB_HOP2_SORT_ABOVE=hop2_above)
+        env = dict(os.environ, FOFB_RADIX_ABOVE=radix_above, FOFB_HOP2_SORT_ABOVE=hop2_above, FOFB_HOP2_SMEM_ROWS=smem_rows)
         subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root)
         outs.append(np.load(out))
     a = outs[0]
