@@ -626,6 +626,7 @@ __global__ void k_member_trig(long long total, View M, double4* trig) {
 }
 
 constexpr int kVirialThreads = 256;
+constexpr int kVirialTrig = 512;  // clusters up to this size keep their members' sines and cosines in shared memory
 constexpr int kBootNum = 100;
 
 // One CTA per cluster.
@@ -718,7 +719,6 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   const long long s0 = off[k];
   const int n = (int)(off[k + 1] - s0);
   const int tid = threadIdx.x;
-  __shared__ double sh[kVirialThreads];
   __shared__ double boot[kBootNum];
   __shared__ double s_zbar, s_vdisp, s_zavg_err;
   __shared__ long long s_taken;
@@ -731,39 +731,61 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
     }
     return;
   }
-  auto getz = [&](long long i) -> double { return M.at(s0 + i, 2); };
+  // The cluster's redshifts, redshift errors and v^2 live in shared memory (clusters of up to 1024 members; longer
+  // ones read the member matrix): thread 0's numpy-ordered sums below are chains of dependent loads, which cost a
+  // shared-memory access each instead of a cache round trip.
+  __shared__ double sv2[1024], s_z[1024], s_e[1024];
+  __shared__ double4 s_trig[kVirialTrig];
+  const bool cached = n <= 1024;
+  const bool trig_cached = n <= kVirialTrig;
+  if (cached)
+    for (int i = tid; i < n; i += kVirialThreads) {
+      const double z = M.at(s0 + i, 2);
+      s_z[i] = z;
+      s_e[i] = fmax(fabs(__dsub_rn(M.at(s0 + i, 3), z)), fabs(__dsub_rn(M.at(s0 + i, 4), z)));
+    }
+  if (trig_cached)
+    for (int i = tid; i < n; i += kVirialThreads) s_trig[i] = trig[s0 + i];
+  for (int i = tid; i < kBootNum; i += kVirialThreads) boot[i] = 0.0;
+  __syncthreads();
+  auto getz = [&](long long i) -> double { return cached ? s_z[i] : M.at(s0 + i, 2); };
   if (tid == 0) {
     s_zbar = __ddiv_rn(np_pairwise_sum(getz, 0, n), (double)n);  // np.mean
     auto getv2 = [&](long long i) -> double {
-      const double v = redshift_to_velocity(M.at(s0 + i, 2), s_zbar);
+      const double v = redshift_to_velocity(getz(i), s_zbar);
       return __dmul_rn(v, v);
     };
     s_vdisp = __ddiv_rn(np_pairwise_sum(getv2, 0, n), (double)(n - 1));  // np.sum(v**2)/(n-1)
     // velocity_error: z_average_err = sqrt(sum(zerr**2)) / n   (builtin sum: sequential)
     double acc = 0.0;
     for (int i = 0; i < n; ++i) {
-      const double z = M.at(s0 + i, 2);
-      const double e = fmax(fabs(__dsub_rn(M.at(s0 + i, 3), z)), fabs(__dsub_rn(M.at(s0 + i, 4), z)));
+      double e;
+      if (cached) {
+        e = s_e[i];
+      } else {
+        const double z = M.at(s0 + i, 2);
+        e = fmax(fabs(__dsub_rn(M.at(s0 + i, 3), z)), fabs(__dsub_rn(M.at(s0 + i, 4), z)));
+      }
       acc = __dadd_rn(acc, __dmul_rn(e, e));
     }
     s_zavg_err = __ddiv_rn(sqrt(acc), (double)n);
     s_taken = 0;
     s_fail = 0;
   }
-  for (int i = tid; i < kBootNum; i += kVirialThreads) boot[i] = 0.0;
   __syncthreads();
   const double zbar = s_zbar;
   // harmonic term: (1/n) * (sum(1/err^2))^-1   (order-free reduction; tolerance 1e-9)
   double part = 0.0, mag = 0.0;
   for (int i = tid; i < n; i += kVirialThreads) {
-    const double z = M.at(s0 + i, 2);
+    const double z = getz(i);
     const double v = redshift_to_velocity(z, zbar);
-    const double e = fmax(fabs(M.at(s0 + i, 3) - z), fabs(M.at(s0 + i, 4) - z));
+    const double e = cached ? s_e[i] : fmax(fabs(M.at(s0 + i, 3) - z), fabs(M.at(s0 + i, 4) - z));
     const double zd = sqrt(s_zavg_err * s_zavg_err + e * e);
     const double a = s_zavg_err / zbar, b = zd / (z - zbar);
     const double err = fabs(v) * sqrt(a * a + b * b);
     part += 1.0 / (err * err);
     mag += pow(10.0, -0.4 * M.at(s0 + i, 5));
+    if (cached) sv2[i] = v * v;
   }
   typedef cub::BlockReduce<double, kVirialThreads> Reduce;
   __shared__ typename Reduce::TempStorage rtmp;
@@ -786,7 +808,7 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
         ++i;
       }
       if (i >= n - 1) break;
-      const double4 a = trig[s0 + i], b = trig[s0 + j];
+      const double4 a = trig_cached ? s_trig[i] : trig[s0 + i], b = trig_cached ? s_trig[j] : trig[s0 + j];
       const double sdlon = b.x * a.y - b.y * a.x, cdlon = b.y * a.y + b.x * a.x;
       const double num1 = b.w * sdlon;
       const double num2 = a.w * b.z - a.z * b.w * cdlon;
@@ -816,13 +838,6 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   const long long want = (long long)kBootNum * (n - 1);
   typedef cub::BlockScan<long long, kVirialThreads> Scan;
   __shared__ typename Scan::TempStorage stmp;
-  __shared__ double sv2[1024];
-  const bool cached = n <= 1024;
-  if (cached)
-    for (int i = tid; i < n; i += kVirialThreads) {
-      const double v = redshift_to_velocity(M.at(s0 + i, 2), zbar);
-      sv2[i] = v * v;
-    }
   long long L = (long long)((double)want * ((double)mask + 1.0) / (double)n * 1.05) + 2048;
   if (L > mt_len) L = mt_len;
   long long lo_w, hi_w, base, total;

@@ -5,95 +5,100 @@
 
 #include "catalog_host.cuh"
 #include "stage0.cuh"
+#include "tile.cuh"
 
 namespace fofb {
 
 // ---- K5a: per-galaxy query record, one thread per z-rank ----------------------------------------
 // theta_0.5(z_i), the velocity window of galaxy i, the bounding box of that window (= the bbox of
-// the GriSPy grid find_number_count builds, helper.py:181) and the resulting cell-box bounds.
+// the GriSPy grid find_number_count builds, helper.py:181) and the resulting cell-box bounds.  The box binds only
+// when a grid edge falls inside the sliver (r, r / cos dec] next to the query: the record keeps a flag
+// (bit 31 of whi) and the four bounds go to a side array that is touched for those queries alone.
 __global__ void k_count_prep(CatalogView cat, Cosmo cosmo, double count_radius, double vmax, int min_window,
-                             int grid_cells, QueryRec* rec, double* theta_out) {
+                             int grid_cells, CountRec* rec, double4* box, double* theta_out) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= cat.n) return;
   const double z = cat.zs[r];
   const double theta = cosmo_linear_to_angular_dist(cosmo, count_radius, z);
   int lo, hi;
   velocity_window(cat.zs, (int)cat.n, z, vmax, &lo, &hi);
-  QueryRec q;
+  CountRec q;
   q.r_deg = theta;
   q.wlo = lo;
   q.whi = hi;
   if (hi - lo >= min_window) {
     const BBox bb = range_bbox(cat, lo, hi);
     const Box b = grid_box(bb, grid_cells, cat.zra[r], cat.zdec[r], theta);
-    q.ra_lo = b.ra_lo; q.ra_hi = b.ra_hi; q.dec_lo = b.dec_lo; q.dec_hi = b.dec_hi;
+    if (b.ra_lo != -INFINITY || b.ra_hi != INFINITY || b.dec_lo != -INFINITY || b.dec_hi != INFINITY) {
+      box[r] = make_double4(b.ra_lo, b.ra_hi, b.dec_lo, b.dec_hi);
+      q.whi |= (int)0x80000000;
+    }
   } else {
-    q.ra_lo = q.dec_lo = INFINITY;
-    q.ra_hi = q.dec_hi = -INFINITY;
     q.whi = lo;  // empty window => N stays 0 (fof.py:71)
   }
   rec[r] = q;
   theta_out[r] = theta;
 }
 
-// ---- K5: the count.  One thread per galaxy in cell order (a warp = 32 consecutive members of one
-// or two adjacent cells, so their probes and candidate loads share L1 lines).  Cells are z-rank
-// sorted, so the velocity window is one contiguous sub-range per neighbour cell, found by binary
-// search; only in-window candidates reach the cell-box and fp64 haversine tests.
-__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int lo, int hi, int key) {
-  while (lo < hi) {
-    const int m = (lo + hi) >> 1;
-    if (__ldg(a + m) < key) lo = m + 1; else hi = m;
+// ---- K5: the count -------------------------------------------------------------------------------------------------
+// One CTA per strip of kCtW consecutive cells of one cell row.  The strip's neighbourhood -- the same cells plus one on
+// either side, in the rows above, at and below -- is three contiguous slices of the cell-ordered SoA (ra, dec, cos dec,
+// z-rank): they are brought into shared memory with bulk asynchronous copies (cp.async.bulk, one mbarrier), and every
+// galaxy of the strip then runs its query against shared memory: per neighbour cell a binary search of its z-rank
+// window (cells are z-rank sorted), then the cell-box and fp64 haversine tests on the in-window candidates.
+// A neighbourhood that does not fit (percolating blobs) is read from global memory by the same code.
+// The queries q0 <= qi < q1 of one strip.  P_* index the staged slices (shared memory) or the cell list itself.
+__device__ __forceinline__ void count_strip(const CellListView& cl, const double* __restrict__ P_ra,
+                                            const double* __restrict__ P_dec, const double* __restrict__ P_cos,
+                                            const int* __restrict__ P_zr, const Tile& t, int q0, int q1,
+                                            const CountRec* __restrict__ rec, const double4* __restrict__ box,
+                                            int* __restrict__ N_row) {
+  for (int qi = q0 + (int)threadIdx.x; qi < q1; qi += kCtThreads) {
+    const int li = qi + t.delta[1];
+    const int zr = P_zr[li];
+    const CountRec qr = rec[zr];
+    const int wlo = qr.wlo, whi = qr.whi & 0x7fffffff;
+    int count = 0;
+    if (whi > wlo) {
+      const double ra = P_ra[li], dec = P_dec[li];
+      BubbleTest bt;
+      bt.init(ra, dec, P_cos[li], qr.r_deg);
+      Box bx{-INFINITY, INFINITY, -INFINITY, INFINITY};
+      if (qr.whi < 0) {
+        const double4 b = box[zr];
+        bx = Box{b.x, b.y, b.z, b.w};
+      }
+      const int cx = cl.cx_of(ra);
+      const int k0 = (cx > 0 ? cx - 1 : 0) - t.xa, k1 = (cx < cl.ncx - 1 ? cx + 1 : cl.ncx - 1) - t.xa;
+      count = tile_count(P_ra, P_dec, P_cos, P_zr, t, 0, 2, k0, k1, wlo, whi, bt, bx);
+    }
+    N_row[cl.row[qi]] = count;
   }
-  return lo;
 }
 
-__global__ void __launch_bounds__(256) k_count(CellListView cl, int n, const QueryRec* __restrict__ rec,
-                                               int* __restrict__ N_row) {
-  __shared__ int run_lo[9][256], run_hi[9][256];  // per thread: the runs of its (at most 3 x 3) neighbour cells
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const QueryRec qr = rec[cl.zrank[q]];
-  int count = 0;
-  if (qr.whi > qr.wlo) {
-    const double ra = cl.ra[q], dec = cl.dec[q];
-    BubbleTest bt;
-    bt.init(ra, dec, cl.cosdec[q], qr.r_deg);
-    const int cx = cl.cx_of(ra), cy = cl.cy_of(dec);
-    const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < cl.ncx - 1 ? cx + 1 : cl.ncx - 1;
-    const int y0 = cy > 0 ? cy - 1 : 0, y1 = cy < cl.ncy - 1 ? cy + 1 : cl.ncy - 1;
-    // pass 1: the in-window run of every neighbour cell (uniform work: two binary searches per cell);
-    // pass 2: ONE loop over the runs back to back, so that a warp iterates max-over-lanes of the TOTAL number of
-    // candidates instead of the sum over cells of the per-cell maxima (the runs are 0-3 long for field galaxies).
-    int nrun = 0;
-    for (int yy = y0; yy <= y1; ++yy) {
-      int s = __ldg(cl.cell_start + yy * cl.ncx + x0);
-      for (int xx = x0; xx <= x1; ++xx) {
-        const int e = __ldg(cl.cell_start + yy * cl.ncx + xx + 1);
-        const int a = lower_bound_i32(cl.zrank, s, e, qr.wlo);
-        const int b = lower_bound_i32(cl.zrank, a, e, qr.whi);
-        if (b > a) {
-          run_lo[nrun][threadIdx.x] = a;
-          run_hi[nrun][threadIdx.x] = b;
-          ++nrun;
-        }
-        s = e;
-      }
-    }
-    int c = 0;
-    int j = nrun ? run_lo[0][threadIdx.x] : 0, end = nrun ? run_hi[0][threadIdx.x] : 0;
-    while (c < nrun) {
-      const double pra = __ldg(cl.ra + j), pdec = __ldg(cl.dec + j);
-      if (pra >= qr.ra_lo && pra <= qr.ra_hi && pdec >= qr.dec_lo && pdec <= qr.dec_hi &&
-          bt.inside(pra, pdec, __ldg(cl.cosdec + j)))
-        ++count;
-      if (++j == end && ++c < nrun) {
-        j = run_lo[c][threadIdx.x];
-        end = run_hi[c][threadIdx.x];
-      }
-    }
-  }
-  N_row[cl.row[q]] = count;
+__global__ void __launch_bounds__(kCtThreads, 2) k_count(CellListView cl, int nsx, const CountRec* __restrict__ rec,
+                                                     const double4* __restrict__ box, int* __restrict__ N_row) {
+  extern __shared__ __align__(128) unsigned char ct_smem[];
+  __shared__ int s_cs[3][kCtW + 3];
+  __shared__ int s_delta[3];
+  __shared__ int s_fits;
+  __shared__ __align__(8) unsigned long long s_bar;
+  Tile t;
+  t.ra = reinterpret_cast<double*>(ct_smem);
+  t.dec = t.ra + kCtMaxPts;
+  t.cos = t.dec + kCtMaxPts;
+  t.zr = reinterpret_cast<int*>(t.cos + kCtMaxPts);
+  t.cs = s_cs;
+  t.delta = s_delta;
+  const int y = blockIdx.x / nsx, x0 = (blockIdx.x % nsx) * kCtW;
+  // the strip's own galaxies are the queries; an empty strip stages nothing
+  const int xe = x0 + kCtW < cl.ncx ? x0 + kCtW : cl.ncx;
+  const int q0 = __ldg(cl.cell_start + (size_t)y * cl.ncx + x0), q1 = __ldg(cl.cell_start + (size_t)y * cl.ncx + xe);
+  if (q1 <= q0) return;
+  if (tile_stage(cl, y, x0, t, &s_bar, &s_fits))
+    count_strip(cl, t.ra, t.dec, t.cos, t.zr, t, q0, q1, rec, box, N_row);
+  else
+    count_strip(cl, cl.ra, cl.dec, cl.cosdec, cl.zrank, t, q0, q1, rec, box, N_row);
 }
 
 // ---- K6: candidate keys: N descending, ties by descending row (oracle pin D1 of fof.py:79-81) ----
@@ -118,11 +123,12 @@ void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat, CellList& c
   const int n = (int)cat.n;
   const int B = 256;
   const Cosmo cosmo = device_cosmo(h, p);
-  QueryRec* recs = rec.alloc(n);
+  CountRec* recs = rec.alloc(n);
+  double4* boxes = box.alloc(n);
   double* th = theta.alloc(n);
   CatalogView cv = cat.view();
   FOFB_PROFILED(h, "k_count_prep", k_count_prep<<<grid_for(n, B), B, 0, st>>>(cv, cosmo, p.count_radius, p.max_velocity, p.min_window, p.grid_cells,
-                                             recs, th));
+                                             recs, boxes, th));
   // largest query radius sizes the cell list
   double* tmax = theta_max.alloc(1);
   size_t bytes = 0;
@@ -135,7 +141,16 @@ void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat, CellList& c
   FOFB_REQUIRE(std::isfinite(r_max) && r_max > 0.0, "non-finite angular radius (check redshifts and cosmology)");
   cells.build(h, cat, r_max);
   int* N = N_row.alloc(n);
-  FOFB_PROFILED(h, "k_count", k_count<<<grid_for(n, 256), 256, 0, st>>>(cells.view(), n, recs, N));
+  {
+    static bool attr_set[64] = {};
+    if (!attr_set[h->device & 63]) {
+      FOFB_CUDA(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
+      attr_set[h->device & 63] = true;
+    }
+    const CellListView clv = cells.view();
+    const int nsx = (clv.ncx + kCtW - 1) / kCtW;
+    FOFB_PROFILED(h, "k_count", k_count<<<nsx * clv.ncy, kCtThreads, kCtSmemBytes, st>>>(clv, nsx, recs, boxes, N));
+  }
 
   unsigned long long* k_all = key_all.alloc(n);
   unsigned long long* k_sel = key_sel.alloc(n);

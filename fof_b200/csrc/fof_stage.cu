@@ -140,7 +140,21 @@ struct CentreCells {
   const int* start;
   const int* idx;     // centre index, cells sorted by centre redshift
   const double* z;    // centre redshift in the same order
+  // the same order, packed for the blocking scan: a = (ra, dec, z, centre index as bits), b = (cos dec, R1, T1, -).
+  // A scan walks consecutive entries, so the candidates' scalars arrive by whole cache lines instead of one random
+  // sector per per-centre array.
+  const double4* a;
+  const double4* b;
 };
+
+__global__ void k_cc_pack(int m, const int* idx, const double* c_ra, const double* c_dec, const double* c_cos, const double* c_z,
+                          const double* c_R1, const double* c_T1, double4* a, double4* b) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int j = idx[k];
+  a[k] = make_double4(c_ra[j], c_dec[j], c_z[j], __longlong_as_double((long long)j));
+  b[k] = make_double4(c_cos[j], c_R1[j], c_T1[j], 0.0);
+}
 
 // ---- K9a: which active centres can be evaluated now ----------------------------------------------------------
 // Centre j (higher priority: j < i) can claim the galaxy that switches centre i off only if that galaxy lies
@@ -188,12 +202,15 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
         int hi = e;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
       }
-      for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
-        const int j = cc.idx[k];
+      for (int k = lo; k < e; ++k) {
+        const double4 ca = cc.a[k];
+        if (ca.z > zhi) break;
+        const int j = (int)__double_as_longlong(ca.w);
         if (j >= i || !alive[j] || decided[j]) continue;
-        if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+        if (fabs(redshift_to_velocity(z, ca.z)) > vmax) continue;
+        const double4 cb = cc.b[k];
         BubbleTest bt;
-        bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
+        bt.init_T(ca.x, ca.y, cb.x, cb.y, cb.z);
         if (bt.inside(ra, dec, cs)) {
           blocked = true;
           resume_row[i] = r;
@@ -240,12 +257,15 @@ __global__ void k_ready_warp(int na, const int* active, CentreCells cc, const do
       const int e = cc.start[yy * cc.ncx + xx + 1];
       int hi = e;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
-      for (int k = lo; k < e && cc.z[k] <= zhi; ++k) {
-        const int j = cc.idx[k];
+      for (int k = lo; k < e; ++k) {
+        const double4 ca = cc.a[k];
+        if (ca.z > zhi) break;
+        const int j = (int)__double_as_longlong(ca.w);
         if (j >= i || !alive[j] || decided[j]) continue;
-        if (fabs(redshift_to_velocity(z, c_z[j])) > vmax) continue;
+        if (fabs(redshift_to_velocity(z, ca.z)) > vmax) continue;
+        const double4 cb = cc.b[k];
         BubbleTest bt;
-        bt.init_T(c_ra[j], c_dec[j], c_cos[j], c_R1[j], c_T1[j]);
+        bt.init_T(ca.x, ca.y, cb.x, cb.y, cb.z);
         if (bt.inside(ra, dec, cs)) { blocked = true; break; }
       }
     }
@@ -1163,6 +1183,8 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
     FOFB_LAUNCH_CHECK(h);
     k_gather_d<<<grid_for(m, B), B, 0, st>>>(m, vb, c_z.p, cc_z.alloc(mm));
     FOFB_LAUNCH_CHECK(h);
+    k_cc_pack<<<grid_for(m, B), B, 0, st>>>(m, vb, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, cc_a.alloc(mm), cc_b.alloc(mm));
+    FOFB_LAUNCH_CHECK(h);
   }
   // ---- priority rounds: initial active list -------------------------------------------------------
   FOFB_CUDA(cudaMemsetAsync(resume_row.alloc(mm), 0, sizeof(int) * mm, st));
@@ -1221,7 +1243,7 @@ void FofState::round_evaluate(fofb_handle* h) {
   if (na <= 0) return;
   const Cosmo cosmo = device_cosmo(h, p);
   CatalogView cv = cat.view();
-  CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p, cc_z.p};
+  CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p, cc_z.p, cc_a.p, cc_b.p};
   CellListView clbig = big.view();
   int* act = act_in_a ? active_a.p : active_b.p;
   int* d_count = reinterpret_cast<int*>(scal.p + 8);

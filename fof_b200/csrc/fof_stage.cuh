@@ -52,7 +52,7 @@ struct FofState {
   DBuf<int> owner, nm_sorted, hop2_qcount, hop2_qlist, hop2_nnm;
   DBuf<unsigned char> ismember;
   DBuf<double> LL;
-  DBuf<double4> bbox1, bbox2;
+  DBuf<double4> bbox1, bbox2, cc_a, cc_b;
   DBuf<long long> scal;    // device scalars
   DBuf<double> sort_keys_d, sort_keys_d2;
   DBuf<int> sort_vals, sort_vals2;

@@ -8,6 +8,7 @@
 
 #include "fof_stage.cuh"
 #include "mt_jump_tables.h"
+#include "tile.cuh"
 
 namespace fofb {
 
@@ -557,9 +558,16 @@ __global__ void k_own_count(int K, const int* centre, const long long* off, cons
   if (lane == 0) N_out[k] = cnt;
 }
 
-// per cluster: window bbox and the "all 300 points out of field" flag (helper.py:207-213, App. B.1)
+// per cluster: window bbox and the "all 300 points out of field" flag (helper.py:207-213, App. B.1), packed with the
+// radius and the window for the point queries.  whi == wlo: nothing to count.
+struct OdCluster {
+  double4 bbox;
+  double r;
+  int wlo, whi;
+};
+
 __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, const int* c_wlo, const int* c_whi,
-                          const double* c_th05, const double* rra, const double* rdec, double4* bbox, int* all_oof) {
+                          const double* c_th05, const double* rra, const double* rdec, OdCluster* oc) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (k >= K) return;
@@ -579,13 +587,17 @@ __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, c
   }
   all = __all_sync(0xffffffffu, all);
   if (lane == 0) {
-    bbox[k] = make_double4(b.ra_min, b.ra_max, b.dec_min, b.dec_max);
-    all_oof[k] = (all || hi <= lo) ? 1 : 0;
+    OdCluster o;
+    o.bbox = make_double4(b.ra_min, b.ra_max, b.dec_min, b.dec_max);
+    o.r = r;
+    o.wlo = lo;
+    o.whi = (all || hi <= lo) ? lo : hi;
+    oc[k] = o;
   }
 }
 
-// cell of every query point, so that the queries can be processed in cell order (neighbouring threads then
-// touch the same cells: the 300 points of one cluster are scattered over the whole footprint)
+// cell of every query point, so that the queries can be processed in cell order (the 300 points of one cluster are
+// scattered over the whole footprint)
 __global__ void k_od_keys(long long total, CellListView cl, const double* rra, const double* rdec, unsigned* key, int* val) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= total) return;
@@ -593,66 +605,75 @@ __global__ void k_od_keys(long long total, CellListView cl, const double* rra, c
   val[q] = (int)q;
 }
 
-// one thread per (cluster, random point): galaxies of the centre's velocity window within theta_0.5
-constexpr int kOdThreads = 128, kOdRuns = 9;
-
-__global__ void __launch_bounds__(kOdThreads) k_od_count(long long total, int npts, const int* order, const int* centre, CellListView cl, const int* c_wlo,
-                           const int* c_whi, const double* c_th05, const double4* bbox, const int* all_oof,
-                           const double* rra, const double* rdec, int grid_cells, int* counts) {
-  __shared__ int run_lo[kOdRuns][kOdThreads], run_hi[kOdRuns][kOdThreads];
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const long long q = order[t];
-  const int k = (int)(q / npts);
-  int cnt = 0;
-  if (!all_oof[k]) {
-    const int c = centre[k];
-    const int wlo = c_wlo[c], whi = c_whi[c];
-    const double r = c_th05[c];
-    const double ra = rra[q], dec = rdec[q];
-    const double4 b4 = bbox[k];
-    const BBox b{b4.x, b4.y, b4.z, b4.w};
-    const Box box = grid_box(b, grid_cells, ra, dec, r);
-    BubbleTest bt;
-    bt.init(ra, dec, cos(__dmul_rn(dec, kDeg2Rad)), r);
-    const double reach = ra_reach(r, dec);
-    const int x0 = cl.cx_of(ra - reach), x1 = cl.cx_of(ra + reach);
-    const int y0 = cl.cy_of(dec - r * 1.000001), y1 = cl.cy_of(dec + r * 1.000001);
-    // runs first, then one loop over all of them (see k_count): neighbouring threads belong to different clusters,
-    // their runs are 0-2 long, and a loop per cell would run with three lanes of a warp active
-    int nrun = 0;
-    for (int yy = y0; yy <= y1; ++yy)
-      for (int xx = x0; xx <= x1; ++xx) {
-        const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
-        int a = s, bnd = e;
-        while (a < bnd) { const int mid = (a + bnd) >> 1; if (cl.zrank[mid] < wlo) a = mid + 1; else bnd = mid; }
-        const int first = a;
-        bnd = e;
-        while (a < bnd) { const int mid = (a + bnd) >> 1; if (cl.zrank[mid] < whi) a = mid + 1; else bnd = mid; }
-        if (a == first) continue;
-        if (nrun < kOdRuns) {
-          run_lo[nrun][threadIdx.x] = first;
-          run_hi[nrun][threadIdx.x] = a;
-          ++nrun;
-        } else {  // more cells than the table holds (cells smaller than the bubble): count this one directly
-          for (int j = first; j < a; ++j) {
-            const double pra = cl.ra[j], pdec = cl.dec[j];
-            if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
+// Galaxies of the centre's velocity window within theta_0.5 of each random point (helper.py:207-216).  One CTA per
+// strip of cells, as in k_count (counts.cu): the strip's neighbourhood is staged in shared memory once with bulk
+// asynchronous copies and serves every query point that fell into the strip -- the points of many different clusters,
+// each with its own window, whose binary searches would otherwise walk the same cells in global memory again and again.
+__global__ void __launch_bounds__(kCtThreads, 2) k_od_count(CellListView cl, int nsx, long long total, int npts,
+                                                            const unsigned* __restrict__ qkey, const int* __restrict__ order,
+                                                            const OdCluster* __restrict__ oc, const double* __restrict__ rra,
+                                                            const double* __restrict__ rdec, int grid_cells,
+                                                            int* __restrict__ counts) {
+  extern __shared__ __align__(128) unsigned char ct_smem[];
+  __shared__ int s_cs[3][kCtW + 3];
+  __shared__ int s_delta[3];
+  __shared__ int s_fits;
+  __shared__ long long s_q[2];
+  __shared__ __align__(8) unsigned long long s_bar;
+  Tile t;
+  t.ra = reinterpret_cast<double*>(ct_smem);
+  t.dec = t.ra + kCtMaxPts;
+  t.cos = t.dec + kCtMaxPts;
+  t.zr = reinterpret_cast<int*>(t.cos + kCtMaxPts);
+  t.cs = s_cs;
+  t.delta = s_delta;
+  const int y = blockIdx.x / nsx, x0 = (blockIdx.x % nsx) * kCtW;
+  const int xe = x0 + kCtW < cl.ncx ? x0 + kCtW : cl.ncx;
+  if (threadIdx.x < 2) {  // the strip's queries: sorted keys in [y * ncx + x0, y * ncx + xe)
+    const unsigned key = (unsigned)(y * cl.ncx + (threadIdx.x == 0 ? x0 : xe));
+    long long lo = 0, hi = total;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (__ldg(qkey + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    s_q[threadIdx.x] = lo;
+  }
+  __syncthreads();
+  const long long q0 = s_q[0], q1 = s_q[1];
+  if (q1 <= q0) return;
+  const bool fits = tile_stage(cl, y, x0, t, &s_bar, &s_fits);
+  const int xb = t.xa + t.ncs - 2;
+  for (long long ti = q0 + threadIdx.x; ti < q1; ti += kCtThreads) {
+    const int q = order[ti];
+    const OdCluster o = oc[q / npts];
+    int cnt = 0;
+    if (o.whi > o.wlo) {
+      const double ra = rra[q], dec = rdec[q], r = o.r;
+      const Box bx = grid_box(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, ra, dec, r);
+      BubbleTest bt;
+      bt.init(ra, dec, cos(__dmul_rn(dec, kDeg2Rad)), r);
+      const double reach = ra_reach(r, dec);
+      const int cx0 = cl.cx_of(ra - reach), cx1 = cl.cx_of(ra + reach);
+      const int cy0 = cl.cy_of(dec - r * 1.000001), cy1 = cl.cy_of(dec + r * 1.000001);
+      if (cx0 >= t.xa && cx1 <= xb && cy0 >= y - 1 && cy1 <= y + 1) {
+        const int r0 = cy0 - (y - 1), r1 = cy1 - (y - 1);
+        cnt = fits ? tile_count(t.ra, t.dec, t.cos, t.zr, t, r0, r1, cx0 - t.xa, cx1 - t.xa, o.wlo, o.whi, bt, bx)
+                   : tile_count(cl.ra, cl.dec, cl.cosdec, cl.zrank, t, r0, r1, cx0 - t.xa, cx1 - t.xa, o.wlo, o.whi, bt, bx);
+      } else {  // a bubble wider than one cell (points beyond the cell list's own declination range): walk the cell list
+        for (int yy = cy0; yy <= cy1; ++yy)
+          for (int xx = cx0; xx <= cx1; ++xx) {
+            const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
+            const int a = lower_bound_zr(cl.zrank, s, e, o.wlo);
+            const int b = lower_bound_zr(cl.zrank, a, e, o.whi);
+            for (int j = a; j < b; ++j) {
+              const double pra = cl.ra[j], pdec = cl.dec[j];
+              if (bx.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
+            }
           }
-        }
-      }
-    int cur = 0;
-    int j = nrun ? run_lo[0][threadIdx.x] : 0, end = nrun ? run_hi[0][threadIdx.x] : 0;
-    while (cur < nrun) {
-      const double pra = cl.ra[j], pdec = cl.dec[j];
-      if (box.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
-      if (++j == end && ++cur < nrun) {
-        j = run_lo[cur][threadIdx.x];
-        end = run_hi[cur][threadIdx.x];
       }
     }
+    counts[q] = cnt;
   }
-  counts[q] = cnt;
 }
 
 // D = (N - mean) / rms over the 300 counts (helper.py:216-221), and the final selection (fof.py:385-390)
@@ -996,9 +1017,8 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   double* D = merged.D.alloc(K);
   FOFB_PROFILED(h, "k_own_count", k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,
                                        c_ra.p, c_dec.p, c_cos.p, c_th05.p, p.grid_cells, N_own));
-  double4* bb = sc.bbox.alloc(K);
-  int* oof = sc.ecount.alloc(K);
-  k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, bb, oof);
+  OdCluster* oc = reinterpret_cast<OdCluster*>(sc.bbox.alloc((size_t)K * 2));  // 48 bytes per cluster
+  k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, oc);
   FOFB_LAUNCH_CHECK(h);
   int* counts = sc.ev_a.alloc((size_t)total);
   FOFB_REQUIRE(total < (1ll << 31), "too many overdensity sample points");
@@ -1017,8 +1037,16 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
     FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, qk, qk2, qv, qv2, (int)total, 0, bits, st));
     count_launch(h, 4);
   }
-  FOFB_PROFILED(h, "k_od_count", k_od_count<<<grid_for(total, 128), 128, 0, st>>>(total, npts, qv2, merged.centre.p, scl, c_wlo.p, c_whi.p, c_th05.p, bb,
-                                                   oof, rra, rdec, p.grid_cells, counts));
+  {
+    static bool attr_set[64] = {};
+    if (!attr_set[h->device & 63]) {
+      FOFB_CUDA(cudaFuncSetAttribute(k_od_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
+      attr_set[h->device & 63] = true;
+    }
+    const int nsx = (scl.ncx + kCtW - 1) / kCtW;
+    FOFB_PROFILED(h, "k_od_count", k_od_count<<<nsx * scl.ncy, kCtThreads, kCtSmemBytes, st>>>(scl, nsx, total, npts, qk2, qv2, oc, rra, rdec,
+                                                                                                p.grid_cells, counts));
+  }
   int* keep = sc.state.alloc(K);
   k_od_finish<<<wblocks, 128, 0, st>>>(K, npts, counts, N_own, merged.off.p, p.overdensity, p.min_count, p.richness, D, keep);
   FOFB_LAUNCH_CHECK(h);
