@@ -13,8 +13,11 @@ numpy's legacy generator + fofb_pipeline_finish.
           the library's stream; algorithmic bytes per unit are the DESIGN.md figures;
   cpu_baseline : the oracle in literal mode (the reference's own O(n^2) control flow), 1 core, on a bounded sample.
 
-N > 1 (torchrun): every rank processes its own independent field of the same size (weak scaling, no data-path
-collective); the time is the max over ranks, the value the sum of galaxies over ranks.
+N > 1 (torchrun): ONE catalogue of --galaxies rows (the N = 1 workload: strong scaling) is split into redshift slabs
+with window-wide halos; boundary centres, the tracker state of every priority round and the cluster lists travel over
+NCCL (fof_b200/distributed.py); the time is the max over ranks.  `--decomposition fields` runs N independent replicas
+instead.  Every line also carries "wide_field": the 100M-galaxy configuration (BASELINE.json configs[3]) on the same
+GPUs, and at N = 1 "cpu_baseline_same_config": GPU and literal CPU path on the same 100k table (configs[0]).
 `--impl reference` times the CPU implementation (oracle port) on the host cores instead.
 """
 import argparse
@@ -150,6 +153,21 @@ def cpu_literal_sample(n_sample, seed, workers=1):
     return time.perf_counter() - t0, len(cleaned)
 
 
+def cpu_literal_table(arr):
+    """The oracle in literal mode, one core, on the given table; returns (seconds, final clusters)."""
+    from oracle import fof_oracle as O
+    p = O.Params()
+    t0 = time.perf_counter()
+    main_arr, cand = O.candidate_center_search(arr, p, mode="literal")
+    g = main_arr[(main_arr[:, 2] >= ZCUT[0]) & (main_arr[:, 2] <= ZCUT[1])]
+    c = cand[(cand[:, 2] >= ZCUT[0]) & (cand[:, 2] <= ZCUT[2])]
+    np.random.seed(1234)
+    clusters = O.FoF(g, c, p, mode="literal")
+    cleaned, _ = O.interloper_removal(clusters, p)
+    O.find_masses(cleaned)
+    return time.perf_counter() - t0, len(cleaned)
+
+
 def _count_rows(arr, rows):
     from oracle import fof_oracle as O
     return O.number_counts_literal(arr, O.Params(), rows=rows)[rows]
@@ -182,62 +200,197 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_slabs(args, rank, world, local_rank, h, p, dist):
-    """One catalogue of world x galaxies rows, split into redshift slabs with window-wide halos; the per-round tracker
-    state, the candidate centres and the cluster lists travel over NCCL (fof_b200/distributed.py)."""
+def _roofline_from_profile(prof, steps, units, peak, peak_kind):
+    """Roofline object for the kernel with the largest share of the event-timed device time."""
+    if not prof:
+        return None
+    tot_ms = sum(v[0] for v in prof.values())
+    share = {k: round(v[0] / tot_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]}
+    name, (kms, cnt) = max(prof.items(), key=lambda kv: kv[1][0])
+    unit_name, bytes_per_unit = ALGO_BYTES.get(name, ("galaxy", 0))
+    launches_per_step = cnt / max(steps, 1)
+    bytes_per_launch = bytes_per_unit * units[unit_name] / max(launches_per_step, 1)
+    avg_ms = kms / cnt
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(name)
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_kind": f"of {peak_kind}", "avg_launch_ms": avg_ms, "launches_per_step": launches_per_step,
+            "algorithmic_bytes_per_launch": bytes_per_launch, "bytes_per_unit": bytes_per_unit, "unit_of_work": unit_name,
+            "share_of_kernel_time": share, "kernel_ms_per_step": {k: round(v[0] / max(steps, 1), 4) for k, v in
+                                                                  sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]}}
+
+
+def _path_bytes(n, m, links, members):
+    """algorithmic bytes of the whole path = 256 n + 36 m + 4 L + 60 M."""
+    return 256.0 * n + 36.0 * m + 4.0 * links + 60.0 * members
+
+
+def slab_inputs(arr_or_dev, world, rank, max_velocity):
+    """This rank's rows of ONE table that every rank holds (numpy on the host, or a torch CUDA tensor sorted by z)."""
     import torch
     from fof_b200 import distributed as D
-    from fof_b200.mock import make_catalog
-    n_total = args.galaxies * world
-    arr = make_catalog(n_total, seed=20260103, as_frame=False)  # every rank builds the same table, keeps its slab
-    edges = D.slab_edges(arr[:, 2], world)
-    rows, own, valid = D.select_local_rows(arr[:, 2], edges, rank, p.max_velocity)
-    local = np.ascontiguousarray(arr[rows])
-    del arr
-    local_dev = torch.from_numpy(local).cuda()  # value: the rank's rows resident in HBM
-    rows_dev = torch.from_numpy(rows).cuda()
-    comm = D.TorchComm()
-    tim = {}
+    if hasattr(arr_or_dev, "data_ptr"):
+        t = arr_or_dev
+        n = t.shape[0]
+        z = t[:, 2]
+        inner = [float(z[(n * k) // world].item()) for k in range(1, world)]  # the table is sorted by redshift
+        edges = np.concatenate([[-np.inf], inner, [np.inf]])
+        own, valid, local = D.plan_slab(edges, rank, max_velocity)
+        rows = torch.nonzero((z >= local[0]) & (z <= local[1])).flatten()
+        return t[rows].contiguous(), rows, own, valid
+    edges = D.slab_edges(arr_or_dev[:, 2], world)
+    rows, own, valid = D.select_local_rows(arr_or_dev[:, 2], edges, rank, max_velocity)
+    return np.ascontiguousarray(arr_or_dev[rows]), rows, own, valid
+
+
+def time_slabs(dist, comm, h, p, local, rows, own, valid, steps, warmup, tim, gather=True):
+    """max-over-ranks seconds per step of find_clusters_slabs on (local, rows); returns (seconds, last result)."""
+    import torch
+    from fof_b200 import distributed as D
 
     def step():
         np.random.seed(4242)  # every rank must hold the same generator state
-        return D.find_clusters_slabs(local_dev, rows_dev, own, valid, comm, h, params=p, zcut=ZCUT, timings=tim)
+        return D.find_clusters_slabs(local, rows, own, valid, comm, h, params=p, zcut=ZCUT, timings=tim, gather=gather)
 
     def barrier():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    res = None
+    for _ in range(warmup):
+        res = step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         res = step()
     barrier()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    return float(t.item()) / max(steps, 1), res
+
+
+def run_slabs(args, rank, world, local_rank, h, p, dist):
+    """N > 1: ONE catalogue of args.galaxies rows (the N = 1 workload: strong scaling) split into redshift slabs with
+    window-wide halos; candidate centres, the per-round tracker state and the cluster lists travel over NCCL
+    (fof_b200/distributed.py).  With --wide-galaxies the 100M wide-field configuration (BASELINE.json configs[3]) is
+    timed afterwards on the same ranks and reported under "wide_field"."""
+    import torch
+    from fof_b200 import distributed as D
+    from fof_b200.mock import make_catalog, make_catalog_torch
+    n_total = args.galaxies
+    arr = make_catalog(n_total, seed=20260103, as_frame=False)  # every rank builds the same table, keeps its slab
+    local, rows, own, valid = slab_inputs(arr, world, rank, p.max_velocity)
+    del arr
+    host = torch.empty(local.shape, dtype=torch.float64, pin_memory=True)
+    host.numpy()[:] = local
+    local_dev = host.cuda()   # value: the rank's rows resident in HBM
+    rows_dev = torch.from_numpy(rows).cuda()
+    comm = D.TorchComm()
+    tim, tim_e = {}, {}
+    clocks = ClockSampler(local_rank)
+    # warm-up outside the clock sampling, then the timed region
+    time_slabs(dist, comm, h, p, local_dev, rows_dev, own, valid, 0, args.warmup, tim)
+    clocks.start()
+    h.profile(2)
+    dt, res = time_slabs(dist, comm, h, p, local_dev, rows_dev, own, valid, args.steps, 0, tim)
+    h.profile(0)
+    prof = h.profile_read()
     clock_info = clocks.stop()
+    launches = int(tim.get("launches", 0))
+    # end to end: the rank's rows start in pinned HOST memory, the global catalogue ends in host arrays on every rank
+    dt_e, res_e = time_slabs(dist, comm, h, p, host.numpy(), rows_dev, own, valid, args.steps, 1, tim_e)
+    h2d = torch.tensor([float(host.numpy().nbytes)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(h2d)
+    d2h = int(sum(np.asarray(x).nbytes for x in res_e[:6]))
+    st = h.pipeline_stats()
+    red = torch.tensor([float(st["candidate_centres"]), float(st["stage1_members"]), float(tim.get("local_rows", 0))],
+                       dtype=torch.float64, device="cuda")
+    dist.all_reduce(red)
+    wide = None
+    if args.wide_galaxies > 0:
+        del local_dev, host
+        torch.cuda.empty_cache()
+        wide = run_wide(args, rank, world, h, p, dist, comm)
     if rank == 0:
-        value = n_total / (dt / max(args.steps, 1))
+        peak, peak_kind = _peaks()
+        members_final = int(res[0][-1])
+        units = {"galaxy": tim.get("local_rows", 0), "candidate_centre": st["candidate_centres"], "stage1_member": st["stage1_members"],
+                 "overdensity_point": tim.get("merged_local", 0) * p.n_random, "final_member": members_final / world}
+        roofline = _roofline_from_profile(prof, args.steps, units, peak, peak_kind)
+        if roofline:
+            roofline["scope"] = "rank 0's kernels on its slab (local rows incl. halos)"
+        path_gbs = _path_bytes(n_total, red[0].item(), red[1].item(), members_final) / dt / 1e9
+        value = n_total / dt
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"ONE {n_total}-galaxy COSMOS-like mock ({args.galaxies} per GPU), whole path",
+                "config": {"workload": f"ONE {n_total}-galaxy COSMOS-like mock (the N=1 workload) in {world} redshift slabs, whole path: "
+                                       "candidate search, FoF, interloper removal, virial masses",
                            "params": f"params.py defaults, linking_length_factor={args.linking_length_factor}",
-                           "parallelism": f"{world} redshift slabs with window-wide halos; NCCL all-gather of centres and cluster lists, "
-                                          "all-reduce of the tracker state every priority round",
-                           "clusters_final": int(len(res[0]) - 1), "members_final": int(res[0][-1]), **{k: (int(v) if float(v).is_integer() else v) for k, v in tim.items()}},
+                           "parallelism": f"{world} redshift slabs with window-wide halos; NCCL all-gather of boundary centres, cluster "
+                                          "lists and final catalogue, one all-reduce of the tracker state per priority round",
+                           "l2": "per-rank inputs larger than the 126 MB L2; no explicit flush",
+                           "rows_held_by_all_ranks": int(red[2].item()), "halo_overhead": round(red[2].item() / n_total - 1.0, 4),
+                           "clusters_final": int(len(res[0]) - 1), "members_final": members_final,
+                           **{k: (int(v) if float(v).is_integer() else v) for k, v in tim.items()}},
                 "clocks": clock_info,
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(res[1].nbytes),
-                        "note": "rows resident in HBM; the assembled global catalogue is returned as host arrays on every rank"},
-                "gpu_launches": int(h.last_timing()[1]) * args.steps, "roofline": None, "cpu_baseline": None}
+                "e2e": {"value": n_total / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": d2h * world,
+                        "ms_per_step": 1e3 * dt_e,
+                        "note": "each rank's rows start in pinned host memory; the assembled global catalogue is read back to host "
+                                "arrays on every rank"},
+                "gpu_launches": launches * args.steps * world, "roofline": roofline,
+                "path_hbm": {"algorithmic_GBps": path_gbs, "frac_of_peak_per_gpu": path_gbs / (peak * world),
+                             "note": "SURVEY 8(d): (256 n + 36 m + 4 L + 60 M) bytes / step time, against N x the measured copy peak"},
+                "cpu_baseline": None, "wide_field": wide}
         print(json.dumps(line), flush=True)
+    dist.barrier()
     dist.destroy_process_group()
+
+
+def run_wide(args, rank, world, h, p, dist, comm):
+    """BASELINE.json configs[3]: the 100M-galaxy wide-field mock (RA 100-150, Dec -20..20) on `world` GPUs.  The table is
+    drawn on the GPU by every rank from one seed (identical everywhere), each rank keeps its slab."""
+    import torch
+    from fof_b200.mock import make_catalog_torch
+    n = args.wide_galaxies
+    steps, warmup = max(1, min(args.steps, 3)), 2
+    table = make_catalog_torch(n, seed=20260104, kind="wide", device=f"cuda:{torch.cuda.current_device()}")
+    tim = {}
+    if world > 1:
+        local, rows, own, valid = slab_inputs(table, world, rank, p.max_velocity)
+        del table
+        torch.cuda.empty_cache()
+        dt, res = time_slabs(dist, comm, h, p, local, rows, own, valid, steps, warmup, tim)
+        K, M = int(len(res[0]) - 1), int(res[0][-1])
+    else:
+        def step():
+            np.random.seed(4242)
+            return h.pipeline_run_np_random(table, p, *ZCUT)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            K, M = step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+    st = h.pipeline_stats()
+    red = torch.tensor([float(st["candidate_centres"]), float(st["stage1_members"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red)
+    peak, _ = _peaks()
+    gbs = _path_bytes(n, red[0].item(), red[1].item(), M) / dt / 1e9
+    return {"workload": f"ONE {n}-galaxy wide-field mock (RA 100-150, Dec -20..20, 0.5<z<2, 20% in Plummer clusters; drawn on the "
+                        f"GPU with torch, seed 20260104), whole path, {world} GPU(s)" + (", redshift slabs over NCCL" if world > 1 else ""),
+            "value": n / dt, "unit": UNIT, "ms_per_step": 1e3 * dt, "steps": steps, "warmup": warmup, "resident": True,
+            "clusters_final": K, "members_final": M, "candidate_centres": int(red[0].item()), "stage1_members": int(red[1].item()),
+            "path_hbm_GBps": gbs, "path_hbm_frac_of_peak_per_gpu": gbs / (peak * world),
+            **{k: (int(v) if float(v).is_integer() else v) for k, v in tim.items()}}
 
 
 def main():
@@ -250,8 +403,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--linking-length-factor", type=float, default=0.2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--decomposition", default="fields", choices=["fields", "slabs"],
-                    help="N > 1: independent fields per GPU (default) or ONE N x galaxies catalogue in redshift slabs with halos")
+    ap.add_argument("--same-config-galaxies", type=int, default=100_000,
+                    help="N = 1: size of the table on which the GPU path (end to end) and the literal CPU path are both timed")
+    ap.add_argument("--decomposition", default="slabs", choices=["fields", "slabs"],
+                    help="N > 1: ONE catalogue of --galaxies rows in redshift slabs with halos (default: the metric's strong-scaling "
+                         "line) or an independent field of --galaxies rows per GPU (replicas, no data-path collective)")
+    ap.add_argument("--wide-galaxies", type=int, default=100_000_000,
+                    help="also time the wide-field configuration (BASELINE.json configs[3]) of this many rows; 0 skips it")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,11 +440,14 @@ def main():
     if args.decomposition == "slabs" and world > 1:
         return run_slabs(args, rank, world, local_rank, h, p, dist)
     arr = make_catalog(n, seed=20260103 + rank, as_frame=False)
-    host = torch.empty((n, 7), dtype=torch.float64, pin_memory=True)
-    host.numpy()[:] = arr
-    dev = host.cuda(non_blocking=False)
+    # host table laid out as the reference's `df.values` is: a consolidated pandas float64 block, every column contiguous
+    # (shape (n, 7), strides (8, 8 n)).  The library uploads the three columns stage 0 reads first and streams the other
+    # four behind the stage-0 kernels.
+    host = torch.empty((7, n), dtype=torch.float64, pin_memory=True)
+    host.numpy()[:] = arr.T
+    dev = torch.from_numpy(arr).cuda()
     del arr
-    host_np = host.numpy()
+    host_np = host.numpy().T
 
     def barrier():
         torch.cuda.synchronize()
@@ -347,30 +508,8 @@ def main():
     peak, peak_kind = _peaks()
     units = {"galaxy": n, "candidate_centre": pstats["candidate_centres"], "stage1_member": pstats["stage1_members"],
              "overdensity_point": stats["K"] * p.n_random, "final_member": stats["total"]}
-    roofline = None
-    share = {}
-    if prof:
-        tot_ms = sum(v[0] for v in prof.values())
-        share = {k: round(v[0] / tot_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]}
-        top = max(prof.items(), key=lambda kv: kv[1][0])
-        name, (kms, cnt) = top
-        unit_name, bytes_per_unit = ALGO_BYTES.get(name, ("galaxy", 0))
-        launches_per_step = cnt / max(args.steps, 1)
-        bytes_per_launch = bytes_per_unit * units[unit_name] / max(launches_per_step, 1)
-        avg_ms = kms / cnt
-        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(name)
-        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
-                    "avg_launch_ms": avg_ms, "launches_per_step": launches_per_step,
-                    "algorithmic_bytes_per_launch": bytes_per_launch, "bytes_per_unit": bytes_per_unit, "unit_of_work": unit_name,
-                    "share_of_kernel_time": share}
-
-    # the one HBM-shaped hot kernel of the path (the N(0.5) link test) is reported beside the dominant kernel
-    stream = None
+    roofline = _roofline_from_profile(prof, args.steps, units, peak, peak_kind)
+    # the HBM-shaped hot kernel of the path (the N(0.5) link test) is reported beside the dominant kernel
     if prof and "k_count" in prof and roofline is not None:
         kms, cnt = prof["k_count"]
         b = ALGO_BYTES["k_count"][1] * n / max(cnt / max(args.steps, 1), 1)
@@ -378,10 +517,43 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             tr = json.load(open(tpath)).get("k_count")
-        stream = {"kernel": "k_count", "bound": "hbm", "achieved": b / (kms / cnt * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                  "frac": b / (kms / cnt * 1e-3) / 1e9 / peak, "traffic": tr, "avg_launch_ms": kms / cnt,
-                  "algorithmic_bytes_per_launch": b}
-        roofline["link_test_kernel"] = stream
+        roofline["link_test_kernel"] = {"kernel": "k_count", "bound": "hbm", "achieved": b / (kms / cnt * 1e-3) / 1e9, "peak": peak,
+                                        "unit": "GB/s", "frac": b / (kms / cnt * 1e-3) / 1e9 / peak, "traffic": tr,
+                                        "avg_launch_ms": kms / cnt, "algorithmic_bytes_per_launch": b}
+    path_gbs = _path_bytes(n, pstats["candidate_centres"], pstats["stage1_members"], stats["total"]) / (ms_per_step * 1e-3) / 1e9
+    path_hbm = {"algorithmic_GBps": path_gbs, "frac_of_peak_per_gpu": path_gbs / peak,
+                "note": "SURVEY 8(d): (256 n + 36 m + 4 L + 60 M) bytes / step time, against the measured copy peak"}
+
+    # BASELINE.json configs[0] (100k galaxies) on both sides: the GPU path end to end from host rows, and -- below -- the
+    # literal CPU path on the very same table, so that one ratio in the record compares like with like
+    same = None
+    if rank == 0 and world == 1 and args.same_config_galaxies > 0 and not args.no_cpu_baseline:
+        small = make_catalog(args.same_config_galaxies, seed=20260101, as_frame=False)
+        for _ in range(3):
+            np.random.seed(1234)
+            Kf_s, tot_s = h.pipeline_run_np_random(small, p, *ZCUT)
+            h.pipeline_fetch(Kf_s, tot_s)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            np.random.seed(1234)
+            Kf_s, tot_s = h.pipeline_run_np_random(small, p, *ZCUT)
+            h.pipeline_fetch(Kf_s, tot_s)
+        torch.cuda.synchronize()
+        t_gpu = (time.perf_counter() - t0) / 5
+        t_cpu, k_cpu = cpu_literal_table(small)
+        same = {"workload": f"BASELINE.json configs[0]: {args.same_config_galaxies}-galaxy COSMOS-like mock (seed 20260101), default "
+                            "params.py, whole path, host rows in / host catalogue out on both sides",
+                "gpu_e2e": {"value": args.same_config_galaxies / t_gpu, "unit": UNIT, "ms": 1e3 * t_gpu, "clusters": int(Kf_s)},
+                "cpu": {"value": args.same_config_galaxies / t_cpu, "unit": UNIT, "seconds": t_cpu, "cores": 1, "kind": "port",
+                        "clusters": int(k_cpu), "what": "oracle literal mode = the reference's control flow, one Python process"},
+                "ratio": t_cpu / t_gpu}
+
+    wide = None
+    if world == 1 and args.wide_galaxies > 0:
+        del dev, host, host_np
+        torch.cuda.empty_cache()
+        wide = run_wide(args, rank, world, h, p, dist, None)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -395,16 +567,19 @@ def main():
         dist.barrier()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+                "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": f"{n}-galaxy COSMOS-like mock per GPU (0.5<z<2, 80% uniform + 20% Plummer clusters, "
                                        "50k gal/deg^2), whole path: candidate search, FoF, interloper removal, virial masses",
                            "params": f"params.py defaults, linking_length_factor={args.linking_length_factor}",
                            "parallelism": "one process per GPU, independent fields (no data-path collective)" if world > 1 else "single GPU",
                            "l2": "inputs (560 MB per step) larger than the 126 MB L2; no explicit flush",
+                           "e2e_input": "pinned host table, column-major like a pandas block (df.values); value: row-major device table",
                            "clusters_final": stats["Kf"], "members_final": stats["total"], **pstats},
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "device_ms_per_step": stats["device_ms"],
-                "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "roofline": roofline, "path_hbm": path_hbm, "cpu_baseline": cpu_baseline, "cpu_baseline_same_config": same,
+                "wide_field": wide}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -87,6 +87,10 @@ def load():
         "fofb_dist_round_evaluate": (C.c_int, [vp]),
         "fofb_dist_state": (C.c_int, [vp, vp, vp, i32]),
         "fofb_dist_round_advance": (C.c_int, [vp, P(i64)]),
+        "fofb_set_stream": (C.c_int, [vp, vp]),
+        "fofb_dist_state_pack": (C.c_int, [vp, i64, vp, vp, vp, i64]),
+        "fofb_dist_state_unpack": (C.c_int, [vp, i64, vp, vp, vp]),
+        "fofb_dist_round_advance2": (C.c_int, [vp, vp, i64, P(i64), P(i32)]),
         "fofb_dist_finalize": (C.c_int, [vp, P(i64), P(i64)]),
         "fofb_dist_local_clusters": (C.c_int, [vp, vp, vp, vp]),
         "fofb_dist_overlap": (C.c_int, [vp, i64, vp, vp, vp, vp]),
@@ -176,6 +180,11 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def use_stream(self, cuda_stream):
+        """Run this handle's kernels on the given CUDA stream (an integer handle such as
+        torch.cuda.current_stream().cuda_stream; None: the handle's own stream)."""
+        self.check(self.lib.fofb_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     def profile(self, on):
         self.check(self.lib.fofb_profile_enable(self.h, int(on)))

@@ -18,6 +18,10 @@ void fof_overlap_external_rows(fofb_handle* h, FofState& S, int K, const double*
                                const double* ids, int* keep_out);
 void fof_set_merged(fofb_handle* h, FofState& S, const int* keep_local);
 void mt19937_words(fofb_handle* h, unsigned* key_host, int* pos_host, long long n_words, unsigned* out, int out_mem);
+void dist_state_pack(fofb_handle* h, FofState& S, long long n_shared, const long long* lpos, const long long* bpos, unsigned char* buf,
+                     long long n_buf);
+void dist_state_unpack(fofb_handle* h, FofState& S, long long n_shared, const long long* lpos, const long long* bpos,
+                       const unsigned char* buf);
 }
 
 namespace fofb {
@@ -61,6 +65,10 @@ Cosmo device_cosmo(fofb_handle* h, const fofb_params& p) {
 View to_device(fofb_handle* h, const fofb_matrix& m, DBuf<double>& staging) {
   FOFB_REQUIRE(m.data != nullptr && m.rows >= 0 && m.cols > 0, "matrix: null data or bad shape");
   FOFB_REQUIRE(m.row_stride >= 0 && m.col_stride >= 0, "matrix: negative strides are not supported");
+  if (h->upload_pending) {  // a split upload that an error left unfinished: its side-stream copies target the staging buffers
+    FOFB_CUDA(cudaStreamWaitEvent(h->stream, h->upload_done, 0));
+    h->upload_pending = false;
+  }
   View v;
   v.rows = m.rows; v.cols = m.cols; v.rs = m.row_stride; v.cs = m.col_stride;
   if (m.mem == 1) {
@@ -72,6 +80,34 @@ View to_device(fofb_handle* h, const fofb_matrix& m, DBuf<double>& staging) {
   double* d = staging.alloc(extent ? extent : 1);
   if (extent) FOFB_CUDA(cudaMemcpyAsync(d, m.data, extent * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   v.data = d;
+  return v;
+}
+
+// Column-major host tables (a pandas block: every column contiguous) for the whole-job path: the three columns stage 0
+// reads go first on the compute stream; the others follow on a side stream while stage 0 runs.  The caller makes the
+// compute stream wait for h->upload_done before anything touches columns >= first_cols (Pipeline::stage0_and_inputs).
+View to_device_split(fofb_handle* h, const fofb_matrix& m, DBuf<double>& staging, int first_cols) {
+  const bool column_major = m.mem == 0 && m.row_stride == 1 && m.col_stride >= m.rows && m.cols > first_cols && m.rows > 0;
+  h->upload_pending = false;
+  if (!column_major) return to_device(h, m, staging);
+  FOFB_REQUIRE(m.data != nullptr, "matrix: null data");
+  if (!h->copy_stream) {
+    FOFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    FOFB_CUDA(cudaEventCreateWithFlags(&h->upload_done, cudaEventDisableTiming));
+    FOFB_CUDA(cudaEventCreateWithFlags(&h->upload_go, cudaEventDisableTiming));
+  }
+  const size_t n = (size_t)m.rows;
+  double* d = staging.alloc(n * m.cols);
+  // the staging buffer may still be read by work enqueued earlier on the compute stream
+  FOFB_CUDA(cudaEventRecord(h->upload_go, h->stream));
+  FOFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->upload_go, 0));
+  for (int c = 0; c < m.cols; ++c)
+    FOFB_CUDA(cudaMemcpyAsync(d + (size_t)c * n, m.data + (size_t)c * m.col_stride, n * sizeof(double), cudaMemcpyHostToDevice,
+                              c < first_cols ? h->stream : h->copy_stream));
+  FOFB_CUDA(cudaEventRecord(h->upload_done, h->copy_stream));
+  h->upload_pending = true;
+  View v;
+  v.data = d; v.rows = m.rows; v.cols = m.cols; v.rs = 1; v.cs = (int64_t)n;
   return v;
 }
 
@@ -163,7 +199,8 @@ int fofb_create(int device, fofb_handle** out) {
   cudaDeviceProp prop;
   FOFB_CUDA(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
-  FOFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  FOFB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
   FOFB_CUDA(cudaEventCreate(&h->ev0));
   FOFB_CUDA(cudaEventCreate(&h->ev1));
   *out = h;
@@ -195,7 +232,10 @@ void fofb_destroy(fofb_handle* h) {
   h->matcher = nullptr;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->upload_done) cudaEventDestroy(h->upload_done);
+  if (h->upload_go) cudaEventDestroy(h->upload_go);
   delete h;
 }
 
@@ -206,6 +246,16 @@ int fofb_synchronize(fofb_handle* h) {
   FOFB_TRY(h)
   FOFB_CUDA(cudaSetDevice(h->device));
   FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_set_stream(fofb_handle* h, void* cuda_stream) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  FOFB_CUDA(cudaSetDevice(h->device));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
   return FOFB_OK;
   FOFB_CATCH(h)
 }
@@ -226,6 +276,9 @@ int fofb_profile_enable(fofb_handle* h, int32_t on) {
 
 int fofb_profile_read(fofb_handle* h, char* buf, int64_t capacity) {
   if (!h || !buf || capacity <= 0) return FOFB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->prof.resolve();  // events of entry points that do not end with a timer (the distributed steps)
   std::string out;
   for (auto& kv : h->prof.acc) out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
   if ((int64_t)out.size() + 1 > capacity) return FOFB_ERR_INVALID;
@@ -580,7 +633,7 @@ int fofb_pipeline_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* g
   FOFB_CUDA(cudaSetDevice(h->device));
   if (!h->pipe) h->pipe = new Pipeline();
   Timed timer(h);
-  const View raw = to_device(h, *galaxies, h->upload);
+  const View raw = to_device_split(h, *galaxies, h->upload, 3);
   h->pipe->begin(h, *p, raw, zmin, zmax_gal, zmax_cen, mt_key, *mt_pos);
   h->pipe->finish(h, nullptr, 0, mt_key, mt_pos);
   timer.stop();
@@ -734,7 +787,6 @@ int fofb_dist_round_evaluate(fofb_handle* h) {
   Pipeline& P = dist_pipe(h);
   FOFB_CUDA(cudaSetDevice(h->device));
   P.fof.round_evaluate(h);
-  FOFB_CUDA(cudaStreamSynchronize(h->stream));
   return FOFB_OK;
   FOFB_CATCH(h)
 }
@@ -767,6 +819,47 @@ int fofb_dist_round_advance(fofb_handle* h, int64_t* n_active) {
   Pipeline& P = dist_pipe(h);
   FOFB_CUDA(cudaSetDevice(h->device));
   P.fof.round_advance(h);
+  if (n_active) *n_active = P.fof.na;
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_state_pack(fofb_handle* h, int64_t n_shared, const int64_t* local_pos, const int64_t* shared_pos, uint8_t* buf,
+                         int64_t n_buf) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(buf && n_buf >= 1 && n_shared >= 0 && (n_shared == 0 || (local_pos && shared_pos)), "fofb_dist_state_pack: bad argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  fofb::dist_state_pack(h, P.fof, n_shared, reinterpret_cast<const long long*>(local_pos), reinterpret_cast<const long long*>(shared_pos),
+                        buf, n_buf);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_state_unpack(fofb_handle* h, int64_t n_shared, const int64_t* local_pos, const int64_t* shared_pos,
+                           const uint8_t* buf) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(buf && n_shared >= 0 && (n_shared == 0 || (local_pos && shared_pos)), "fofb_dist_state_unpack: bad argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  fofb::dist_state_unpack(h, P.fof, n_shared, reinterpret_cast<const long long*>(local_pos), reinterpret_cast<const long long*>(shared_pos), buf);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_round_advance2(fofb_handle* h, const uint8_t* buf, int64_t n_buf, int64_t* n_active, int32_t* any_active) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(buf && n_buf >= 1 && any_active, "fofb_dist_round_advance2: bad argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  uint8_t* flag = reinterpret_cast<uint8_t*>(h->pinned_i64.alloc(1));
+  FOFB_CUDA(cudaMemcpyAsync(flag, buf + (n_buf - 1), 1, cudaMemcpyDeviceToHost, h->stream));
+  P.fof.round_advance(h);  // synchronises the stream when there is anything to advance
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  *any_active = *flag ? 1 : 0;
   if (n_active) *n_active = P.fof.na;
   return FOFB_OK;
   FOFB_CATCH(h)

@@ -127,7 +127,11 @@ struct fofb_handle {
   int device = 0;
   fofb::KernelProfile prof;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream every call runs on: own_stream, or one borrowed through fofb_set_stream
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // second half of a split upload (to_device_split)
+  cudaEvent_t upload_done = nullptr, upload_go = nullptr;
+  bool upload_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string last_error;
   double last_ms = 0.0;

@@ -1425,6 +1425,43 @@ void FofState::round_advance(fofb_handle* h) {
   act_in_a = !act_in_a;
 }
 
+// ---- tracker state for the one-collective-per-round exchange (0 alive and undecided, 1 switched off, 2 evaluated) ----
+__global__ void k_state_pack(long long n, const long long* lpos, const long long* bpos, const unsigned char* alive,
+                             const unsigned char* decided, unsigned char* buf) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long i = lpos[t];
+  buf[bpos[t]] = decided[i] ? 2 : (alive[i] ? 0 : 1);
+}
+
+__global__ void k_state_unpack(long long n, const long long* lpos, const long long* bpos, const unsigned char* buf,
+                               unsigned char* alive, unsigned char* decided) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long i = lpos[t];
+  const unsigned char s = buf[bpos[t]];
+  if (s == 2) decided[i] = 1;
+  else if (s == 1) alive[i] = 0;
+}
+
+void dist_state_pack(fofb_handle* h, FofState& S, long long n_shared, const long long* lpos, const long long* bpos, unsigned char* buf,
+                     long long n_buf) {
+  cudaStream_t st = h->stream;
+  FOFB_CUDA(cudaMemsetAsync(buf, 0, (size_t)n_buf, st));
+  if (S.na > 0) FOFB_CUDA(cudaMemsetAsync(buf + (n_buf - 1), 1, 1, st));
+  if (n_shared > 0) {
+    k_state_pack<<<grid_for(n_shared, 256), 256, 0, st>>>(n_shared, lpos, bpos, S.alive.p, S.decided.p, buf);
+    FOFB_LAUNCH_CHECK(h);
+  }
+}
+
+void dist_state_unpack(fofb_handle* h, FofState& S, long long n_shared, const long long* lpos, const long long* bpos,
+                       const unsigned char* buf) {
+  if (n_shared <= 0) return;
+  k_state_unpack<<<grid_for(n_shared, 256), 256, 0, h->stream>>>(n_shared, lpos, bpos, buf, S.alive.p, S.decided.p);
+  FOFB_LAUNCH_CHECK(h);
+}
+
 void FofState::finalize(fofb_handle* h) {
   cudaStream_t st = h->stream;
   const int B = 256;

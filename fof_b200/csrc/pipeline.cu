@@ -233,6 +233,10 @@ void Pipeline::stage0_and_inputs(fofb_handle* h, const fofb_params& p, const Vie
   n_g = d2h_scalar(h, dcount);
   FOFB_REQUIRE(n_g > 0, "no galaxy passes the redshift cut");
   const int ocols = 8;
+  if (h->upload_pending) {  // columns 3.. of a split upload arrive on the side stream; nothing before here read them
+    FOFB_CUDA(cudaStreamWaitEvent(st, h->upload_done, 0));
+    h->upload_pending = false;
+  }
   double* G = g_rows.alloc((size_t)n_g * ocols);
   FOFB_PROFILED(h, "k_build_rows", k_build_rows<<<grid_for((int64_t)n_g * ocols, B), B, 0, st>>>(n_g, gsrc, raw, s0.N_row.p, G, ocols));
   // candidate centres in priority order

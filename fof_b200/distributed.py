@@ -90,6 +90,9 @@ class SoloComm:
     def allreduce_bytes(self, alive, decided):
         pass
 
+    def allreduce_max_bytes(self, buf):
+        pass
+
     def barrier(self):
         pass
 
@@ -112,17 +115,27 @@ class ThreadComm:
         return [cls(sh, r) for r in range(world)]
 
     def _exchange(self, x):
+        """Every rank's x, as private copies.  CUDA tensors are produced and consumed on per-rank streams: the producer
+        finishes its work before publishing, the consumers finish copying before anybody moves on."""
+        cuda = hasattr(x, "is_cuda") and x.is_cuda
+        if cuda:
+            import torch
+            torch.cuda.current_stream(x.device).synchronize()
         self.s.slots[self.rank] = x
         self.s.barrier.wait()
-        out = list(self.s.slots)
+        if cuda:
+            out = [a.clone() for a in self.s.slots]
+            torch.cuda.current_stream(x.device).synchronize()
+        else:
+            out = [np.array(a, copy=True) if isinstance(a, np.ndarray) else a for a in self.s.slots]
         self.s.barrier.wait()
         return out
 
     def allgatherv(self, x):
-        return [np.array(a, copy=True) for a in self._exchange(x)]
+        return self._exchange(np.asarray(x))
 
     def allgatherv_t(self, t):
-        return [a.clone() for a in self._exchange(t)]
+        return self._exchange(t)
 
     def allreduce(self, x, op):
         vals = self._exchange(np.asarray(x))
@@ -131,11 +144,16 @@ class ThreadComm:
     def allreduce_bytes(self, alive, decided):
         """alive := elementwise MIN, decided := elementwise MAX over ranks (torch CUDA uint8 tensors)."""
         import torch
-        a = self._exchange(alive.clone())
-        d = self._exchange(decided.clone())
+        a = self._exchange(alive)
+        d = self._exchange(decided)
         alive.copy_(torch.stack(a).min(dim=0).values)
         decided.copy_(torch.stack(d).max(dim=0).values)
-        self.s.barrier.wait()
+
+    def allreduce_max_bytes(self, buf):
+        """buf := elementwise MAX over ranks (torch CUDA uint8 tensor), in place."""
+        import torch
+        parts = self._exchange(buf)
+        buf.copy_(torch.stack(parts).max(dim=0).values)
 
     def barrier(self):
         self.s.barrier.wait()
@@ -195,6 +213,9 @@ class TorchComm:
         self.dist.all_reduce(alive, op=self.dist.ReduceOp.MIN)
         self.dist.all_reduce(decided, op=self.dist.ReduceOp.MAX)
 
+    def allreduce_max_bytes(self, buf):
+        self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX)
+
     def barrier(self):
         self.dist.barrier()
 
@@ -220,7 +241,7 @@ def select_local_rows(z, edges, rank, max_velocity):
 
 
 def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params=None, zcut=None, timings=None,
-                        mt_state=None):
+                        mt_state=None, gather=True):
     """Run the whole path on this rank's rows and assemble the global catalogue.
 
     local_rows : (n_local, 7) float64 (numpy, or a torch CUDA tensor already on the handle's device), the rows of
@@ -228,24 +249,49 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     global_row : their indices in the global table;  own / valid: intervals from ``plan_slab``;
     mt_state   : (key[624], pos) of numpy's legacy MT19937 generator to draw the overdensity points from; None uses
                  (and advances) this process's ``np.random`` -- every process must then hold the same state.
+    gather     : True: every rank returns the GLOBAL catalogue (one all-gather of the final lists); False: every rank
+                 returns only the clusters it owns (same layout, global priority order within the rank).
     Every rank works only with the candidate centres of its own redshift neighbourhood (its own plus the neighbours'
-    centres inside its valid interval); centres are identified across ranks by their priority key.
-    Returns (offsets, member_global_rows, centre_global_row, N, D, props) of the GLOBAL final catalogue, identical
-    on every rank, in the order the single-GPU run produces (plus the advanced (key, pos) when mt_state is given).
+    centres inside its valid interval); centres are identified across ranks by their priority key.  The library's
+    kernels, the torch glue and the NCCL collectives are all enqueued on ONE stream per rank, so the only host
+    synchronisations are the scalar read-backs that size buffers.
+    Returns (offsets, member_global_rows, centre_global_row, N, D, props), in the order the single-GPU run produces
+    (plus the advanced (key, pos) when mt_state is given).
     """
-    import time
     import torch
     h = handle
-    L = h.lib
     dev = torch.device("cuda", h.device)
+    stream = h.__dict__.get("_slab_stream")
+    if stream is None:
+        stream = h.__dict__["_slab_stream"] = torch.cuda.Stream(dev)
+    stream.wait_stream(torch.cuda.current_stream(dev))   # inputs prepared by the caller on its own stream
+    h.use_stream(stream.cuda_stream)
+    try:
+        with torch.cuda.stream(stream):
+            return _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, zcut, timings, mt_state, gather)
+    finally:
+        stream.synchronize()
+        h.use_stream(None)
+
+
+def _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, zcut, timings, mt_state, gather):
+    import time
+    import torch
+    L = h.lib
     _t = [time.perf_counter()]
     phases = {}
+    launches = [0]
 
     def lap(name):
+        if timings is None:
+            return
         torch.cuda.current_stream(dev).synchronize()
         now = time.perf_counter()
         phases[name] = phases.get(name, 0.0) + 1e3 * (now - _t[0])
         _t[0] = now
+
+    def count():
+        launches[0] += h.last_timing()[1]
 
     def cat0(parts):
         return torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
@@ -264,6 +310,7 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     v2 = (C.c_double * 2)(*valid)
     o2 = (C.c_double * 2)(*own)
     h.check(L.fofb_dist_begin(h.h, C.byref(p), C.byref(m), z3, v2, o2, C.byref(ng), C.byref(mc)))
+    count()
     n_g, m_loc = ng.value, mc.value
     # the MT19937 stream of the overdensity points is generated on a side stream while the rounds run
     if mt_state is None:
@@ -309,43 +356,33 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     loc_rows = loc_rows[order].contiguous()
     loc_grow, loc_owned, loc_bidx, key = loc_grow[order], loc_owned[order].contiguous(), loc_bidx[order], key[order]
     m_l = len(loc_grow)
-    lpos = torch.nonzero(loc_bidx >= 0).flatten()
-    bpos = loc_bidx[lpos]
+    lpos = torch.nonzero(loc_bidx >= 0).flatten().contiguous()
+    bpos = loc_bidx[lpos].contiguous()
+    n_shared = len(lpos)
     lap("exchange_centres")
 
     bbox = np.empty(4)
-    torch.cuda.current_stream(dev).synchronize()
     h.check(L.fofb_dist_prepare(h.h, loc_rows.data_ptr(), m_l, loc_owned.data_ptr(), bbox.ctypes.data))
-    lo = comm.allreduce(np.array([bbox[0], bbox[2]]), "min")
-    hi = comm.allreduce(np.array([bbox[1], bbox[3]]), "max")
-    gbbox = np.array([lo[0], hi[0], lo[1], hi[1]])
+    ext = comm.allreduce(np.array([-bbox[0], bbox[1], -bbox[2], bbox[3]]), "max")   # one call: min as -max
+    gbbox = np.array([-ext[0], ext[1], -ext[2], ext[3]])
     lap("prepare")
 
-    # ---- priority rounds; the state of the shared (boundary) centres is merged after each ---------------------
-    alive = torch.empty(max(m_l, 1), dtype=torch.uint8, device=dev)
-    decided = torch.empty(max(m_l, 1), dtype=torch.uint8, device=dev)
+    # ---- priority rounds; ONE collective per round: the states of the shared (boundary) centres, merged by MAX
+    #      (0 alive and undecided < 1 switched off < 2 evaluated), plus a byte telling whether anybody still had work
+    n_buf = nB + 1
+    buf = torch.empty(n_buf, dtype=torch.uint8, device=dev)
     rounds = 0
     while True:
-        na = C.c_int64(0)
         if m_l > 0:
             h.check(L.fofb_dist_round_evaluate(h.h))
-            h.check(L.fofb_dist_state(h.h, alive.data_ptr(), decided.data_ptr(), 0))
-        ab = torch.ones(max(nB, 1), dtype=torch.uint8, device=dev)
-        db = torch.zeros(max(nB, 1), dtype=torch.uint8, device=dev)
-        if m_l > 0 and len(lpos):
-            ab[bpos] = alive[lpos]
-            db[bpos] = decided[lpos]
-        comm.allreduce_bytes(ab, db)
-        if m_l > 0:
-            if len(lpos):
-                alive[lpos] = ab[bpos]
-                decided[lpos] = db[bpos]
-            torch.cuda.current_stream(dev).synchronize()
-            h.check(L.fofb_dist_state(h.h, alive.data_ptr(), decided.data_ptr(), 1))
-            h.check(L.fofb_dist_round_advance(h.h, C.byref(na)))
-        rounds += 1
-        if int(comm.allreduce(np.array([float(na.value)]), "sum")[0]) == 0:
+        h.check(L.fofb_dist_state_pack(h.h, n_shared, lpos.data_ptr(), bpos.data_ptr(), buf.data_ptr(), n_buf))
+        comm.allreduce_max_bytes(buf)
+        h.check(L.fofb_dist_state_unpack(h.h, n_shared, lpos.data_ptr(), bpos.data_ptr(), buf.data_ptr()))
+        na, any_active = C.c_int64(0), C.c_int32(0)
+        h.check(L.fofb_dist_round_advance2(h.h, buf.data_ptr(), n_buf, C.byref(na), C.byref(any_active)))
+        if not any_active.value:
             break
+        rounds += 1
     kc, kt = C.c_int64(), C.c_int64()
     h.check(L.fofb_dist_finalize(h.h, C.byref(kc), C.byref(kt)))
     K_loc, tot_loc = kc.value, kt.value
@@ -375,12 +412,11 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
         sizes_s = sizes_all[corder]
         off_s = torch.zeros(K_glob + 1, dtype=i64, device=dev)
         off_s[1:] = torch.cumsum(sizes_s, 0)
-        total_ids = int(off_s[-1].item())
-        seg = torch.repeat_interleave(torch.arange(K_glob, device=dev), sizes_s)
-        gather = starts[corder][seg] + (torch.arange(total_ids, device=dev) - off_s[:-1][seg])
-        ids_s = ids_all[gather].contiguous()
+        total_ids = int(ids_all.shape[0])
+        seg = torch.repeat_interleave(torch.arange(K_glob, device=dev), sizes_s, output_size=total_ids)
+        gather_idx = starts[corder][seg] + (torch.arange(total_ids, device=dev) - off_s[:-1][seg])
+        ids_s = ids_all[gather_idx].contiguous()
         rows_s = M_all[corder, :8].contiguous()
-        torch.cuda.current_stream(dev).synchronize()
         h.check(L.fofb_dist_overlap_rows(h.h, K_glob, rows_s.data_ptr(), off_s.data_ptr(), total_ids, ids_s.data_ptr(),
                                          keep_glob.data_ptr()))
         keepb = keep_glob != 0
@@ -393,7 +429,6 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
         keep_local = torch.zeros(1, dtype=torch.int32, device=dev)
         gidx_local = torch.zeros(1, dtype=torch.int32, device=dev)
         K_merged = 0
-    torch.cuda.current_stream(dev).synchronize()
     h.check(L.fofb_dist_set_merged(h.h, keep_local.data_ptr(), gidx_local.data_ptr(), K_merged, gbbox.ctypes.data))
     h._slab_last_merged = K_merged
     lap("overlap")
@@ -405,16 +440,25 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     else:
         Kf, total, nkey, npos = h.pipeline_finish_mt(mt_state[0], mt_state[1])
         new_state = (nkey, npos)
+    count()
     off_t, rows_t, cidx32, N_t, D_t, props_t = h.pipeline_fetch_torch(Kf, total, dev)
     lap("finish")
 
-    # ---- the global catalogue, in priority order -------------------------------------------------------------
+    # ---- the catalogue in priority order: global (one all-gather of the packed lists) or this rank's share -------
     cidx_t = cidx32.long()
     fmeta = torch.cat([key[cidx_t].view(f64).unsqueeze(1), loc_grow[cidx_t].to(f64).unsqueeze(1),
                        (off_t[1:] - off_t[:-1]).to(f64).unsqueeze(1), N_t.unsqueeze(1), D_t.unsqueeze(1), props_t],
                       dim=1) if Kf else torch.zeros((0, 13), dtype=f64, device=dev)
-    f_meta = cat0(comm.allgatherv_t(fmeta))
-    f_rows = cat0(comm.allgatherv_t(grow_t[rows_t.long()] if total else torch.zeros(0, dtype=i64, device=dev)))
+    frows = grow_t[rows_t.long()] if total else torch.zeros(0, dtype=i64, device=dev)
+    if gather and world > 1:
+        # one exchange: [K, total] per rank, then one padded buffer holding meta (13 doubles per cluster) and the rows
+        sizes = np.concatenate(comm.allgatherv(np.array([[Kf, total]], dtype=np.int64)), axis=0)
+        packed = torch.cat([fmeta.reshape(-1), frows.view(f64)])
+        parts = comm.allgatherv_t(packed)
+        f_meta = cat0([pt[: 13 * int(k)].reshape(-1, 13) for pt, (k, t) in zip(parts, sizes)])
+        f_rows = cat0([pt[13 * int(k): 13 * int(k) + int(t)].view(i64) for pt, (k, t) in zip(parts, sizes)])
+    else:
+        f_meta, f_rows = fmeta, frows
     Kt = len(f_meta)
     if Kt:
         fo = torch.argsort(f_meta[:, 0].contiguous().view(i64), descending=True)
@@ -423,17 +467,17 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
         fs = fs_all[fo]
         out_off = torch.zeros(Kt + 1, dtype=i64, device=dev)
         out_off[1:] = torch.cumsum(fs, 0)
-        tot = int(out_off[-1].item())
-        seg = torch.repeat_interleave(torch.arange(Kt, device=dev), fs)
+        tot = int(f_rows.shape[0])
+        seg = torch.repeat_interleave(torch.arange(Kt, device=dev), fs, output_size=tot)
         out_rows = f_rows[fstarts[fo][seg] + (torch.arange(tot, device=dev) - out_off[:-1][seg])]
         fm = f_meta[fo]
 
         def to_host(name, t):  # pinned, reused host buffers: a fresh pageable allocation per call costs more than the copy
             cache = h.__dict__.setdefault("_slab_pinned", {})
-            buf = cache.get(name)
-            if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
-                buf = cache[name] = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype, pin_memory=True)
-            view = buf[: t.numel()].view(t.shape)
+            buf_h = cache.get(name)
+            if buf_h is None or buf_h.numel() < t.numel() or buf_h.dtype != t.dtype:
+                buf_h = cache[name] = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype, pin_memory=True)
+            view = buf_h[: t.numel()].view(t.shape)
             view.copy_(t, non_blocking=True)
             return view
 
@@ -448,7 +492,8 @@ def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params
     if timings is not None:
         timings.update({"ms_" + k: round(v, 2) for k, v in phases.items()})
         timings.update(rounds=rounds, local_centres=m_l, shared_centres=nB, stage1_clusters=K_glob, merged=K_merged,
-                       local_rows=int(m.rows), fof_rows=n_g)
+                       merged_local=int(len(gidx_local)) if K_glob else 0, local_rows=int(m.rows), fof_rows=n_g,
+                       launches=launches[0])
     del keep
     return res + (new_state,) if mt_state is not None else res
 

@@ -124,3 +124,86 @@ def make_catalog(n, seed=20260101, kind="cosmos", density=50000.0, zmin=0.5, zma
     if not as_frame:
         return np.column_stack(cols)
     return pd.DataFrame(dict(zip(COLUMNS, cols)), columns=COLUMNS)
+
+
+def make_catalog_torch(n, seed=20260104, kind="wide", density=50000.0, zmin=0.5, zmax=2.0, cluster_fraction=0.2,
+                       richness_range=(20, 300), ra0=150.1, dec0=2.2, device="cuda"):
+    """The same distributions as ``make_catalog`` drawn with torch's generator on a GPU, for tables too large to build
+    on the host in a benchmark's set-up time (BASELINE.json configs[3]: 100M galaxies).  Returns an (n, 7) float64 CUDA
+    tensor sorted by redshift.  Deterministic for a given seed and device type, so every rank of a multi-GPU run can
+    build the identical table; it is NOT the numpy stream of ``make_catalog`` (parity fixtures use that one)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    f64 = torch.float64
+    n = int(n)
+
+    def uniform(lo, hi, m):
+        return lo + (hi - lo) * torch.rand(m, dtype=f64, device=dev, generator=g)
+
+    def normal(m):
+        return torch.randn(m, dtype=f64, device=dev, generator=g)
+
+    grid = torch.linspace(zmin, zmax, 20001, dtype=f64, device=dev)
+    pdf = grid ** 2 * torch.exp(-grid / 0.5)
+    cdf = torch.cumsum(pdf, 0)
+    cdf = (cdf - cdf[0]) / (cdf[-1] - cdf[0])
+
+    def sample_z(m, lo=None, hi=None):
+        u = torch.rand(m, dtype=f64, device=dev, generator=g)
+        if lo is not None:  # restrict to [lo, hi] through the CDF
+            c_lo = cdf[torch.searchsorted(grid, torch.tensor(lo, dtype=f64, device=dev))]
+            c_hi = cdf[torch.searchsorted(grid, torch.tensor(hi, dtype=f64, device=dev)).clamp(max=len(grid) - 1)]
+            u = c_lo + (c_hi - c_lo) * u
+        i = torch.searchsorted(cdf, u).clamp(1, len(grid) - 1)
+        t = (u - cdf[i - 1]) / (cdf[i] - cdf[i - 1]).clamp(min=1e-300)
+        return grid[i - 1] + t * (grid[i] - grid[i - 1])
+
+    if kind == "wide":
+        ra_lo, ra_hi, dec_lo, dec_hi = 100.0, 150.0, -20.0, 20.0
+    else:
+        side = float(np.sqrt(n / density))
+        half_ra = 0.5 * side / np.cos(np.deg2rad(dec0))
+        ra_lo, ra_hi, dec_lo, dec_hi = ra0 - half_ra, ra0 + half_ra, dec0 - 0.5 * side, dec0 + 0.5 * side
+    target = int(cluster_fraction * n)
+    mean_rich = 0.5 * (richness_range[0] + richness_range[1])
+    n_cl = int(target / mean_rich)
+    rich = torch.randint(richness_range[0], richness_range[1] + 1, (max(n_cl, 1),), device=dev, generator=g)
+    n_members = int(rich.sum().item()) if n_cl else 0
+    if n_members > n // 2:
+        n_members, n_cl = 0, 0
+    n_bg = n - n_members
+    ra = torch.empty(n, dtype=f64, device=dev)
+    dec = torch.empty(n, dtype=f64, device=dev)
+    z = torch.empty(n, dtype=f64, device=dev)
+    ra[:n_bg] = uniform(ra_lo, ra_hi, n_bg)
+    s_lo, s_hi = float(np.sin(np.deg2rad(dec_lo))), float(np.sin(np.deg2rad(dec_hi)))
+    dec[:n_bg] = torch.rad2deg(torch.asin(uniform(s_lo, s_hi, n_bg)))
+    z[:n_bg] = sample_z(n_bg)
+    if n_members:
+        mra, mdec = 0.05 * (ra_hi - ra_lo), 0.05 * (dec_hi - dec_lo)
+        c_ra = uniform(ra_lo + mra, ra_hi - mra, n_cl)
+        c_dec = uniform(dec_lo + mdec, dec_hi - mdec, n_cl)
+        c_z = sample_z(n_cl, zmin + 0.02, zmax - 0.02)
+        sigma_v = uniform(300.0, 1000.0, n_cl)
+        d_a = torch.from_numpy(_angular_diameter_distance(c_z.cpu().numpy())).to(dev)
+        theta_a = torch.rad2deg((0.2 / 0.7) / d_a)
+        owner = torch.repeat_interleave(torch.arange(n_cl, device=dev), rich)
+        uu = uniform(0.0, 0.99, n_members)
+        radius = theta_a[owner] * torch.sqrt(uu / (1.0 - uu))
+        phi = uniform(0.0, 2 * np.pi, n_members)
+        m_dec = c_dec[owner] + radius * torch.cos(phi)
+        ra[n_bg:] = c_ra[owner] + radius * torch.sin(phi) / torch.cos(torch.deg2rad(m_dec))
+        dec[n_bg:] = m_dec
+        vel = normal(n_members) * sigma_v[owner]
+        z[n_bg:] = (c_z[owner] + vel * (1.0 + c_z[owner]) / C_KMS).clamp(zmin, zmax + 0.02)
+    z_lower = z - (normal(n) * 0.02 * (1 + z)).abs()
+    z_upper = z + (normal(n) * 0.02 * (1 + z)).abs()
+    rmag = -21.0 + normal(n)
+    order = torch.argsort(z, stable=True)
+    out = torch.empty((n, 7), dtype=f64, device=dev)
+    for col, a in enumerate((ra, dec, z, z_lower, z_upper, rmag)):
+        out[:, col] = a[order]
+    out[:, 6] = order.to(f64)   # the generation index, as in make_catalog (ID = arange before the redshift sort)
+    return out

@@ -79,6 +79,10 @@ int fofb_create(int device, fofb_handle** out);      /* fails with FOFB_ERR_NO_D
 void fofb_destroy(fofb_handle* h);
 const char* fofb_last_error(const fofb_handle* h);
 int fofb_synchronize(fofb_handle* h);
+/* Run the handle's work on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * instead of the handle's own: kernels of the caller and NCCL collectives enqueued on that stream are then ordered
+ * with the library's without host synchronisation.  NULL returns to the handle's own stream.  The stream is borrowed. */
+int fofb_set_stream(fofb_handle* h, void* cuda_stream);
 /* CUDA-event time [ms] of the kernels launched by the last compute call, and their count.    */
 int fofb_last_timing(const fofb_handle* h, double* device_ms, int64_t* kernel_launches);
 
@@ -229,6 +233,19 @@ int fofb_dist_prepare(fofb_handle* h, const double* centres, int64_t n_centres, 
 int fofb_dist_round_evaluate(fofb_handle* h);
 int fofb_dist_state(fofb_handle* h, uint8_t* alive, uint8_t* decided, int32_t direction);
 int fofb_dist_round_advance(fofb_handle* h, int64_t* n_active);
+/* The same loop with ONE collective per round.  The tracker state of a centre is 0 (alive, undecided), 1 (switched off)
+ * or 2 (evaluated); it only ever rises and 2 wins, so an element-wise MAX over processes merges it.
+ *   fofb_dist_state_pack   : buf[0 .. n_buf) := 0, buf[shared_pos[t]] := state of local centre local_pos[t]
+ *                            (t < n_shared), buf[n_buf - 1] := 1 if this process entered the round with active centres
+ *   [all-reduce MAX over buf]
+ *   fofb_dist_state_unpack : the merged states back into the local table
+ *   fofb_dist_round_advance2: as fofb_dist_round_advance; *any_active = buf[n_buf - 1] (somebody still had work)
+ * All pointers are device pointers; local_pos / shared_pos are int64. */
+int fofb_dist_state_pack(fofb_handle* h, int64_t n_shared, const int64_t* local_pos, const int64_t* shared_pos, uint8_t* buf,
+                         int64_t n_buf);
+int fofb_dist_state_unpack(fofb_handle* h, int64_t n_shared, const int64_t* local_pos, const int64_t* shared_pos,
+                           const uint8_t* buf);
+int fofb_dist_round_advance2(fofb_handle* h, const uint8_t* buf, int64_t n_buf, int64_t* n_active, int32_t* any_active);
 int fofb_dist_finalize(fofb_handle* h, int64_t* n_clusters, int64_t* n_members);
 int fofb_dist_local_clusters(fofb_handle* h, int32_t* centre, int64_t* offsets, double* ids);
 int fofb_dist_overlap(fofb_handle* h, int64_t K, const int32_t* centre, const int64_t* offsets, const double* ids, int32_t* keep);

@@ -73,6 +73,10 @@ import torch
 a = torch.tensor([1, r, 1], dtype=torch.uint8); d = torch.tensor([0, r, 1 - r], dtype=torch.uint8)
 c.allreduce_bytes(a, d)
 assert a.tolist() == [1, 0, 1] and d.tolist() == [0, 1, 1]
+# one collective per round: states 0 alive < 1 switched off < 2 evaluated, merged by MAX; last byte = anybody active
+buf = torch.tensor([0, 2 * r, 1 - r, r], dtype=torch.uint8)
+c.allreduce_max_bytes(buf)
+assert buf.tolist() == [0, 2, 1, 1]
 c.barrier()
 dist.destroy_process_group()
 print("ok", r)
@@ -116,6 +120,12 @@ def test_thread_comm_collectives_world3():
             alive[r] = 0                                                                   # rank r kills centre r
             decided[3 - r] = 1                                                             # and decides centre 3 - r
             c.allreduce_bytes(alive, decided)
+            state = torch.zeros(5, dtype=torch.uint8)
+            state[r] = 1                                                                   # rank r switches centre r off
+            state[3 - r] = 2                                                               # and evaluates centre 3 - r
+            state[4] = 1 if r == 1 else 0                                                  # only rank 1 still has work
+            c.allreduce_max_bytes(state)
+            assert state.tolist() == [1, 2, 2, 2, 1], state.tolist()
             c.barrier()
             results[r] = (g, t, s, mn, mx, alive.clone(), decided.clone())
         except Exception as e:  # noqa: BLE001

@@ -157,3 +157,20 @@ def test_single_shared_value_switches_off_the_first_centre_only(lib, handle):
     for k, (attrs, members) in enumerate(stages["candidates"]):
         assert np.array_equal(c[cen[k]], attrs)
         assert np.array_equal(g[mem[off[k]:off[k + 1]]], members)
+
+
+def test_dataframe_column_major_input_takes_the_split_upload(lib):
+    """A pandas DataFrame hands over a column-major block (df.values: every column contiguous).  The whole-job entry
+    uploads ra/dec/z first and streams the other columns behind stage 0; the catalogue must equal the row-major run."""
+    from fof_b200 import pipeline
+    df = make_catalog(30000, seed=51)
+    vals = df.values
+    assert vals.strides[0] == 8 and vals.strides[1] >= 8 * len(df), "expected a column-major pandas block"
+    np.random.seed(8)
+    a = pipeline.find_clusters(df)
+    np.random.seed(8)
+    b = pipeline.find_clusters(np.ascontiguousarray(vals))
+    assert len(a) > 20
+    for name in ("offsets", "member_rows", "centre_row", "N", "D", "N_row"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    np.testing.assert_allclose(a.props, b.props, rtol=1e-12)

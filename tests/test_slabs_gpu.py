@@ -53,3 +53,62 @@ def test_slabs_equal_single_gpu(lib, n, seed):
             assert np.array_equal(cat.N, ref.N) and np.array_equal(cat.D, ref.D)
             np.testing.assert_allclose(cat.props, ref.props, rtol=1e-12)
             assert np.array_equal(cat.mt_state[0], ref_state[1]) and cat.mt_state[1] == ref_state[2]
+
+
+NCCL_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch
+import torch.distributed as dist
+rank = int(os.environ["RANK"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+from fof_b200 import _lib, distributed as D
+from fof_b200.mock import make_catalog
+arr = make_catalog(int(sys.argv[2]), seed=17, as_frame=False)
+np.random.seed(99)
+st = np.random.get_state()
+cat = D.find_clusters_distributed(arr, comm=D.TorchComm(), handle=_lib.Handle(rank), mt_state=(st[1].copy(), st[2]))
+np.savez(sys.argv[3] + f".rank{rank}.npz", off=cat.offsets, rows=cat.member_rows, centre=cat.centre_row, N=cat.N, D=cat.D,
+         props=cat.props, key=cat.mt_state[0], pos=cat.mt_state[1])
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_process_nccl_slabs_equal_single_gpu(lib, tmp_path):
+    """One process per GPU over NCCL (the production layout): the catalogue both ranks assemble must be byte-identical to
+    the single-GPU run.  Needs two GPUs on the box (``gpurun --gpus 2``); skipped on a single-GPU box, where the
+    thread-emulated ranks above cover the same driver code."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from fof_b200 import pipeline
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 200000
+    arr = make_catalog(n, seed=17, as_frame=False)
+    np.random.seed(99)
+    ref = pipeline.find_clusters(arr)
+    ref_state = np.random.get_state()
+    script = tmp_path / "worker.py"
+    script.write_text(NCCL_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), root, str(n), str(tmp_path / "out")],
+                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert len(ref) > 100
+    for r in range(2):
+        got = np.load(str(tmp_path / "out") + f".rank{r}.npz")
+        assert np.array_equal(got["off"], ref.offsets) and np.array_equal(got["rows"], ref.member_rows)
+        assert np.array_equal(got["centre"], ref.centre_row)
+        assert np.array_equal(got["N"], ref.N) and np.array_equal(got["D"], ref.D)
+        np.testing.assert_allclose(got["props"], ref.props, rtol=1e-12)
+        assert np.array_equal(got["key"], ref_state[1]) and int(got["pos"]) == ref_state[2]
