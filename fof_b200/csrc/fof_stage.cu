@@ -694,7 +694,13 @@ __device__ int hop2_global_path(int w, int n_f, int n_nm, long long off, long lo
     bt.init_T(fra, fdec, have ? v2cos[off + fi] : 1.0, LL, T);
     const Box fbox = grid_box(b2, p.grid_cells, fra, fdec, LL);  // the friend's cell box: once per friend
     for (int q = 0; q < n_nm; ++q) {
-      if (*(volatile int*)(first_batch + off + q) <= base) continue;  // an earlier friend already has it
+      // an earlier friend already has it?  ONE lane reads, so that the whole warp takes the same branch: other warps
+      // lower first_batch[q] concurrently, and lanes that re-converge late could otherwise read different values and
+      // split over the ballot below
+      int cur = 0;
+      if (lane == 0) cur = *(volatile int*)(first_batch + off + q);
+      cur = __shfl_sync(0xffffffffu, cur, 0);
+      if (cur <= base) continue;
       const int vp = nm_list[off + q];
       const double pra = v2ra[off + vp], pdec = v2dec[off + vp];
       const bool hit = have && fbox.contains(pra, pdec) && bt.inside(pra, pdec, v2cos[off + vp]);
@@ -868,7 +874,10 @@ __global__ void __launch_bounds__(kHop2Threads) k_hop2_heavy(
         bt.init_T(fra, fdec, have ? v2cos[off + fi] : 1.0, LL, T);
         const Box fbox = grid_box(b2, p.grid_cells, fra, fdec, LL);
         for (int q = 0; q < n_nm; ++q) {
-          if (*(volatile int*)(s_fb + q) <= base) continue;  // an earlier friend already has it
+          int cur = 0;  // one lane reads (see hop2_global_path): the skip must be warp-uniform
+          if (lane == 0) cur = *(volatile int*)(s_fb + q);
+          cur = __shfl_sync(0xffffffffu, cur, 0);
+          if (cur <= base) continue;  // an earlier friend already has it
           const double pra = s_ra[q], pdec = s_dec[q];
           const bool hit = have && fbox.contains(pra, pdec) && bt.inside(pra, pdec, s_cos[q]);
           const unsigned mh = __ballot_sync(0xffffffffu, hit);
