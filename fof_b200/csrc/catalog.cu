@@ -76,16 +76,25 @@ __global__ void k_cell_keys(int n, const double* zra, const double* zdec, CellLi
 
 // ---- K3: gather into the cell-ordered SoA ---------------------------------------------------------------
 __global__ void k_cell_gather(int n, const int* sorted_rank, const int* zorder, const double* zra, const double* zdec,
-                              double* ra, double* dec, double* cosdec, int* zrank, int* row) {
+                              double* ra, double* dec, double* cosdec, int* zrank, int* row, CellListView cl, PackedPoint* pk) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int r = sorted_rank[k];
-  const double d = zdec[r];
-  ra[k] = zra[r];
+  const double a = zra[r], d = zdec[r];
+  const double c = cos(__dmul_rn(d, kDeg2Rad));
+  ra[k] = a;
   dec[k] = d;
-  cosdec[k] = cos(__dmul_rn(d, kDeg2Rad));
+  cosdec[k] = c;
   zrank[k] = r;
   row[k] = zorder[r];
+  if (pk) {
+    PackedPoint p;
+    p.fx = (float)(a - (cl.ra0 + (double)cl.cx_of(a) * cl.s_ra));
+    p.fy = (float)(d - (cl.dec0 + (double)cl.cy_of(d) * cl.s_dec));
+    p.fcos = (float)c;
+    p.zr = r;
+    pk[k] = p;
+  }
 }
 
 // ---- K4: cell table from the sorted keys ----------------------------------------------------------------
@@ -176,7 +185,7 @@ void Catalog::build(fofb_handle* h, const View& rows_in) {
   dec_absmax = fmax(fabs(g.z), fabs(g.w));
 }
 
-void CellList::build(fofb_handle* h, const Catalog& cat, double r_max_deg) {
+void CellList::build(fofb_handle* h, const Catalog& cat, double r_max_deg, bool packed) {
   FOFB_REQUIRE(r_max_deg > 0.0 && std::isfinite(r_max_deg), "cell list needs a positive finite query radius");
   cudaStream_t st = h->stream;
   const int64_t n = cat.n;
@@ -211,8 +220,9 @@ void CellList::build(fofb_handle* h, const Catalog& cat, double r_max_deg) {
   FOFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in, key_out, val_in, val_out, ni, 0, bits, st));
   FOFB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp(h, bytes), bytes, key_in, key_out, val_in, val_out, ni, 0, bits, st));
   count_launch(h, 2 + (bits + 7) / 8);
+  has_packed = packed;
   FOFB_PROFILED(h, "k_cell_gather", k_cell_gather<<<grid_for(n, B), B, 0, st>>>(ni, val_out, cat.zorder.p, cat.zra.p, cat.zdec.p, ra.alloc(n), dec.alloc(n),
-                                              cosdec.alloc(n), zrank.alloc(n), row.alloc(n)));
+                                              cosdec.alloc(n), zrank.alloc(n), row.alloc(n), cl, packed ? pk.alloc(n) : nullptr));
   int* cs = cell_start.alloc((size_t)ncell + 1);
   k_cell_starts<<<grid_for(n + 1, B), B, 0, st>>>(ni, key_out, ncell, cs);
   FOFB_LAUNCH_CHECK(h);
@@ -226,6 +236,9 @@ CellListView CellList::view() const {
   v.dec0 = dec0;
   v.inv_sra = 1.0 / s_ra;
   v.inv_sdec = 1.0 / s_dec;
+  v.s_ra = s_ra;
+  v.s_dec = s_dec;
+  v.pk = has_packed ? pk.p : nullptr;
   v.ncx = ncx;
   v.ncy = ncy;
   v.cell_start = cell_start.p;

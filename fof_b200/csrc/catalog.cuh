@@ -11,9 +11,20 @@ namespace fofb {
 
 constexpr int kBBoxBlock = 256;  // block size of the two-level range min/max structure
 
+// One cell-list entry for the tiled bubble counts (16 bytes): offsets from the entry's own cell corner in degrees and
+// cos(dec) in fp32, plus the z-rank.  Differences between entries of neighbouring cells are then exact to ~1e-8 deg in
+// fp32 (the cell shift is added as a small multiple of the cell size), which is enough to decide every pair that is not
+// within 1e-4 of the threshold; those few are re-decided in fp64 from the full-precision arrays.
+struct PackedPoint {
+  float fx, fy, fcos;
+  int zr;
+};
+
 struct CellListView {
   double ra0, dec0, inv_sra, inv_sdec;
+  double s_ra, s_dec;      // cell size in degrees
   int ncx, ncy;
+  const PackedPoint* pk;   // cell-ordered, or null when the list was built without them
   const int* cell_start;   // [ncx*ncy + 1]
   const double* ra;        // cell-ordered SoA; z-rank ascending inside a cell
   const double* dec;

@@ -13,9 +13,11 @@ struct CellList {
   double ra0 = 0, dec0 = 0, s_ra = 1, s_dec = 1;
   int ncx = 1, ncy = 1;
   DBuf<double> ra, dec, cosdec;
+  DBuf<PackedPoint> pk;   // only when built with packed = true (the tiled count kernels)
   DBuf<int> zrank, row, cell_start, val_a, val_b;
   DBuf<unsigned> key_a, key_b;
-  void build(fofb_handle* h, const Catalog& cat, double r_max_deg);
+  void build(fofb_handle* h, const Catalog& cat, double r_max_deg, bool packed = false);
+  bool has_packed = false;
   CellListView view() const;
 };
 

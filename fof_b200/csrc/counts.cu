@@ -47,47 +47,14 @@ __global__ void k_count_prep(CatalogView cat, Cosmo cosmo, double count_radius, 
 // galaxy of the strip then runs its query against shared memory: per neighbour cell a binary search of its z-rank
 // window (cells are z-rank sorted), then the cell-box and fp64 haversine tests on the in-window candidates.
 // A neighbourhood that does not fit (percolating blobs) is read from global memory by the same code.
-// The queries q0 <= qi < q1 of one strip.  P_* index the staged slices (shared memory) or the cell list itself.
-__device__ __forceinline__ void count_strip(const CellListView& cl, const double* __restrict__ P_ra,
-                                            const double* __restrict__ P_dec, const double* __restrict__ P_cos,
-                                            const int* __restrict__ P_zr, const Tile& t, int q0, int q1,
-                                            const CountRec* __restrict__ rec, const double4* __restrict__ box,
-                                            int* __restrict__ N_row) {
-  for (int qi = q0 + (int)threadIdx.x; qi < q1; qi += kCtThreads) {
-    const int li = qi + t.delta[1];
-    const int zr = P_zr[li];
-    const CountRec qr = rec[zr];
-    const int wlo = qr.wlo, whi = qr.whi & 0x7fffffff;
-    int count = 0;
-    if (whi > wlo) {
-      const double ra = P_ra[li], dec = P_dec[li];
-      BubbleTest bt;
-      bt.init(ra, dec, P_cos[li], qr.r_deg);
-      Box bx{-INFINITY, INFINITY, -INFINITY, INFINITY};
-      if (qr.whi < 0) {
-        const double4 b = box[zr];
-        bx = Box{b.x, b.y, b.z, b.w};
-      }
-      const int cx = cl.cx_of(ra);
-      const int k0 = (cx > 0 ? cx - 1 : 0) - t.xa, k1 = (cx < cl.ncx - 1 ? cx + 1 : cl.ncx - 1) - t.xa;
-      count = tile_count(P_ra, P_dec, P_cos, P_zr, t, 0, 2, k0, k1, wlo, whi, bt, bx);
-    }
-    N_row[cl.row[qi]] = count;
-  }
-}
-
-__global__ void __launch_bounds__(kCtThreads, 2) k_count(CellListView cl, int nsx, const CountRec* __restrict__ rec,
-                                                     const double4* __restrict__ box, int* __restrict__ N_row) {
+__global__ void __launch_bounds__(kCtThreads, 4) k_count(CellListView cl, int nsx, const CountRec* __restrict__ rec,
+                                                        const double4* __restrict__ box, int* __restrict__ N_row) {
   extern __shared__ __align__(128) unsigned char ct_smem[];
   __shared__ int s_cs[3][kCtW + 3];
   __shared__ int s_delta[3];
   __shared__ int s_fits;
   __shared__ __align__(8) unsigned long long s_bar;
   Tile t;
-  t.ra = reinterpret_cast<double*>(ct_smem);
-  t.dec = t.ra + kCtMaxPts;
-  t.cos = t.dec + kCtMaxPts;
-  t.zr = reinterpret_cast<int*>(t.cos + kCtMaxPts);
   t.cs = s_cs;
   t.delta = s_delta;
   const int y = blockIdx.x / nsx, x0 = (blockIdx.x % nsx) * kCtW;
@@ -95,10 +62,34 @@ __global__ void __launch_bounds__(kCtThreads, 2) k_count(CellListView cl, int ns
   const int xe = x0 + kCtW < cl.ncx ? x0 + kCtW : cl.ncx;
   const int q0 = __ldg(cl.cell_start + (size_t)y * cl.ncx + x0), q1 = __ldg(cl.cell_start + (size_t)y * cl.ncx + xe);
   if (q1 <= q0) return;
-  if (tile_stage(cl, y, x0, t, &s_bar, &s_fits))
-    count_strip(cl, t.ra, t.dec, t.cos, t.zr, t, q0, q1, rec, box, N_row);
-  else
-    count_strip(cl, cl.ra, cl.dec, cl.cosdec, cl.zrank, t, q0, q1, rec, box, N_row);
+  tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem), &s_bar, &s_fits);
+  const double cell_deg = fmax(cl.s_ra, cl.s_dec);
+  for (int qi = q0 + (int)threadIdx.x; qi < q1; qi += kCtThreads) {
+    const PackedPoint self = t.pk[qi + t.delta[1]];
+    const CountRec qr = rec[self.zr];
+    TileQuery q;
+    q.wlo = qr.wlo;
+    q.whi = qr.whi & 0x7fffffff;
+    int count = 0;
+    if (q.whi > q.wlo) {
+      const double ra = cl.ra[qi], dec = cl.dec[qi];
+      BubbleTest bt;
+      bt.init(ra, dec, cl.cosdec[qi], qr.r_deg);
+      Box bx{-INFINITY, INFINITY, -INFINITY, INFINITY};
+      const bool boxed = qr.whi < 0;
+      if (boxed) {
+        const double4 b = box[self.zr];
+        bx = Box{b.x, b.y, b.z, b.w};
+      }
+      q.fx = self.fx; q.fy = self.fy; q.fcos = self.fcos;
+      q.cx = cl.cx_of(ra);
+      q.cy = y;
+      tile_thresholds(qr.r_deg, cell_deg, &q.T_lo, &q.T_hi);
+      const int cx0 = q.cx > 0 ? q.cx - 1 : 0, cx1 = q.cx < cl.ncx - 1 ? q.cx + 1 : cl.ncx - 1;
+      count = tile_count(cl, t, y, q, y > 0 ? 0 : 1, y < cl.ncy - 1 ? 2 : 1, cx0, cx1, bt, boxed, bx);
+    }
+    N_row[cl.row[qi]] = count;
+  }
 }
 
 // ---- K6: candidate keys: N descending, ties by descending row (oracle pin D1 of fof.py:79-81) ----
@@ -139,7 +130,7 @@ void Stage0::run(fofb_handle* h, const fofb_params& p, Catalog& cat, CellList& c
   FOFB_CUDA(cudaMemcpyAsync(&r_max, tmax, sizeof(double), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
   FOFB_REQUIRE(std::isfinite(r_max) && r_max > 0.0, "non-finite angular radius (check redshifts and cosmology)");
-  cells.build(h, cat, r_max);
+  cells.build(h, cat, r_max, true);
   int* N = N_row.alloc(n);
   {
     static bool attr_set[64] = {};

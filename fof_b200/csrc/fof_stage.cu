@@ -1110,7 +1110,7 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
   FOFB_REQUIRE(std::isfinite(R1max) && R1max > 0 && std::isfinite(r2[1]) && r2[1] > 0,
                "non-finite search radius (check centre redshifts)");
   big.build(h, cat, R1max);
-  small.build(h, cat, r2[1]);
+  small.build(h, cat, r2[1], true);  // packed records: the overdensity counts run on tiles (overlap.cu)
 
   // tracker kill targets
   {

@@ -605,60 +605,73 @@ __global__ void k_od_keys(long long total, CellListView cl, const double* rra, c
   val[q] = (int)q;
 }
 
-// Galaxies of the centre's velocity window within theta_0.5 of each random point (helper.py:207-216).  One CTA per
-// strip of cells, as in k_count (counts.cu): the strip's neighbourhood is staged in shared memory once with bulk
-// asynchronous copies and serves every query point that fell into the strip -- the points of many different clusters,
-// each with its own window, whose binary searches would otherwise walk the same cells in global memory again and again.
-__global__ void __launch_bounds__(kCtThreads, 2) k_od_count(CellListView cl, int nsx, long long total, int npts,
-                                                            const unsigned* __restrict__ qkey, const int* __restrict__ order,
-                                                            const OdCluster* __restrict__ oc, const double* __restrict__ rra,
-                                                            const double* __restrict__ rdec, int grid_cells,
-                                                            int* __restrict__ counts) {
-  extern __shared__ __align__(128) unsigned char ct_smem[];
-  __shared__ int s_cs[3][kCtW + 3];
-  __shared__ int s_delta[3];
-  __shared__ int s_fits;
-  __shared__ long long s_q[2];
-  __shared__ __align__(8) unsigned long long s_bar;
-  Tile t;
-  t.ra = reinterpret_cast<double*>(ct_smem);
-  t.dec = t.ra + kCtMaxPts;
-  t.cos = t.dec + kCtMaxPts;
-  t.zr = reinterpret_cast<int*>(t.cos + kCtMaxPts);
-  t.cs = s_cs;
-  t.delta = s_delta;
-  const int y = blockIdx.x / nsx, x0 = (blockIdx.x % nsx) * kCtW;
-  const int xe = x0 + kCtW < cl.ncx ? x0 + kCtW : cl.ncx;
-  if (threadIdx.x < 2) {  // the strip's queries: sorted keys in [y * ncx + x0, y * ncx + xe)
-    const unsigned key = (unsigned)(y * cl.ncx + (threadIdx.x == 0 ? x0 : xe));
-    long long lo = 0, hi = total;
+// first query (in cell order) of every strip: qstart[strip] = lower bound of the strip's first cell key, qstart[nstrips] = total
+__global__ void k_od_strip_starts(int nstrips, int nsx, int ncx, long long total, const unsigned* __restrict__ qkey,
+                                  int* __restrict__ qstart) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nstrips) return;
+  long long lo = 0, hi = total;
+  if (s < nstrips) {
+    const unsigned key = (unsigned)((s / nsx) * ncx + (s % nsx) * kCtW);
     while (lo < hi) {
       const long long mid = (lo + hi) >> 1;
       if (__ldg(qkey + mid) < key) lo = mid + 1; else hi = mid;
     }
-    s_q[threadIdx.x] = lo;
+  } else {
+    lo = total;
   }
-  __syncthreads();
-  const long long q0 = s_q[0], q1 = s_q[1];
+  qstart[s] = (int)lo;
+}
+
+// Galaxies of the centre's velocity window within theta_0.5 of each random point (helper.py:207-216).  One CTA per
+// strip of cells, as in k_count (counts.cu): the strip's neighbourhood is staged in shared memory once with a bulk
+// asynchronous copy and serves every query point that fell into the strip -- the points of many different clusters,
+// each with its own window, whose binary searches would otherwise walk the same cells in global memory again and again.
+__global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int nsx, int npts, const int* __restrict__ qstart,
+                                                            const int* __restrict__ order, const OdCluster* __restrict__ oc,
+                                                            const double* __restrict__ rra, const double* __restrict__ rdec,
+                                                            int grid_cells, int* __restrict__ counts) {
+  extern __shared__ __align__(128) unsigned char ct_smem[];
+  __shared__ int s_cs[3][kCtW + 3];
+  __shared__ int s_delta[3];
+  __shared__ int s_fits;
+  __shared__ __align__(8) unsigned long long s_bar;
+  Tile t;
+  t.cs = s_cs;
+  t.delta = s_delta;
+  const int y = blockIdx.x / nsx, x0 = (blockIdx.x % nsx) * kCtW;
+  // a row's strips are consecutive key ranges except the last, which ends with the row: the next row's first strip
+  // starts exactly there, so [qstart[b], qstart[b + 1]) is this strip's slice of the cell-sorted queries
+  const int q0 = qstart[blockIdx.x], q1 = qstart[blockIdx.x + 1];
   if (q1 <= q0) return;
-  const bool fits = tile_stage(cl, y, x0, t, &s_bar, &s_fits);
+  tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem), &s_bar, &s_fits);
   const int xb = t.xa + t.ncs - 2;
-  for (long long ti = q0 + threadIdx.x; ti < q1; ti += kCtThreads) {
-    const int q = order[ti];
-    const OdCluster o = oc[q / npts];
+  const double cell_deg = fmax(cl.s_ra, cl.s_dec);
+  for (int ti = q0 + (int)threadIdx.x; ti < q1; ti += kCtThreads) {
+    const int qid = order[ti];
+    const OdCluster o = oc[qid / npts];
     int cnt = 0;
     if (o.whi > o.wlo) {
-      const double ra = rra[q], dec = rdec[q], r = o.r;
+      const double ra = rra[qid], dec = rdec[qid], r = o.r;
       const Box bx = grid_box(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, ra, dec, r);
+      const bool boxed = bx.ra_lo != -INFINITY || bx.ra_hi != INFINITY || bx.dec_lo != -INFINITY || bx.dec_hi != INFINITY;
+      const double cs = cos(__dmul_rn(dec, kDeg2Rad));
       BubbleTest bt;
-      bt.init(ra, dec, cos(__dmul_rn(dec, kDeg2Rad)), r);
+      bt.init(ra, dec, cs, r);
       const double reach = ra_reach(r, dec);
       const int cx0 = cl.cx_of(ra - reach), cx1 = cl.cx_of(ra + reach);
       const int cy0 = cl.cy_of(dec - r * 1.000001), cy1 = cl.cy_of(dec + r * 1.000001);
       if (cx0 >= t.xa && cx1 <= xb && cy0 >= y - 1 && cy1 <= y + 1) {
-        const int r0 = cy0 - (y - 1), r1 = cy1 - (y - 1);
-        cnt = fits ? tile_count(t.ra, t.dec, t.cos, t.zr, t, r0, r1, cx0 - t.xa, cx1 - t.xa, o.wlo, o.whi, bt, bx)
-                   : tile_count(cl.ra, cl.dec, cl.cosdec, cl.zrank, t, r0, r1, cx0 - t.xa, cx1 - t.xa, o.wlo, o.whi, bt, bx);
+        TileQuery q;
+        q.cx = cl.cx_of(ra);
+        q.cy = cl.cy_of(dec);
+        q.fx = (float)(ra - (cl.ra0 + (double)q.cx * cl.s_ra));
+        q.fy = (float)(dec - (cl.dec0 + (double)q.cy * cl.s_dec));
+        q.fcos = (float)cs;
+        q.wlo = o.wlo;
+        q.whi = o.whi;
+        tile_thresholds(r, cell_deg, &q.T_lo, &q.T_hi);
+        cnt = tile_count(cl, t, y, q, cy0 - (y - 1), cy1 - (y - 1), cx0, cx1, bt, boxed, bx);
       } else {  // a bubble wider than one cell (points beyond the cell list's own declination range): walk the cell list
         for (int yy = cy0; yy <= cy1; ++yy)
           for (int xx = cx0; xx <= cx1; ++xx) {
@@ -672,7 +685,7 @@ __global__ void __launch_bounds__(kCtThreads, 2) k_od_count(CellListView cl, int
           }
       }
     }
-    counts[q] = cnt;
+    counts[qid] = cnt;
   }
 }
 
@@ -1044,8 +1057,12 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
       attr_set[h->device & 63] = true;
     }
     const int nsx = (scl.ncx + kCtW - 1) / kCtW;
-    FOFB_PROFILED(h, "k_od_count", k_od_count<<<nsx * scl.ncy, kCtThreads, kCtSmemBytes, st>>>(scl, nsx, total, npts, qk2, qv2, oc, rra, rdec,
-                                                                                                p.grid_cells, counts));
+    const int nstrips = nsx * scl.ncy;
+    int* qstart = sc.wlo.alloc((size_t)nstrips + 1);
+    k_od_strip_starts<<<grid_for(nstrips + 1, 256), 256, 0, st>>>(nstrips, nsx, scl.ncx, total, qk2, qstart);
+    FOFB_LAUNCH_CHECK(h);
+    FOFB_PROFILED(h, "k_od_count", k_od_count<<<nstrips, kCtThreads, kCtSmemBytes, st>>>(scl, nsx, npts, qstart, qv2, oc, rra, rdec,
+                                                                                          p.grid_cells, counts));
   }
   int* keep = sc.state.alloc(K);
   k_od_finish<<<wblocks, 128, 0, st>>>(K, npts, counts, N_own, merged.off.p, p.overdensity, p.min_count, p.richness, D, keep);

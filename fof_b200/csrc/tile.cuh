@@ -47,22 +47,23 @@ __device__ __forceinline__ int lower_bound_zr(const ZR* __restrict__ a, int lo, 
 
 // ---- one strip of cells and its neighbourhood ---------------------------------------------------------------------
 // A strip is kCtW consecutive cells of one cell row.  Its neighbourhood -- the same cells plus one on either side, in
-// the rows above, at and below -- is three contiguous slices of the cell-ordered SoA (ra, dec, cos dec, z-rank).
-constexpr int kCtW = 8, kCtThreads = 512, kCtMaxPts = 3584;
-constexpr size_t kCtSmemBytes = (size_t)kCtMaxPts * (3 * sizeof(double) + sizeof(int));
+// the rows above, at and below -- is three contiguous slices of the cell-ordered packed records (PackedPoint, 16 bytes).
+constexpr int kCtW = 4, kCtThreads = 256, kCtMaxPts = 3072;
+constexpr size_t kCtSmemBytes = (size_t)kCtMaxPts * sizeof(PackedPoint);
+constexpr float kHalfDeg2RadF = 0.00872664625997164788f;  // pi / 360
 
 struct Tile {
-  double *ra, *dec, *cos;  // shared-memory slices (row r of the neighbourhood is shifted by delta[r])
-  int* zr;
+  const PackedPoint* pk;   // the staged slices (shared memory), or the cell list's own array when they did not fit
   int (*cs)[kCtW + 3];     // global cell boundaries of the three rows, from cell xa on
-  int* delta;
+  int* delta;              // index of an entry in pk = its global index + delta[row]
   int xa, ncs;
 };
 
-// Fills t.cs, then brings the three slices into shared memory (thread 0 issues the bulk copies, everybody waits on the
-// mbarrier).  Returns false -- with delta = 0, so that the caller indexes the cell list itself -- when the slices
-// exceed kCtMaxPts points (percolating blobs).  Must be called by every thread of the CTA; bar and fits are shared.
-__device__ __forceinline__ bool tile_stage(const CellListView& cl, int y, int x0, Tile& t, unsigned long long* bar, int* fits_sh) {
+// Fills t.cs, then brings the three slices into `smem` (thread 0 issues the bulk copies, everybody waits on the
+// mbarrier).  When the slices exceed kCtMaxPts entries (percolating blobs) nothing is copied: t.pk is the cell list's
+// array and delta = 0.  Must be called by every thread of the CTA; bar and fits_sh are shared.
+__device__ __forceinline__ void tile_stage(const CellListView& cl, int y, int x0, Tile& t, PackedPoint* smem,
+                                           unsigned long long* bar, int* fits_sh) {
   const int tid = threadIdx.x;
   t.xa = x0 > 0 ? x0 - 1 : 0;
   const int xb = x0 + kCtW < cl.ncx - 1 ? x0 + kCtW : cl.ncx - 1;  // staged cells xa..xb
@@ -75,58 +76,96 @@ __device__ __forceinline__ bool tile_stage(const CellListView& cl, int y, int x0
   if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
   if (tid == 0) {
-    int sbase = 0, fits = 1;
+    int sbase = 0;
     int ga[3], la[3];
     for (int r = 0; r < 3; ++r) {
-      const int gs = t.cs[r][0], ge = t.cs[r][t.ncs - 1];
-      ga[r] = gs & ~3;  // 16-byte aligned slices: 4 ints, 4 doubles (the buffers carry slack past their last element)
-      la[r] = ge > gs ? ((ge + 3) & ~3) - ga[r] : 0;
+      ga[r] = t.cs[r][0];
+      la[r] = t.cs[r][t.ncs - 1] - ga[r];
       t.delta[r] = sbase - ga[r];
       sbase += la[r];
     }
-    if (sbase > kCtMaxPts) fits = 0;
+    const int fits = sbase <= kCtMaxPts ? 1 : 0;
     if (fits) {
-      mbar_expect_tx(bar, (unsigned)sbase * 28u);
-      for (int r = 0; r < 3; ++r) {
-        if (!la[r]) continue;
-        const int so = t.delta[r] + ga[r];
-        bulk_g2s(t.ra + so, cl.ra + ga[r], (unsigned)la[r] * 8u, bar);
-        bulk_g2s(t.dec + so, cl.dec + ga[r], (unsigned)la[r] * 8u, bar);
-        bulk_g2s(t.cos + so, cl.cosdec + ga[r], (unsigned)la[r] * 8u, bar);
-        bulk_g2s(t.zr + so, cl.zrank + ga[r], (unsigned)la[r] * 4u, bar);
-      }
+      mbar_expect_tx(bar, (unsigned)sbase * (unsigned)sizeof(PackedPoint));
+      for (int r = 0; r < 3; ++r)
+        if (la[r]) bulk_g2s(smem + t.delta[r] + ga[r], cl.pk + ga[r], (unsigned)la[r] * (unsigned)sizeof(PackedPoint), bar);
     } else {
       t.delta[0] = t.delta[1] = t.delta[2] = 0;
     }
     *fits_sh = fits;
   }
   __syncthreads();
-  const bool fits = *fits_sh != 0;
-  if (fits) mbar_wait(bar, 0);
-  return fits;
+  if (*fits_sh) {
+    mbar_wait(bar, 0);
+    t.pk = smem;
+  } else {
+    t.pk = cl.pk;
+  }
 }
 
-// Number of points of the window [wlo, whi) inside the bubble `bt` (and the cell box `bx`) among the cells
-// (rows r0..r1 of the neighbourhood, columns k0..k1 counted from t.xa).  P_* are the staged slices or the cell list.
-__device__ __forceinline__ int tile_count(const double* __restrict__ P_ra, const double* __restrict__ P_dec,
-                                          const double* __restrict__ P_cos, const int* __restrict__ P_zr, const Tile& t,
-                                          int r0, int r1, int k0, int k1, int wlo, int whi, const BubbleTest& bt, const Box& bx) {
+// One bubble query against the neighbourhood: the number of entries of the window [wlo, whi) within the bubble.
+//   (cx, cy), q : the query point's cell and its packed offsets (q.fx / q.fy relative to that cell's corner);
+//   bt          : the same bubble in fp64 -- decides the pairs the fp32 test leaves open (|a - T| <= band * T);
+//   bx          : the GriSPy cell box of the query when `boxed` (rare): those queries run in fp64 throughout;
+//   rows r0..r1 of the neighbourhood (0 = row y - 1), cells cx0..cx1.
+struct TileQuery {
+  float fx, fy, fcos, T_lo, T_hi;
+  int cx, cy, wlo, whi;
+};
+
+__device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t, int y, const TileQuery& q, int r0, int r1, int cx0,
+                                          int cx1, const BubbleTest& bt, bool boxed, const Box& bx) {
   int count = 0;
+  const float sx = (float)cl.s_ra, sy = (float)cl.s_dec;
   for (int r = r0; r <= r1; ++r) {
     const int d = t.delta[r];
-    int s = t.cs[r][k0] + d;
-    for (int k = k0; k <= k1; ++k) {
-      const int e = t.cs[r][k + 1] + d;
-      const int a = lower_bound_zr(P_zr, s, e, wlo);
-      const int b = lower_bound_zr(P_zr, a, e, whi);
-      for (int j = a; j < b; ++j) {
-        const double pra = P_ra[j], pdec = P_dec[j];
-        if (bx.contains(pra, pdec) && bt.inside(pra, pdec, P_cos[j])) ++count;
+    const float oy = (float)(y - 1 + r - q.cy) * sy - q.fy;
+    int s = t.cs[r][cx0 - t.xa] + d;
+    for (int cx = cx0; cx <= cx1; ++cx) {
+      const int e = t.cs[r][cx - t.xa + 1] + d;
+      // in-window run of this cell (entries are z-rank sorted inside a cell)
+      int lo = s, hi = e;
+      while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (t.pk[m].zr < q.wlo) lo = m + 1; else hi = m;
+      }
+      const int first = lo;
+      hi = e;
+      while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (t.pk[m].zr < q.whi) lo = m + 1; else hi = m;
+      }
+      const float ox = (float)(cx - q.cx) * sx - q.fx;
+      for (int j = first; j < lo; ++j) {
+        const PackedPoint p = t.pk[j];
+        bool hit;
+        if (!boxed) {
+          const float hx = kHalfDeg2RadF * (p.fx + ox), hy = kHalfDeg2RadF * (p.fy + oy);
+          const float sl = hx * (1.0f - hx * hx * (1.0f / 6.0f)), sd = hy * (1.0f - hy * hy * (1.0f / 6.0f));
+          const float a = sd * sd + (q.fcos * p.fcos) * (sl * sl);
+          if (a < q.T_lo) hit = true;
+          else if (a > q.T_hi) hit = false;
+          else hit = bt.inside(cl.ra[j - d], cl.dec[j - d], cl.cosdec[j - d]);
+        } else {
+          const double pra = cl.ra[j - d], pdec = cl.dec[j - d];
+          hit = bx.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j - d]);
+        }
+        count += hit ? 1 : 0;
       }
       s = e;
     }
   }
   return count;
+}
+
+// fp32 thresholds of a bubble of radius r_deg: pairs with a = sin^2(d/2) outside [T_lo, T_hi] are decided in fp32.
+// The band covers the rounding of the packed offsets (a few 1e-8 deg against r_deg) with two orders of magnitude to spare.
+__device__ __forceinline__ void tile_thresholds(double r_deg, double cell_deg, float* T_lo, float* T_hi) {
+  const double sh = sin(0.5 * r_deg * kDeg2Rad);
+  const double T = sh * sh;
+  const double band = fmax(1.0e-4, 1.0e-5 * cell_deg / r_deg);
+  *T_lo = (float)(T * (1.0 - band));
+  *T_hi = (float)(T * (1.0 + band));
 }
 
 }  // namespace fofb
