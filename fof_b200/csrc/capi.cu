@@ -385,6 +385,7 @@ int fofb_fof_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxi
   FOFB_CUDA(cudaSetDevice(h->device));
   if (!h->fof) h->fof = new FofState();
   h->fof->ran = h->fof->finished = false;
+  h->fof->adopt(nullptr, nullptr);
   Timed timer(h);
   // the state owns its copies: other entry points on this handle reuse h->upload between run / finish / fetch
   const View G = to_device(h, *galaxies, h->fof->g_store);
@@ -394,8 +395,8 @@ int fofb_fof_run(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxi
   timer.stop();
   if (n_clusters) *n_clusters = h->fof->merged.K;
   if (bbox) {
-    bbox[0] = h->fof->cat.gbox.ra_min; bbox[1] = h->fof->cat.gbox.ra_max;
-    bbox[2] = h->fof->cat.gbox.dec_min; bbox[3] = h->fof->cat.gbox.dec_max;
+    bbox[0] = h->fof->cat_().gbox.ra_min; bbox[1] = h->fof->cat_().gbox.ra_max;
+    bbox[2] = h->fof->cat_().gbox.dec_min; bbox[3] = h->fof->cat_().gbox.dec_max;
   }
   return FOFB_OK;
   FOFB_CATCH(h)
@@ -774,8 +775,8 @@ int fofb_dist_prepare(fofb_handle* h, const double* centres, int64_t n_centres, 
   P.fof.prepare(h, P.params, P.Gv, Cv, o);
   timer.stop();
   if (local_bbox4) {  // bounding box of this process's FoF() rows; the driver reduces it over processes
-    local_bbox4[0] = P.fof.cat.gbox.ra_min; local_bbox4[1] = P.fof.cat.gbox.ra_max;
-    local_bbox4[2] = P.fof.cat.gbox.dec_min; local_bbox4[3] = P.fof.cat.gbox.dec_max;
+    local_bbox4[0] = P.fof.cat_().gbox.ra_min; local_bbox4[1] = P.fof.cat_().gbox.ra_max;
+    local_bbox4[2] = P.fof.cat_().gbox.dec_min; local_bbox4[3] = P.fof.cat_().gbox.dec_max;
   }
   return FOFB_OK;
   FOFB_CATCH(h)

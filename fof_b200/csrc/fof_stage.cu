@@ -1079,7 +1079,9 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
   m = (int)Cn.rows;
   const int B = 256;
   const Cosmo cosmo = device_cosmo(h, p);
-  cat.build(h, G);
+  Catalog& cat = cat_();
+  if (catp == &cat_own) cat.build(h, G);
+  FOFB_REQUIRE(cat.n == G.rows, "adopted catalogue does not match the FoF() rows");
   CatalogView cv = cat.view();
   k_cos_row<<<grid_for(n, B), B, 0, st>>>(n, cat.dec_row.p, cos_row.alloc(n));
   FOFB_LAUNCH_CHECK(h);
@@ -1110,7 +1112,9 @@ void FofState::prepare(fofb_handle* h, const fofb_params& p, const View& G_in, c
   FOFB_REQUIRE(std::isfinite(R1max) && R1max > 0 && std::isfinite(r2[1]) && r2[1] > 0,
                "non-finite search radius (check centre redshifts)");
   big.build(h, cat, R1max);
-  small.build(h, cat, r2[1], true);  // packed records: the overdensity counts run on tiles (overlap.cu)
+  // packed records: the overdensity counts run on tiles (overlap.cu).  A lent list serves if its cells are large enough.
+  if (smallp != &small_own && !(smallp->built && smallp->has_packed && smallp->radius >= r2[1])) smallp = &small_own;
+  if (smallp == &small_own) small_own.build(h, cat, r2[1], true);
 
   // tracker kill targets
   {
@@ -1251,6 +1255,7 @@ void FofState::round_evaluate(fofb_handle* h) {
   const int B = 256;
   if (na <= 0) return;
   const Cosmo cosmo = device_cosmo(h, p);
+  Catalog& cat = cat_();
   CatalogView cv = cat.view();
   CentreCells cc{cc_ra0, cc_dec0, 1.0 / cc_sra, 1.0 / cc_sdec, cc_ncx, cc_ncy, cc_start.p, cc_idx.p, cc_z.p, cc_a.p, cc_b.p};
   CellListView clbig = big.view();

@@ -20,9 +20,19 @@ struct FofState {
   int n = 0, m = 0;
   View G, Cn;
   DBuf<double> g_store, c_store;  // fofb_fof_run: host matrices are staged here, not in the handle's shared buffers
-  Catalog cat;
-  CellList big;    // sized for the stage-1 virial search radius
-  CellList small;  // sized for theta_0.5 (overdensity counts)
+  Catalog cat_own;
+  CellList big;        // sized for the stage-1 virial search radius
+  CellList small_own;  // sized for theta_0.5 (overdensity counts)
+  // The whole-job pipeline has already sorted these very rows and built the theta_0.5 cell list for stage 0: when
+  // no row was cut between stage 0 and FoF() it lends them (adopt) instead of having them built a second time.
+  Catalog* catp = &cat_own;
+  CellList* smallp = &small_own;
+  void adopt(Catalog* c, CellList* s) {
+    catp = c ? c : &cat_own;
+    smallp = (c && s) ? s : &small_own;
+  }
+  Catalog& cat_() { return *catp; }
+  const Catalog& cat_() const { return *catp; }
   fofb_params params{};
 
   // per-centre (index = priority)

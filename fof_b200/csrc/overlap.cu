@@ -507,7 +507,7 @@ void fof_bcg_check(fofb_handle* h, FofState& S) {
     int* fired = sc.selcount.alloc(1);
     FOFB_CUDA(cudaMemsetAsync(fired, 0, sizeof(int), st));
     k_bcg_check<<<grid_for((int64_t)S.merged.K * 32, 128), 128, 0, st>>>(
-        S.merged.K, S.merged.centre.p, S.merged.off.p, S.merged.rows.p, S.G, S.cat.ra_row.p, S.cat.dec_row.p, S.cos_row.p,
+        S.merged.K, S.merged.centre.p, S.merged.off.p, S.merged.rows.p, S.G, S.cat_().ra_row.p, S.cat_().dec_row.p, S.cos_row.p,
         S.c_ra.p, S.c_dec.p, S.c_cos.p, S.c_thvir.p, S.c_mag.p, S.c_id.p, p.bcg_fraction, p.grid_cells, fired);
     FOFB_LAUNCH_CHECK(h);
     if (d2h_scalar(h, fired) != 0)
@@ -949,6 +949,7 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
   }
   double* pts = unit_pts.alloc((size_t)total * 2);
   // the box helper.py:197-202 draws from: min/max of galaxy_data (all processes' FoF() rows when distributed)
+  const Catalog& cat = cat_();
   const BBox pb = have_global_bbox ? global_bbox : cat.gbox;
   const double ra_range = pb.ra_max - pb.ra_min, dec_range = pb.dec_max - pb.dec_min;
   const double ra_lo = pb.ra_min, dec_lo = pb.dec_min;
@@ -994,6 +995,7 @@ void FofState::finish_unit(fofb_handle* h, const double* u, int mem) {
     du = a;
   }
   double* pts = unit_pts.alloc((size_t)total * 2);
+  const Catalog& cat = cat_();
   // volatile-free host arithmetic: high - low is one rounding, as in numpy
   const double ra_range = cat.gbox.ra_max - cat.gbox.ra_min, dec_range = cat.gbox.dec_max - cat.gbox.dec_min;
   k_scale_points<<<grid_for(total, 256), 256, 0, st>>>(total, npts, du, cat.gbox.ra_min, ra_range, cat.gbox.dec_min,
@@ -1025,6 +1027,7 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
     rdec = a + total;
   }
   const int B = 256;
+  const Catalog& cat = cat_();
   const int wblocks = grid_for((int64_t)K * 32, 128);
   int* N_own = merged.N.alloc(K);
   double* D = merged.D.alloc(K);
@@ -1035,7 +1038,7 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   FOFB_LAUNCH_CHECK(h);
   int* counts = sc.ev_a.alloc((size_t)total);
   FOFB_REQUIRE(total < (1ll << 31), "too many overdensity sample points");
-  const CellListView scl = small.view();
+  const CellListView scl = smallp->view();
   unsigned* qk = reinterpret_cast<unsigned*>(sc.ev_c.alloc((size_t)total));
   unsigned* qk2 = reinterpret_cast<unsigned*>(sc.ev_loser.alloc((size_t)total));
   int* qv = sc.kidx.alloc((size_t)total);

@@ -256,6 +256,8 @@ void Pipeline::stage0_and_inputs(fofb_handle* h, const fofb_params& p, const Vie
   if (m_c > 0) {
     FOFB_PROFILED(h, "k_build_rows", k_build_rows<<<grid_for((int64_t)m_c * ocols, B), B, 0, st>>>(m_c, csrc, raw, s0.N_row.p, C, ocols));
   }
+  // FoF() rows == stage-0 rows (nothing cut): the z-sorted catalogue and the theta_0.5 cell list are shared
+  if (n_g == n) fof.adopt(&cat, &cells); else fof.adopt(nullptr, nullptr);
   Gv.data = G; Gv.rows = n_g; Gv.cols = ocols; Gv.rs = ocols; Gv.cs = 1;
   Cv.data = C; Cv.rows = m_c; Cv.cols = ocols; Cv.rs = ocols; Cv.cs = 1;
 }

@@ -515,3 +515,70 @@ def find_clusters_distributed(galaxy_data, comm=None, handle=None, **kw):
     if kw.get("mt_state") is not None:
         cat.mt_state = res[6]
     return cat
+
+
+# ------------------------------------------------------------------------------------------------------
+# transitive mode (union-find) over slabs: per-GPU forests merged through the communicator
+# ------------------------------------------------------------------------------------------------------
+def friends_of_friends_slabs(local_rows, global_row, own, comm, handle, linking_length=0.5, max_velocity=None):
+    """Connected components of ONE catalogue held as redshift slabs (fofb_transitive_labels per rank + a merge).
+
+    Every rank holds its own redshift interval ``own`` widened by one velocity window (``plan_slab``'s *valid* interval
+    is enough; more does no harm): a link needs each galaxy inside the other's window, so every link that touches an
+    owned row has both ends on that rank.  The rank labels its rows with the lock-free union-find of K14; a local label
+    is the smallest held row of the local component.  Rows held by two ranks tie their two local components together:
+    those (row, label) pairs are all-gathered, the label pairs of one row become edges, and a replicated min-label
+    propagation with pointer jumping (the same hook-and-jump scheme, on the few boundary labels) runs to its fixpoint.
+    Returns (labels int64[n_own] = smallest GLOBAL row of each owned row's component, owned global rows int64[n_own]);
+    together over all ranks they equal the single-GPU ``fofb_transitive_labels`` of the whole table."""
+    import torch
+    h = handle
+    dev = torch.device("cuda", h.device)
+    i64 = torch.int64
+    p = _lib.default_params(H0=P.cosmo.H0, Om0=P.cosmo.Om0, Ode0=P.cosmo.Ode0,
+                            max_velocity=as_float(P.max_velocity if max_velocity is None else max_velocity, "km/s"))
+    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64) if not hasattr(local_rows, "data_ptr") else local_rows
+    m, keep = _lib.matrix_of(local_rows)
+    n_loc = int(m.rows)
+    lab32 = torch.empty(max(n_loc, 1), dtype=torch.int32, device=dev)[:n_loc]
+    g, l = C.c_int64(), C.c_int64(-1)
+    h.check(h.lib.fofb_transitive_labels(h.h, C.byref(p), C.byref(m), float(as_float(linking_length)), lab32.data_ptr(), 1,
+                                         C.byref(g), None))
+    del keep
+    grow = global_row.to(dev) if hasattr(global_row, "data_ptr") else torch.from_numpy(np.asarray(global_row, dtype=np.int64)).to(dev)
+    z = local_rows[:, 2] if hasattr(local_rows, "data_ptr") else torch.from_numpy(local_rows[:, 2].copy()).to(dev)
+    glab = grow[lab32.long()]                       # local root -> its global row (rows are held in global row order)
+    owned = (z >= own[0]) & (z < own[1])
+    if comm.world == 1:
+        return glab[owned].cpu().numpy(), grow[owned].cpu().numpy()
+    # rows another rank may hold as well: everything outside the own interval, and the own rows within two windows of
+    # the interval's ends (a neighbour holds at most its own interval widened twice, see plan_slab)
+    beta = float(p.max_velocity) / C_KMS
+    lo2 = _widen(*_widen(own[0], own[0], beta), beta)[0]
+    hi2 = _widen(*_widen(own[1], own[1], beta), beta)[1]
+    lo_edge = own[0] + (own[0] - lo2) * 1.05 if np.isfinite(own[0]) else own[0]
+    hi_edge = own[1] - (hi2 - own[1]) * 1.05 if np.isfinite(own[1]) else own[1]
+    shared = (~owned) | (z <= lo_edge) | (z >= hi_edge)
+    pairs = torch.stack([grow[shared], glab[shared]], dim=1)
+    allp = torch.cat(comm.allgatherv_t(pairs), dim=0)
+    # edges between the labels different ranks gave to one row
+    order = torch.argsort(allp[:, 0], stable=True)
+    rows_s, labs_s = allp[order, 0], allp[order, 1]
+    same = rows_s[1:] == rows_s[:-1]
+    ea, eb = labs_s[:-1][same], labs_s[1:][same]
+    # dense ids for the labels that occur, then min-label hooking + pointer jumping to the fixpoint
+    uniq, inv = torch.unique(torch.cat([ea, eb, glab]), return_inverse=True)
+    ia, ib, il = inv[: len(ea)], inv[len(ea): 2 * len(ea)], inv[2 * len(ea):]
+    parent = torch.arange(len(uniq), device=dev, dtype=i64)   # uniq is sorted: a smaller id is a smaller global row
+    while len(ea):
+        pa, pb = parent[ia], parent[ib]
+        lo_p = torch.minimum(pa, pb)
+        before = parent.clone()
+        parent.scatter_reduce_(0, pa, lo_p, reduce="amin")
+        parent.scatter_reduce_(0, pb, lo_p, reduce="amin")
+        parent = parent[parent]                                  # pointer jumping
+        parent = parent[parent]
+        if torch.equal(parent, before):
+            break
+    final = uniq[parent[il]]
+    return final[owned].cpu().numpy(), grow[owned].cpu().numpy()

@@ -35,6 +35,24 @@ def main(path):
             if col in names:
                 i = names.index(col)
                 e[key] = f"{r[i]} {units[i]}".strip()
+        # the three largest warp-stall reasons (cycles a warp waits per issued instruction, by reason)
+        stalls = []
+        for i, nm in enumerate(names):
+            if nm.startswith("smsp__average_warps_issue_stalled_") and nm.endswith("_per_issue_active.ratio") and "not_issued" not in nm:
+                try:
+                    stalls.append((float(r[i].replace(",", "")), nm[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        stalls.sort(reverse=True)
+        e["top_stalls"] = ", ".join(f"{n} {v:.2f}" for v, n in stalls[:4])
+        for col, key in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                         ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
+                         ("smsp__inst_executed_pipe_fp64.sum", "fp64_warp_insts"),
+                         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
+                         ("launch__occupancy_limit_shared_mem", "occ_limit_smem"), ("launch__occupancy_limit_registers", "occ_limit_regs"),
+                         ("sm__warps_active.avg.per_cycle_active", "warps_per_cycle")):
+            if col in names:
+                e[key] = r[names.index(col)]
         out.append(e)
     print(json.dumps(out, indent=1))
 

@@ -112,3 +112,46 @@ def test_two_process_nccl_slabs_equal_single_gpu(lib, tmp_path):
         assert np.array_equal(got["N"], ref.N) and np.array_equal(got["D"], ref.D)
         np.testing.assert_allclose(got["props"], ref.props, rtol=1e-12)
         assert np.array_equal(got["key"], ref_state[1]) and int(got["pos"]) == ref_state[2]
+
+
+def _run_uf_ranks(arr, world, ll):
+    from fof_b200 import _lib, distributed as D
+    comms = D.ThreadComm.group(world)
+    edges = D.slab_edges(arr[:, 2], world)
+    out = [None] * world
+    err = []
+
+    def work(r):
+        try:
+            h = _lib.Handle(0)
+            own, valid, local = D.plan_slab(edges, r, 2000.0)
+            rows = np.nonzero((arr[:, 2] >= valid[0]) & (arr[:, 2] <= valid[1]))[0]
+            out[r] = D.friends_of_friends_slabs(arr[rows], rows, own, comms[r], h, linking_length=ll)
+            h.close()
+        except Exception as e:  # pragma: no cover
+            err.append(e)
+            comms[r].s.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if err:
+        raise err[0]
+    return out
+
+
+@pytest.mark.parametrize("n,seed,kind,ll", [(60000, 5, "cosmos", 0.4), (40000, 6, "dense", 0.8)])
+def test_union_find_forests_merge_across_slabs(lib, n, seed, kind, ll):
+    """Transitive mode over slabs: per-rank union-find forests, boundary (row, label) pairs exchanged, replicated merge.
+    The labels of the owned rows of 2, 3 and 4 ranks together must equal the single-GPU labels (min row of the component)."""
+    from fof_b200 import transitive
+    arr = make_catalog(n, seed=seed, kind=kind, as_frame=False)
+    want, n_groups, _ = transitive.friends_of_friends(arr, linking_length=ll, count_links=False)
+    assert np.unique(want, return_counts=True)[1].max() > 20
+    for world in (2, 3, 4):
+        parts = _run_uf_ranks(arr, world, ll)
+        got = np.full(n, -1, dtype=np.int64)
+        for lab, rows in parts:
+            assert (got[rows] == -1).all()          # every row is owned by exactly one rank
+            got[rows] = lab
+        assert np.array_equal(got, want.astype(np.int64))
