@@ -161,6 +161,12 @@ __global__ void k_cc_pack(int m, const int* idx, const double* c_ra, const doubl
 // in j's velocity window and within j's virial search radius (members are a subset of virial_points,
 // fof.py:180-228).  i is ready when no alive, undecided such j exists.  Cells are z-sorted, so only the
 // centres whose window can contain the galaxy are visited.
+// The scan is a chain of dependent loads (cell table -> binary search -> candidate record -> its tracker bytes), and a
+// thread runs it alone: what bounds the kernel is memory latency, not bandwidth or issue slots.  So the loads are
+// issued in independent groups: the binary searches of all (up to 9) neighbour cells advance in lockstep, and the
+// candidates of a cell are fetched four at a time, records first, then their tracker bytes, before any is judged.
+constexpr int kReadyCells = 9, kReadyBatch = 4;
+
 __global__ void k_ready(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
                         const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
                         const unsigned char* alive, const unsigned char* decided, const long long* t_off, const int* t_rows,
@@ -192,31 +198,66 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
     x0 = max(x0, 0); y0 = max(y0, 0);
     x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
     const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
-    for (int cidx = c0 > 0 ? c0 : 0; cidx < ncells && !blocked; ++cidx) {
-      const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
-      int lo = cc.start[yy * cc.ncx + xx];
-      const int e = cc.start[yy * cc.ncx + xx + 1];
-      if (cidx == c0) {
-        lo = k0;
-      } else {
-        int hi = e;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
+    for (int cbase = c0 > 0 ? c0 : 0; cbase < ncells && !blocked; cbase += kReadyCells) {
+      // candidate range [lo, e) of each cell of the group: entries with zlo <= z_j (the upper end is checked on the way)
+      int lo[kReadyCells], e[kReadyCells];
+#pragma unroll
+      for (int u = 0; u < kReadyCells; ++u) {
+        const int cidx = cbase + u;
+        lo[u] = e[u] = 0;
+        if (cidx < ncells) {
+          const int cell = (y0 + cidx / nx) * cc.ncx + x0 + cidx % nx;
+          lo[u] = cc.start[cell];
+          e[u] = cc.start[cell + 1];
+        }
       }
-      for (int k = lo; k < e; ++k) {
-        const double4 ca = cc.a[k];
-        if (ca.z > zhi) break;
-        const int j = (int)__double_as_longlong(ca.w);
-        if (j >= i || !alive[j] || decided[j]) continue;
-        if (fabs(redshift_to_velocity(z, ca.z)) > vmax) continue;
-        const double4 cb = cc.b[k];
-        BubbleTest bt;
-        bt.init_T(ca.x, ca.y, cb.x, cb.y, cb.z);
-        if (bt.inside(ra, dec, cs)) {
-          blocked = true;
-          resume_row[i] = r;
-          resume_cell[i] = cidx;
-          resume_k[i] = k;
-          break;
+      int hi[kReadyCells];
+#pragma unroll
+      for (int u = 0; u < kReadyCells; ++u) {
+        hi[u] = e[u];
+        if (cbase + u == c0) { lo[u] = k0; hi[u] = k0; }  // the stored scan position: no search
+      }
+      for (bool any = true; any;) {
+        any = false;
+#pragma unroll
+        for (int u = 0; u < kReadyCells; ++u)
+          if (lo[u] < hi[u]) {
+            const int mid = (lo[u] + hi[u]) >> 1;
+            if (cc.z[mid] < zlo) lo[u] = mid + 1; else hi[u] = mid;
+            any = true;
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < kReadyCells; ++u) {
+        if (blocked) break;
+        for (int k = lo[u]; k < e[u] && !blocked; k += kReadyBatch) {
+          double4 ca[kReadyBatch];
+          bool live[kReadyBatch];
+#pragma unroll
+          for (int v = 0; v < kReadyBatch; ++v) ca[v] = k + v < e[u] ? cc.a[k + v] : make_double4(0.0, 0.0, INFINITY, 0.0);
+#pragma unroll
+          for (int v = 0; v < kReadyBatch; ++v) {
+            const int j = (int)__double_as_longlong(ca[v].w);
+            live[v] = ca[v].z <= zhi && j < i && alive[j] && !decided[j];
+          }
+          bool past = false;
+#pragma unroll
+          for (int v = 0; v < kReadyBatch; ++v) {
+            if (blocked || past) break;
+            if (ca[v].z > zhi) { past = true; break; }  // cells are z-sorted: nothing further in this cell
+            if (!live[v]) continue;
+            if (fabs(redshift_to_velocity(z, ca[v].z)) > vmax) continue;
+            const double4 cb = cc.b[k + v];
+            BubbleTest bt;
+            bt.init_T(ca[v].x, ca[v].y, cb.x, cb.y, cb.z);
+            if (bt.inside(ra, dec, cs)) {
+              blocked = true;
+              resume_row[i] = r;
+              resume_cell[i] = cbase + u;
+              resume_k[i] = k + v;
+            }
+          }
+          if (past) break;
         }
       }
     }
