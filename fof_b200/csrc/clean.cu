@@ -625,8 +625,9 @@ __global__ void k_member_trig(long long total, View M, double4* trig) {
   trig[t] = make_double4(sl, cl, sp, cp);
 }
 
-constexpr int kVirialThreads = 256;
-constexpr int kVirialTrig = 512;  // clusters up to this size keep their members' sines and cosines in shared memory
+constexpr int kVirialThreads = 128;
+constexpr int kVirialCache = 512;  // clusters up to this size keep z, z errors and v^2 in shared memory
+constexpr int kVirialTrig = 256;   // and up to this size their members' sines and cosines too  // clusters up to this size keep their members' sines and cosines in shared memory
 constexpr int kBootNum = 100;
 
 // One CTA per cluster.
@@ -734,9 +735,9 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   // The cluster's redshifts, redshift errors and v^2 live in shared memory (clusters of up to 1024 members; longer
   // ones read the member matrix): thread 0's numpy-ordered sums below are chains of dependent loads, which cost a
   // shared-memory access each instead of a cache round trip.
-  __shared__ double sv2[1024], s_z[1024], s_e[1024];
+  __shared__ double sv2[kVirialCache], s_z[kVirialCache], s_e[kVirialCache];
   __shared__ double4 s_trig[kVirialTrig];
-  const bool cached = n <= 1024;
+  const bool cached = n <= kVirialCache;
   const bool trig_cached = n <= kVirialTrig;
   if (cached)
     for (int i = tid; i < n; i += kVirialThreads) {

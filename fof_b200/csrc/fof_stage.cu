@@ -165,7 +165,14 @@ __global__ void k_cc_pack(int m, const int* idx, const double* c_ra, const doubl
 // thread runs it alone: what bounds the kernel is memory latency, not bandwidth or issue slots.  So the loads are
 // issued in independent groups: the binary searches of all (up to 9) neighbour cells advance in lockstep, and the
 // candidates of a cell are fetched four at a time, records first, then their tracker bytes, before any is judged.
-constexpr int kReadyCells = 9, kReadyBatch = 4;
+// one copy of the bubble test for the readiness scan (kept out of line on purpose)
+__device__ __noinline__ bool bubble_inside(double cra, double cdec, double ccos, double R1, double T1, double ra, double dec, double cs) {
+  BubbleTest bt;
+  bt.init_T(cra, cdec, ccos, R1, T1);
+  return bt.inside(ra, dec, cs);
+}
+
+constexpr int kReadyCells = 3, kReadyBatch = 4, kReadyThreads = 128;
 
 __global__ void k_ready(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
                         const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
@@ -173,6 +180,7 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
                         const double* ra_row, const double* dec_row,
                         const double* cos_row, const double* z_row, double vmax, double R1max, int* ready_flag,
                         int* resume_row, int* resume_cell, int* resume_k) {
+  __shared__ int s_lo[kReadyCells][kReadyThreads], s_e[kReadyCells][kReadyThreads];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= na) return;
   const int i = active[t];
@@ -198,6 +206,7 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
     x0 = max(x0, 0); y0 = max(y0, 0);
     x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
     const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
+    // cells are taken in groups of kReadyCells; a stored scan position is the first cell of its group
     for (int cbase = c0 > 0 ? c0 : 0; cbase < ncells && !blocked; cbase += kReadyCells) {
       // candidate range [lo, e) of each cell of the group: entries with zlo <= z_j (the upper end is checked on the way)
       int lo[kReadyCells], e[kReadyCells];
@@ -227,35 +236,46 @@ __global__ void k_ready(int na, const int* active, CentreCells cc, const double*
             any = true;
           }
       }
+      // the ranges go through shared memory so that the candidate loop below exists once (not once per cell: the bubble
+      // test is a large body, and copies of it thrash the instruction cache)
 #pragma unroll
       for (int u = 0; u < kReadyCells; ++u) {
-        if (blocked) break;
-        for (int k = lo[u]; k < e[u] && !blocked; k += kReadyBatch) {
+        s_lo[u][threadIdx.x] = lo[u];
+        s_e[u][threadIdx.x] = e[u];
+      }
+#pragma unroll 1
+      for (int u = 0; u < kReadyCells && !blocked; ++u) {
+        const int ce = s_e[u][threadIdx.x];
+#pragma unroll 1
+        for (int k = s_lo[u][threadIdx.x]; k < ce && !blocked; k += kReadyBatch) {
           double4 ca[kReadyBatch];
           bool live[kReadyBatch];
 #pragma unroll
-          for (int v = 0; v < kReadyBatch; ++v) ca[v] = k + v < e[u] ? cc.a[k + v] : make_double4(0.0, 0.0, INFINITY, 0.0);
+          for (int v = 0; v < kReadyBatch; ++v) ca[v] = k + v < ce ? cc.a[k + v] : make_double4(0.0, 0.0, INFINITY, 0.0);
 #pragma unroll
           for (int v = 0; v < kReadyBatch; ++v) {
             const int j = (int)__double_as_longlong(ca[v].w);
             live[v] = ca[v].z <= zhi && j < i && alive[j] && !decided[j];
           }
+          // which of the four is the first that blocks (or ends the cell)?  The bubble test itself is not unrolled.
           bool past = false;
+          int hit = -1;
 #pragma unroll
           for (int v = 0; v < kReadyBatch; ++v) {
-            if (blocked || past) break;
-            if (ca[v].z > zhi) { past = true; break; }  // cells are z-sorted: nothing further in this cell
+            if (hit >= 0 || past) continue;
+            if (ca[v].z > zhi) { past = true; continue; }  // cells are z-sorted: nothing further in this cell
             if (!live[v]) continue;
             if (fabs(redshift_to_velocity(z, ca[v].z)) > vmax) continue;
             const double4 cb = cc.b[k + v];
-            BubbleTest bt;
-            bt.init_T(ca[v].x, ca[v].y, cb.x, cb.y, cb.z);
-            if (bt.inside(ra, dec, cs)) {
-              blocked = true;
-              resume_row[i] = r;
-              resume_cell[i] = cbase + u;
-              resume_k[i] = k + v;
-            }
+            const double dd = fabs(ca[v].y - dec);
+            if (dd > cb.y * 1.000001) continue;  // farther in declination than j's radius: cannot be inside
+            if (bubble_inside(ca[v].x, ca[v].y, cb.x, cb.y, cb.z, ra, dec, cs)) hit = v;
+          }
+          if (hit >= 0) {
+            blocked = true;
+            resume_row[i] = r;
+            resume_cell[i] = cbase + u;
+            resume_k[i] = k + hit;
           }
           if (past) break;
         }
@@ -1306,7 +1326,7 @@ void FofState::round_evaluate(fofb_handle* h) {
     ++rounds;
     int* fl = flags.alloc((size_t)na);
     if (na > 8192) {
-      FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
+      FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, kReadyThreads), kReadyThreads, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
                                                t_off.p, t_rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
                                                p.max_velocity, R1max, fl, resume_row.p, resume_cell.p, resume_k.p));
     } else {
