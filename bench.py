@@ -49,6 +49,9 @@ ALGO_BYTES = {
     "k_build_rows": ("galaxy", 64 + 64 + 8),
     "k_kill_targets": ("galaxy", 8 + 4),
     "k_ready": ("candidate_centre", 36),
+    "k_ready_r1": ("candidate_centre", 36),
+    "k_ready_warp": ("candidate_centre", 36),
+    "k_hop2_front": ("stage1_member", 1 + 4),
     "k_centre_prep": ("candidate_centre", 64 + 96),
     "k_virial_count": ("stage1_member", 28),
     "k_virial_fill": ("stage1_member", 28 + 8),

@@ -161,6 +161,73 @@ __global__ void k_cc_pack(int m, const int* idx, const double* c_ra, const doubl
 // in j's velocity window and within j's virial search radius (members are a subset of virial_points,
 // fof.py:180-228).  i is ready when no alive, undecided such j exists.  Cells are z-sorted, so only the
 // centres whose window can contain the galaxy are visited.
+// The scan taken cell by cell and candidate by candidate: the least work when a blocker turns up early, as it does
+// for almost every centre of the first rounds (two million threads hide each other's latency).
+__global__ void k_ready_lazy(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
+                        const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
+                        const unsigned char* alive, const unsigned char* decided, const long long* t_off, const int* t_rows,
+                        const double* ra_row, const double* dec_row,
+                        const double* cos_row, const double* z_row, double vmax, double R1max, int* ready_flag,
+                        int* resume_row, int* resume_cell, int* resume_k) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= na) return;
+  const int i = active[t];
+  // centre i is switched off when a galaxy row carrying its column-4 value joins a cluster (Q3)
+  const int nrows = (int)(t_off[i + 1] - t_off[i]);
+  if (nrows == 0) { ready_flag[t] = 1; return; }
+  const int* rows = t_rows + t_off[i];
+  // |v(z; z_j)| <= vmax  =>  (z - beta)/(1 + beta) <= z_j <= (z + beta)/(1 - beta), beta = vmax/c (+ margin)
+  const double beta = vmax / kCkms;
+  // A candidate that does not block now never will again (alive only falls, decided only rises), so the scan resumes
+  // where the previous round found its blocker instead of starting over: one pass per centre over all rounds.  The
+  // rows are walked in list order; a row whose scan ended without a blocker is done for good.
+  int c0 = resume_cell[i], k0 = resume_k[i];
+  bool blocked = false;
+  for (int r = resume_row[i]; r < nrows && !blocked; ++r) {
+    const int g = rows[r];
+    const double ra = ra_row[g], dec = dec_row[g], cs = cos_row[g], z = z_row[g];
+    const double zlo = (z - beta) / (1.0 + beta) - 1e-9, zhi = (z + beta) / (1.0 - beta) + 1e-9;
+    const double reach = ra_reach(R1max, dec);
+    int x0 = (int)floor((ra - reach - cc.ra0) * cc.inv_sra), x1 = (int)floor((ra + reach - cc.ra0) * cc.inv_sra);
+    int y0 = (int)floor((dec - R1max * 1.000001 - cc.dec0) * cc.inv_sdec),
+        y1 = (int)floor((dec + R1max * 1.000001 - cc.dec0) * cc.inv_sdec);
+    x0 = max(x0, 0); y0 = max(y0, 0);
+    x1 = min(x1, cc.ncx - 1); y1 = min(y1, cc.ncy - 1);
+    const int nx = x1 - x0 + 1, ncells = nx * (y1 - y0 + 1);
+    for (int cidx = c0 > 0 ? c0 : 0; cidx < ncells && !blocked; ++cidx) {
+      const int yy = y0 + cidx / nx, xx = x0 + cidx % nx;
+      int lo = cc.start[yy * cc.ncx + xx];
+      const int e = cc.start[yy * cc.ncx + xx + 1];
+      if (cidx == c0) {
+        lo = k0;
+      } else {
+        int hi = e;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cc.z[mid] < zlo) lo = mid + 1; else hi = mid; }
+      }
+      for (int k = lo; k < e; ++k) {
+        const double4 ca = cc.a[k];
+        if (ca.z > zhi) break;
+        const int j = (int)__double_as_longlong(ca.w);
+        if (j >= i || !alive[j] || decided[j]) continue;
+        if (fabs(redshift_to_velocity(z, ca.z)) > vmax) continue;
+        const double4 cb = cc.b[k];
+        BubbleTest bt;
+        bt.init_T(ca.x, ca.y, cb.x, cb.y, cb.z);
+        if (bt.inside(ra, dec, cs)) {
+          blocked = true;
+          resume_row[i] = r;
+          resume_cell[i] = cidx;
+          resume_k[i] = k;
+          break;
+        }
+      }
+    }
+    c0 = -1;  // the stored scan position belongs to the row it was found on
+  }
+  ready_flag[t] = blocked ? 0 : 1;
+}
+
+
 // The scan is a chain of dependent loads (cell table -> binary search -> candidate record -> its tracker bytes), and a
 // thread runs it alone: what bounds the kernel is memory latency, not bandwidth or issue slots.  So the loads are
 // issued in independent groups: the binary searches of all (up to 9) neighbour cells advance in lockstep, and the
@@ -1325,12 +1392,25 @@ void FofState::round_evaluate(fofb_handle* h) {
   {
     ++rounds;
     int* fl = flags.alloc((size_t)na);
+    // FOFB_READY=lazy|ilp forces one scan kernel (diagnostics); by default the big early rounds take the lazy scan and
+    // the later ones, whose few long scans are pure latency, the one with grouped loads
+    static const int ready_mode = [] {
+      const char* e = getenv("FOFB_READY");
+      return !e ? 0 : (e[0] == 'l' ? 1 : 2);
+    }();
     if (na > 8192) {
-      FOFB_PROFILED(h, "k_ready", k_ready<<<grid_for(na, kReadyThreads), kReadyThreads, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
+      const bool lazy = ready_mode == 1 || (ready_mode == 0 && na > (1 << 19));
+      if (lazy) {
+        FOFB_PROFILED(h, rounds == 1 ? "k_ready_r1" : "k_ready", k_ready_lazy<<<grid_for(na, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
                                                t_off.p, t_rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
                                                p.max_velocity, R1max, fl, resume_row.p, resume_cell.p, resume_k.p));
+      } else {
+        FOFB_PROFILED(h, rounds == 1 ? "k_ready_r1" : "k_ready", k_ready<<<grid_for(na, kReadyThreads), kReadyThreads, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
+                                               t_off.p, t_rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
+                                               p.max_velocity, R1max, fl, resume_row.p, resume_cell.p, resume_k.p));
+      }
     } else {
-      FOFB_PROFILED(h, "k_ready", k_ready_warp<<<grid_for((int64_t)na * 32, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
+      FOFB_PROFILED(h, "k_ready_warp", k_ready_warp<<<grid_for((int64_t)na * 32, 128), 128, 0, st>>>(na, act, cc, c_ra.p, c_dec.p, c_cos.p, c_z.p, c_R1.p, c_T1.p, alive.p, decided.p,
                                                t_off.p, t_rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p, cat.z_row.p,
                                                p.max_velocity, R1max, fl));
     }
