@@ -88,6 +88,9 @@ def load():
         "fofb_dist_state": (C.c_int, [vp, vp, vp, i32]),
         "fofb_dist_round_advance": (C.c_int, [vp, P(i64)]),
         "fofb_set_stream": (C.c_int, [vp, vp]),
+        "fofb_dist_overlap_events": (C.c_int, [vp, i64, vp, vp, i64, vp, P(i64)]),
+        "fofb_dist_overlap_events_fetch": (C.c_int, [vp, i64, vp, vp, vp]),
+        "fofb_dist_overlap_resolve": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
         "fofb_dist_state_pack": (C.c_int, [vp, i64, vp, vp, vp, i64]),
         "fofb_dist_state_unpack": (C.c_int, [vp, i64, vp, vp, vp]),
         "fofb_dist_round_advance2": (C.c_int, [vp, vp, i64, P(i64), P(i32)]),

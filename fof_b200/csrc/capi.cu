@@ -17,6 +17,11 @@ void fof_overlap_external(fofb_handle* h, FofState& S, int K, const int* centre,
 void fof_overlap_external_rows(fofb_handle* h, FofState& S, int K, const double* centre_rows, const long long* off, long long total,
                                const double* ids, int* keep_out);
 void fof_set_merged(fofb_handle* h, FofState& S, const int* keep_local);
+long long fof_overlap_events_rows(fofb_handle* h, FofState& S, int K, const double* centre_rows, const long long* off, long long total,
+                                  const double* ids);
+void fof_overlap_events_fetch(fofb_handle* h, FofState& S, long long E, int* ev_a, int* ev_c, int* ev_loser);
+void fof_overlap_resolve_external(fofb_handle* h, FofState& S, int K, long long E, const int* ev_a, const int* ev_c, const int* ev_loser,
+                                  int* keep_out);
 void mt19937_words(fofb_handle* h, unsigned* key_host, int* pos_host, long long n_words, unsigned* out, int out_mem);
 void dist_state_pack(fofb_handle* h, FofState& S, long long n_shared, const long long* lpos, const long long* bpos, unsigned char* buf,
                      long long n_buf);
@@ -943,6 +948,46 @@ int fofb_dist_overlap_rows(fofb_handle* h, int64_t K, const double* centre_rows,
   FOFB_REQUIRE(centre_rows && offsets && ids && keep, "fofb_dist_overlap_rows: null argument");
   FOFB_CUDA(cudaSetDevice(h->device));
   fof_overlap_external_rows(h, P.fof, (int)K, centre_rows, reinterpret_cast<const long long*>(offsets), total, ids, keep);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_overlap_events(fofb_handle* h, int64_t K, const double* centre_rows, const int64_t* offsets, int64_t total,
+                             const double* ids, int64_t* n_events) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(K >= 0 && K < (1ll << 31) && n_events, "fofb_dist_overlap_events: bad argument");
+  *n_events = 0;
+  if (K == 0) return FOFB_OK;
+  FOFB_REQUIRE(centre_rows && offsets && (ids || total == 0), "fofb_dist_overlap_events: null argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  *n_events = fof_overlap_events_rows(h, P.fof, (int)K, centre_rows, reinterpret_cast<const long long*>(offsets), total, ids);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_overlap_events_fetch(fofb_handle* h, int64_t n_events, int32_t* ev_a, int32_t* ev_c, int32_t* ev_loser) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(n_events >= 0 && (n_events == 0 || (ev_a && ev_c && ev_loser)), "fofb_dist_overlap_events_fetch: bad argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  fof_overlap_events_fetch(h, P.fof, n_events, ev_a, ev_c, ev_loser);
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_overlap_resolve(fofb_handle* h, int64_t K, int64_t n_events, const int32_t* ev_a, const int32_t* ev_c,
+                              const int32_t* ev_loser, int32_t* keep) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(K >= 0 && K < (1ll << 31) && n_events >= 0 && n_events < (1ll << 31), "fofb_dist_overlap_resolve: bad size");
+  if (K == 0) return FOFB_OK;
+  FOFB_REQUIRE(keep && (n_events == 0 || (ev_a && ev_c && ev_loser)), "fofb_dist_overlap_resolve: null argument");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  fof_overlap_resolve_external(h, P.fof, (int)K, n_events, ev_a, ev_c, ev_loser, keep);
   return FOFB_OK;
   FOFB_CATCH(h)
 }

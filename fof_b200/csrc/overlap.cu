@@ -357,14 +357,16 @@ __global__ void k_attrs_from_rows(int K, const double* rows, Cosmo cosmo, double
   iota[k] = k;
 }
 
-// Stage 2 on an arbitrary cluster list (centre index per cluster, CSR offsets, member ids): returns a device array of
-// K keep flags (non-zero = survives the contests).  `ext_ids` == nullptr: ids are column 6 of S.G at `rows`.
-static int* overlap_keep_flags(fofb_handle* h, FofState& S, const CentreAttrs& A, int K, const int* centre, const long long* off,
-                               long long total_members, const int* rows, const double* ext_ids) {
+// Stage 2, first half, on an arbitrary cluster list (centre index per cluster, CSR offsets, member ids): the ordered
+// list of contests.  Fills sc.ev_a / ev_c / ev_loser (cluster a, its partner c, the static loser or -1 when the contest
+// cannot fire), ordered by a and, within a, in GriSPy's return order; returns their number.
+// `ext_ids` == nullptr: ids are column 6 of S.G at `rows`.
+static long long overlap_events(fofb_handle* h, FofState& S, const CentreAttrs& A, int K, const int* centre, const long long* off,
+                                long long total_members, const int* rows, const double* ext_ids) {
   cudaStream_t st = h->stream;
   OverlapScratch& sc = scratch(S);
   const int B = 256;
-  if (K == 0) return nullptr;
+  if (K == 0) return 0;
   const fofb_params& p = S.params;
   size_t bytes = 0;
   // clusters sorted by centre redshift -> velocity windows over the candidate list
@@ -390,36 +392,55 @@ static int* overlap_keep_flags(fofb_handle* h, FofState& S, const CentreAttrs& A
   FOFB_LAUNCH_CHECK(h);
   const long long E = scan_offsets(h, elen, eoff, K);
   FOFB_REQUIRE(E < (1ll << 31), "too many overlap events");
-  // event states [0, E) followed by the per-cluster keep flags
-  int* keep_flags = sc.state.alloc((size_t)std::max<long long>(E, 1) + K + 8) + std::max<long long>(E, 1);
-  if (E > 0) {
-    unsigned long long* ekey = sc.ekey.alloc((size_t)E);
-    unsigned long long* ekey_s = sc.ekey_sorted.alloc((size_t)E);
-    k_overlap_events<1><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, A.ra, A.dec,
-                                                 A.cos, A.z, A.thvir, p.max_velocity, p.grid_cells, ecount, eoff, ekey);
+  if (E == 0) return 0;
+  unsigned long long* ekey = sc.ekey.alloc((size_t)E);
+  unsigned long long* ekey_s = sc.ekey_sorted.alloc((size_t)E);
+  k_overlap_events<1><<<wblocks, 128, 0, st>>>(K, centre, sc.kz_sorted.p, sc.kidx_sorted.p, A.ra, A.dec,
+                                               A.cos, A.z, A.thvir, p.max_velocity, p.grid_cells, ecount, eoff, ekey);
+  FOFB_LAUNCH_CHECK(h);
+  FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
+  FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
+  count_launch(h, 4);
+  // sorted member ids per candidate cluster
+  const long long total = total_members;
+  const double* ids = ext_ids;
+  if (!ids) {
+    double* own = sc.ids.alloc((size_t)total);
+    k_member_ids<<<grid_for(total, B), B, 0, st>>>(total, rows, S.G, own);
     FOFB_LAUNCH_CHECK(h);
-    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
-    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ekey, ekey_s, E, K, eoff, eoff + 1, st));
-    count_launch(h, 4);
-    // sorted member ids per candidate cluster
-    const long long total = total_members;
-    const double* ids = ext_ids;
-    if (!ids) {
-      double* own = sc.ids.alloc((size_t)total);
-      k_member_ids<<<grid_for(total, B), B, 0, st>>>(total, rows, S.G, own);
-      FOFB_LAUNCH_CHECK(h);
-      ids = own;
-    }
-    double* ids_s = sc.ids_sorted.alloc((size_t)total);
-    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ids, ids_s, total, K, off, off + 1, st));
-    FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ids, ids_s, total, K, off, off + 1, st));
-    count_launch(h, 4);
-    int* ev_a = sc.ev_a.alloc((size_t)E);
-    int* ev_c = sc.ev_c.alloc((size_t)E);
-    int* ev_l = sc.ev_loser.alloc((size_t)E);
-    int* state = sc.state.p;
-    FOFB_PROFILED(h, "k_event_static", k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, centre, A.id,
-                                                          A.N, A.mag, off, ids_s, ev_a, ev_c, ev_l, state));
+    ids = own;
+  }
+  double* ids_s = sc.ids_sorted.alloc((size_t)total);
+  FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, ids, ids_s, total, K, off, off + 1, st));
+  FOFB_CUDA(cub::DeviceSegmentedSort::SortKeys(cub_tmp(h, bytes), bytes, ids, ids_s, total, K, off, off + 1, st));
+  count_launch(h, 4);
+  int* ev_a = sc.ev_a.alloc((size_t)E);
+  int* ev_c = sc.ev_c.alloc((size_t)E);
+  int* ev_l = sc.ev_loser.alloc((size_t)E);
+  int* state = sc.state.alloc((size_t)E + K + 8);
+  FOFB_PROFILED(h, "k_event_static", k_event_static<<<grid_for(E * 32, 128), 128, 0, st>>>(K, E, eoff, ekey_s, sc.first_by_id.p, centre, A.id,
+                                                        A.N, A.mag, off, ids_s, ev_a, ev_c, ev_l, state));
+  return E;
+}
+
+__global__ void k_state_from_loser(long long E, const int* ev_loser, int* state) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) state[e] = ev_loser[e] >= 0 ? 0 : 2;
+}
+
+// Stage 2, second half: which clusters survive the ordered contests (ev_* in contest order, device arrays of E entries
+// with cluster indices in [0, K)).  Returns K keep flags (device; non-zero = survives).
+static int* overlap_resolve(fofb_handle* h, FofState& S, int K, long long E, const int* ev_a, const int* ev_c, const int* ev_l) {
+  cudaStream_t st = h->stream;
+  OverlapScratch& sc = scratch(S);
+  const int B = 256;
+  size_t bytes = 0;
+  // event states [0, E) followed by the per-cluster keep flags
+  int* state = sc.state.alloc((size_t)std::max<long long>(E, 1) + K + 8);
+  int* keep_flags = state + std::max<long long>(E, 1);
+  if (E > 0) {
+    k_state_from_loser<<<grid_for(E, B), B, 0, st>>>(E, ev_l, state);
+    FOFB_LAUNCH_CHECK(h);
     // per-cluster lists of the events it would lose, in event order
     unsigned long long* lkey = sc.lkey.alloc((size_t)E);
     unsigned long long* lkey_s = sc.lkey_sorted.alloc((size_t)E);
@@ -445,6 +466,14 @@ static int* overlap_keep_flags(fofb_handle* h, FofState& S, const CentreAttrs& A
     FOFB_CUDA(cudaMemsetAsync(keep_flags, 1, sizeof(int) * K, st));  // any non-zero value keeps
   }
   return keep_flags;
+}
+
+static int* overlap_keep_flags(fofb_handle* h, FofState& S, const CentreAttrs& A, int K, const int* centre, const long long* off,
+                               long long total_members, const int* rows, const double* ext_ids) {
+  if (K == 0) return nullptr;
+  OverlapScratch& sc = scratch(S);
+  const long long E = overlap_events(h, S, A, K, centre, off, total_members, rows, ext_ids);
+  return overlap_resolve(h, S, K, E, sc.ev_a.p, sc.ev_c.p, sc.ev_loser.p);
 }
 
 void fof_overlap_and_bcg(fofb_handle* h, FofState& S) {
@@ -486,6 +515,42 @@ void fof_overlap_external_rows(fofb_handle* h, FofState& S, int K, const double*
   int* keep = overlap_keep_flags(h, S, A, K, iota, off, total, nullptr, ids);
   FOFB_CUDA(cudaMemcpyAsync(keep_out, keep, sizeof(int) * K, cudaMemcpyDeviceToDevice, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
+}
+
+// Distributed stage 2, step 1: the contests of a cluster list that holds this process's clusters and the neighbours'
+// boundary clusters (centres as rows, K x 8, in global priority order).  Returns the number of contests; the arrays
+// stay in the scratch until fof_overlap_events_fetch copies them out.
+long long fof_overlap_events_rows(fofb_handle* h, FofState& S, int K, const double* centre_rows, const long long* off, long long total,
+                                  const double* ids) {
+  if (K == 0) return 0;
+  cudaStream_t st = h->stream;
+  OverlapScratch& sc = scratch(S);
+  double* buf = sc.attr.alloc((size_t)K * 8);
+  int* iota = sc.attr_iota.alloc(K);
+  const Cosmo cosmo = device_cosmo(h, S.params);
+  k_attrs_from_rows<<<grid_for(K, 256), 256, 0, st>>>(K, centre_rows, cosmo, S.params.virial_radius, buf, buf + K, buf + 2LL * K,
+                                                      buf + 3LL * K, buf + 4LL * K, buf + 5LL * K, buf + 6LL * K, buf + 7LL * K, iota);
+  FOFB_LAUNCH_CHECK(h);
+  const CentreAttrs A{buf, buf + K, buf + 2LL * K, buf + 3LL * K, buf + 4LL * K, buf + 5LL * K, buf + 6LL * K, buf + 7LL * K};
+  return overlap_events(h, S, A, K, iota, off, total, nullptr, ids);
+}
+
+void fof_overlap_events_fetch(fofb_handle* h, FofState& S, long long E, int* ev_a, int* ev_c, int* ev_loser) {
+  if (E <= 0) return;
+  OverlapScratch& sc = scratch(S);
+  cudaStream_t st = h->stream;
+  FOFB_CUDA(cudaMemcpyAsync(ev_a, sc.ev_a.p, sizeof(int) * E, cudaMemcpyDeviceToDevice, st));
+  FOFB_CUDA(cudaMemcpyAsync(ev_c, sc.ev_c.p, sizeof(int) * E, cudaMemcpyDeviceToDevice, st));
+  FOFB_CUDA(cudaMemcpyAsync(ev_loser, sc.ev_loser.p, sizeof(int) * E, cudaMemcpyDeviceToDevice, st));
+}
+
+// Distributed stage 2, step 2: the all-process contest list (global contest order, cluster indices into the all-process
+// cluster list) resolved on every process alike.
+void fof_overlap_resolve_external(fofb_handle* h, FofState& S, int K, long long E, const int* ev_a, const int* ev_c, const int* ev_loser,
+                                  int* keep_out) {
+  if (K == 0) return;
+  int* keep = overlap_resolve(h, S, K, E, ev_a, ev_c, ev_loser);
+  FOFB_CUDA(cudaMemcpyAsync(keep_out, keep, sizeof(int) * K, cudaMemcpyDeviceToDevice, h->stream));
 }
 
 // merged := the local candidates whose flag is set (flags on the device, one per local candidate)

@@ -388,37 +388,81 @@ def _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, z
     K_loc, tot_loc = kc.value, kt.value
     lap("rounds")
 
-    # ---- stage 2 on the all-process cluster list (replicated) ------------------------------------------------
+    # ---- stage 2: every rank lists the contests of ITS clusters (it needs the neighbours' boundary clusters for that:
+    #      a contest joins clusters within one velocity window), the contests are all-gathered and resolved alike
+    #      everywhere.  Member ids travel only for the boundary clusters; the cluster centres (10 doubles each) for all.
     lc = torch.empty(max(K_loc, 1), dtype=torch.int32, device=dev)[:K_loc]
     ls = torch.empty(max(K_loc, 1), dtype=i64, device=dev)[:K_loc]
     lids = torch.empty(max(tot_loc, 1), dtype=f64, device=dev)[:tot_loc]
     if K_loc:
         h.check(L.fofb_dist_local_clusters_dev(h.h, lc.data_ptr(), ls.data_ptr(), lids.data_ptr()))
+    lcl = lc.long()
+    zcl = loc_rows[lcl, 2]
+    need_cl = torch.zeros(K_loc, dtype=torch.bool, device=dev)
+    for s in range(world):
+        if s != rank:
+            need_cl |= (zcl >= iv[s, 0]) & (zcl <= iv[s, 1])
     # the int64 priority key travels as its bit pattern (N * 2^40 exceeds 2^53 for N >= 8192)
-    meta = torch.cat([loc_rows[lc.long()], key[lc.long()].view(f64).unsqueeze(1), ls.to(f64).unsqueeze(1)], dim=1)  # K x 10
-    g_meta = comm.allgatherv_t(meta)
-    g_ids = comm.allgatherv_t(lids)
+    meta = torch.cat([loc_rows[lcl], key[lcl].view(f64).unsqueeze(1), ls.to(f64).unsqueeze(1), need_cl.to(f64).unsqueeze(1)], dim=1)
+    g_meta = comm.allgatherv_t(meta)                                   # K x 11 per rank
+    member_cl = torch.repeat_interleave(torch.arange(K_loc, device=dev), ls, output_size=tot_loc)
+    g_bids = comm.allgatherv_t(lids[need_cl[member_cl]] if tot_loc else lids)   # member ids of the boundary clusters only
     kcounts = [len(x) for x in g_meta]
     M_all = cat0(g_meta)
-    ids_all = cat0(g_ids)
     K_glob = len(M_all)
-    keep_glob = torch.ones(max(K_glob, 1), dtype=torch.int32, device=dev)[:K_glob]
     cl_owner = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(kcounts)]) if K_glob else \
         torch.zeros(0, dtype=torch.int32, device=dev)
+    keep_glob = torch.ones(max(K_glob, 1), dtype=torch.int32, device=dev)[:K_glob]
+    n_events_glob = 0
     if K_glob:
-        corder = torch.argsort(M_all[:, 8].contiguous().view(i64), descending=True)  # priority order = the order fof.py:232 appends clusters
-        sizes_all = M_all[:, 9].to(i64)
-        starts = torch.cumsum(sizes_all, 0) - sizes_all
-        sizes_s = sizes_all[corder]
-        off_s = torch.zeros(K_glob + 1, dtype=i64, device=dev)
-        off_s[1:] = torch.cumsum(sizes_s, 0)
-        total_ids = int(ids_all.shape[0])
-        seg = torch.repeat_interleave(torch.arange(K_glob, device=dev), sizes_s, output_size=total_ids)
-        gather_idx = starts[corder][seg] + (torch.arange(total_ids, device=dev) - off_s[:-1][seg])
-        ids_s = ids_all[gather_idx].contiguous()
-        rows_s = M_all[corder, :8].contiguous()
-        h.check(L.fofb_dist_overlap_rows(h.h, K_glob, rows_s.data_ptr(), off_s.data_ptr(), total_ids, ids_s.data_ptr(),
-                                         keep_glob.data_ptr()))
+        keys_all = M_all[:, 8].contiguous().view(i64)
+        corder = torch.argsort(keys_all, descending=True)   # priority order = the order fof.py:232 appends clusters
+        neg_sorted = -keys_all[corder]                      # ascending, for searchsorted
+        # the list this rank works on: its own clusters plus the other ranks' boundary clusters inside its valid interval
+        bmask = M_all[:, 10] != 0
+        b_sizes = M_all[bmask, 9].to(i64)
+        b_starts = torch.cumsum(b_sizes, 0) - b_sizes
+        b_rows = M_all[bmask]
+        b_owner = cl_owner[bmask]
+        imp = torch.nonzero((b_owner != rank) & (b_rows[:, 2] >= valid[0]) & (b_rows[:, 2] <= valid[1])).flatten()
+        bids_all = cat0(g_bids)
+        own_starts = torch.cumsum(ls, 0) - ls
+        L_rows = torch.cat([loc_rows[lcl], b_rows[imp, :8]], dim=0)
+        L_keys = torch.cat([key[lcl], b_rows[imp, 8].contiguous().view(i64)])
+        L_sizes = torch.cat([ls, b_sizes[imp]])
+        L_starts = torch.cat([own_starts, tot_loc + b_starts[imp]])   # into the pool [own ids | all boundary ids]
+        L_owned = torch.cat([torch.ones(K_loc, dtype=torch.bool, device=dev), torch.zeros(len(imp), dtype=torch.bool, device=dev)])
+        pool = torch.cat([lids, bids_all])
+        lo = torch.argsort(L_keys, descending=True)
+        L_rows, L_keys, L_sizes, L_starts, L_owned = L_rows[lo].contiguous(), L_keys[lo], L_sizes[lo], L_starts[lo], L_owned[lo]
+        K_L = len(L_keys)
+        L_off = torch.zeros(K_L + 1, dtype=i64, device=dev)
+        L_off[1:] = torch.cumsum(L_sizes, 0)
+        tot_L = int(L_off[-1].item())
+        seg = torch.repeat_interleave(torch.arange(K_L, device=dev), L_sizes, output_size=tot_L)
+        L_ids = pool[L_starts[seg] + (torch.arange(tot_L, device=dev) - L_off[:-1][seg])].contiguous()
+        ne = C.c_int64(0)
+        h.check(L.fofb_dist_overlap_events(h.h, K_L, L_rows.data_ptr(), L_off.data_ptr(), tot_L, L_ids.data_ptr(), C.byref(ne)))
+        E_L = ne.value
+        ev = torch.empty((3, max(E_L, 1)), dtype=torch.int32, device=dev)
+        if E_L:
+            h.check(L.fofb_dist_overlap_events_fetch(h.h, E_L, ev[0].data_ptr(), ev[1].data_ptr(), ev[2].data_ptr()))
+        ev = ev[:, :E_L].long()
+        gpos = torch.searchsorted(neg_sorted, -L_keys)       # position of every listed cluster in the all-process order
+        mine = L_owned[ev[0]] if E_L else torch.zeros(0, dtype=torch.bool, device=dev)
+        e_a, e_c, e_l = ev[0][mine], ev[1][mine], ev[2][mine]
+        send = torch.stack([gpos[e_a], gpos[e_c.clamp(min=0)], torch.where(e_l >= 0, gpos[e_l.clamp(min=0)], torch.full_like(e_l, -1))],
+                           dim=1).to(torch.int32) if E_L else torch.zeros((0, 3), dtype=torch.int32, device=dev)
+        send[:, 1] = torch.where(e_c >= 0, send[:, 1], torch.full_like(send[:, 1], -1)) if E_L else send[:, 1]
+        ev_all = cat0(comm.allgatherv_t(send))
+        n_events_glob = len(ev_all)
+        if n_events_glob:
+            eo = torch.argsort(ev_all[:, 0], stable=True)    # contests of one cluster come from one rank, already in order
+            ev_all = ev_all[eo]
+            ga, gc, gl = ev_all[:, 0].contiguous(), ev_all[:, 1].contiguous(), ev_all[:, 2].contiguous()
+        else:
+            ga = gc = gl = torch.zeros(1, dtype=torch.int32, device=dev)
+        h.check(L.fofb_dist_overlap_resolve(h.h, K_glob, n_events_glob, ga.data_ptr(), gc.data_ptr(), gl.data_ptr(), keep_glob.data_ptr()))
         keepb = keep_glob != 0
         gidx_sorted = torch.cumsum(keepb.to(i64), 0) - 1
         mine_sorted = cl_owner[corder] == rank
@@ -493,7 +537,7 @@ def _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, z
         timings.update({"ms_" + k: round(v, 2) for k, v in phases.items()})
         timings.update(rounds=rounds, local_centres=m_l, shared_centres=nB, stage1_clusters=K_glob, merged=K_merged,
                        merged_local=int(len(gidx_local)) if K_glob else 0, local_rows=int(m.rows), fof_rows=n_g,
-                       launches=launches[0])
+                       contests=n_events_glob, launches=launches[0])
     del keep
     return res + (new_state,) if mt_state is not None else res
 

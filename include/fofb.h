@@ -233,6 +233,20 @@ int fofb_dist_prepare(fofb_handle* h, const double* centres, int64_t n_centres, 
 int fofb_dist_round_evaluate(fofb_handle* h);
 int fofb_dist_state(fofb_handle* h, uint8_t* alive, uint8_t* decided, int32_t direction);
 int fofb_dist_round_advance(fofb_handle* h, int64_t* n_active);
+/* Stage 2 distributed.  A contest needs its two clusters within one velocity window of each other, so a process can list
+ * the contests of its own clusters from its own clusters plus the neighbours' boundary clusters:
+ *   fofb_dist_overlap_events       : cluster list (centre rows K x 8 in global priority order, CSR offsets, member ids;
+ *                                    device arrays) -> number of contests, kept in the handle
+ *   fofb_dist_overlap_events_fetch : ev_a / ev_c / ev_loser [n_events] (device): cluster a, its partner c, the static
+ *                                    loser (-1: the contest cannot fire), ordered by a, then in GriSPy's return order
+ *   [all-gather the contests of the owned clusters; order them by a's global priority; indices -> all-process list]
+ *   fofb_dist_overlap_resolve      : the ordered relaxation (fof.py:294-310 with the in-place mutation of Q6) on the
+ *                                    all-process contest list, replicated; keep[K] (device, non-zero = survives) */
+int fofb_dist_overlap_events(fofb_handle* h, int64_t K, const double* centre_rows, const int64_t* offsets, int64_t total,
+                             const double* ids, int64_t* n_events);
+int fofb_dist_overlap_events_fetch(fofb_handle* h, int64_t n_events, int32_t* ev_a, int32_t* ev_c, int32_t* ev_loser);
+int fofb_dist_overlap_resolve(fofb_handle* h, int64_t K, int64_t n_events, const int32_t* ev_a, const int32_t* ev_c,
+                              const int32_t* ev_loser, int32_t* keep);
 /* The same loop with ONE collective per round.  The tracker state of a centre is 0 (alive, undecided), 1 (switched off)
  * or 2 (evaluated); it only ever rises and 2 wins, so an element-wise MAX over processes merges it.
  *   fofb_dist_state_pack   : buf[0 .. n_buf) := 0, buf[shared_pos[t]] := state of local centre local_pos[t]
