@@ -297,10 +297,10 @@ def run_slabs(args, rank, world, local_rank, h, p, dist):
     tim, tim_e = {}, {}
     clocks = ClockSampler(local_rank)
     # warm-up outside the clock sampling, then the timed region
-    time_slabs(dist, comm, h, p, local_dev, rows_dev, own, valid, 0, args.warmup, tim)
+    time_slabs(dist, comm, h, p, local_dev, rows_dev, own, valid, 0, args.warmup, tim, gather=False)
     clocks.start()
     h.profile(2)
-    dt, res = time_slabs(dist, comm, h, p, local_dev, rows_dev, own, valid, args.steps, 0, tim)
+    dt, res = time_slabs(dist, comm, h, p, local_dev, rows_dev, own, valid, args.steps, 0, tim, gather=False)
     h.profile(0)
     prof = h.profile_read()
     clock_info = clocks.stop()
@@ -321,7 +321,7 @@ def run_slabs(args, rank, world, local_rank, h, p, dist):
         wide = run_wide(args, rank, world, h, p, dist, comm)
     if rank == 0:
         peak, peak_kind = _peaks()
-        members_final = int(res[0][-1])
+        members_final = int(res_e[0][-1])
         units = {"galaxy": tim.get("local_rows", 0), "candidate_centre": st["candidate_centres"], "stage1_member": st["stage1_members"],
                  "overdensity_point": tim.get("merged_local", 0) * p.n_random, "final_member": members_final / world}
         roofline = _roofline_from_profile(prof, args.steps, units, peak, peak_kind)
@@ -339,7 +339,9 @@ def run_slabs(args, rank, world, local_rank, h, p, dist):
                                           "lists and final catalogue, one all-reduce of the tracker state per priority round",
                            "l2": "per-rank inputs larger than the 126 MB L2; no explicit flush",
                            "rows_held_by_all_ranks": int(red[2].item()), "halo_overhead": round(red[2].item() / n_total - 1.0, 4),
-                           "clusters_final": int(len(res[0]) - 1), "members_final": members_final,
+                           "clusters_final": int(len(res_e[0]) - 1), "members_final": members_final,
+                           "value_output": "the final catalogue stays sharded (every rank holds the clusters it owns, in host arrays); "
+                                           "e2e gathers the global catalogue on every rank",
                            **{k: (int(v) if float(v).is_integer() else v) for k, v in tim.items()}},
                 "clocks": clock_info,
                 "e2e": {"value": n_total / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": d2h * world,
@@ -368,8 +370,10 @@ def run_wide(args, rank, world, h, p, dist, comm):
         local, rows, own, valid = slab_inputs(table, world, rank, p.max_velocity)
         del table
         torch.cuda.empty_cache()
-        dt, res = time_slabs(dist, comm, h, p, local, rows, own, valid, steps, warmup, tim)
-        K, M = int(len(res[0]) - 1), int(res[0][-1])
+        dt, res = time_slabs(dist, comm, h, p, local, rows, own, valid, steps, warmup, tim, gather=False)
+        km = torch.tensor([float(len(res[0]) - 1), float(res[0][-1])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(km)   # the catalogue stays sharded: every rank holds the clusters it owns
+        K, M = int(km[0].item()), int(km[1].item())
     else:
         def step():
             np.random.seed(4242)

@@ -172,35 +172,31 @@ class TorchComm:
         import torch
         return torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu")
 
+    def _sizes(self, n, dev):
+        """Every rank's first dimension: one small all-gather and ONE host read-back."""
+        import torch
+        mine = torch.tensor([n], dtype=torch.int64, device=dev)
+        out = torch.empty(self.world, dtype=torch.int64, device=dev)
+        self.dist.all_gather_into_tensor(out, mine)
+        return out.tolist()
+
     def allgatherv(self, x):
         import torch
         x = np.ascontiguousarray(x)
         dev = self._dev()
-        n = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros_like(n) for _ in range(self.world)]
-        self.dist.all_gather(sizes, n)
-        sizes = [int(s.item()) for s in sizes]
-        mx = max(max(sizes), 1)
-        pad = torch.zeros((mx,) + x.shape[1:], dtype=torch.from_numpy(x[:0]).dtype, device=dev)
-        if x.shape[0]:
-            pad[: x.shape[0]] = torch.from_numpy(x).to(dev)
-        outs = [torch.empty_like(pad) for _ in range(self.world)]
-        self.dist.all_gather(outs, pad)
-        return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)]
+        return [o.cpu().numpy() for o in self.allgatherv_t(torch.from_numpy(x).to(dev))]
 
     def allgatherv_t(self, t):
         """All-gather of tensors whose first dimension differs between ranks (padded all_gather on the device)."""
         import torch
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        sizes = [torch.zeros_like(n) for _ in range(self.world)]
-        self.dist.all_gather(sizes, n)
-        sizes = [int(s.item()) for s in sizes]
+        sizes = self._sizes(t.shape[0], t.device)
         mx = max(max(sizes), 1)
-        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        row = tuple(t.shape[1:])
+        pad = torch.empty((mx,) + row, dtype=t.dtype, device=t.device)
         pad[: t.shape[0]] = t
-        outs = [torch.empty_like(pad) for _ in range(self.world)]
-        self.dist.all_gather(outs, pad)
-        return [o[:s] for o, s in zip(outs, sizes)]
+        out = torch.empty((self.world * mx,) + row, dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, pad)
+        return [out[r * mx: r * mx + s] for r, s in enumerate(sizes)]
 
     def allreduce(self, x, op):
         import torch
