@@ -711,10 +711,63 @@ __global__ void k_pair_sum_finish(int nbig, const int* list, int tiles_max, cons
   big_psum[list[b]] = acc;
 }
 
+// ---- bootstrap index table --------------------------------------------------------------------------------------
+// astropy's bootstrap under NumpyRNGContext(1) (mass_estimator.py:178-184) draws, for a cluster of n members, 100
+// resamples of n - 1 indices with np.random.randint(0, n): 32-bit words of the seed-1 MT19937 stream, masked to the
+// next power of two and rejected above n - 1.  The index sequence depends on n alone, so it is built once per distinct
+// cluster size (one CTA per size, the masked-rejection filter as a counting pass, a block scan and a writing pass) and
+// kept for the life of the handle: entry r * (n - 1) + j of the slice at boot_table_offset(n).
+constexpr int kBootTabThreads = 256;
+__host__ __device__ inline long long boot_table_offset(int n) { return (long long)kBootNum * (n - 1) * (n - 2) / 2; }
+
+__global__ void k_sizes_present(int K, const long long* off, int max_n, int* present) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const long long n = off[k + 1] - off[k];
+  if (n >= 2 && n <= max_n) present[n] = 1;
+}
+
+__global__ void __launch_bounds__(kBootTabThreads) k_boot_table(const int* todo, const unsigned* mt, long long mt_len,
+                                                                unsigned short* table, int* status) {
+  const int n = todo[blockIdx.x];
+  const int tid = threadIdx.x;
+  unsigned mask = (unsigned)(n - 1);
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  const long long want = (long long)kBootNum * (n - 1);
+  typedef cub::BlockScan<long long, kBootTabThreads> Scan;
+  __shared__ typename Scan::TempStorage stmp;
+  long long L = (long long)((double)want * ((double)mask + 1.0) / (double)n * 1.05) + 2048;
+  if (L > mt_len) L = mt_len;
+  long long lo_w, hi_w, base, total;
+  for (;;) {
+    const long long span = (L + kBootTabThreads - 1) / kBootTabThreads;
+    lo_w = (long long)tid * span;
+    hi_w = lo_w + span < L ? lo_w + span : L;
+    long long cnt = 0;
+    for (long long w = lo_w; w < hi_w; ++w) cnt += (mt[w] & mask) <= (unsigned)(n - 1) ? 1 : 0;
+    __syncthreads();
+    Scan(stmp).ExclusiveSum(cnt, base, total);
+    if (total >= want || L >= mt_len) break;
+    L = L + L / 4 + 4096;
+    if (L > mt_len) L = mt_len;
+  }
+  if (total < want) {
+    if (tid == 0) atomicAdd(status, 1);
+    return;
+  }
+  unsigned short* dst = table + boot_table_offset(n);
+  long long ord = base;
+  for (long long w = lo_w; w < hi_w && ord < want; ++w) {
+    const unsigned val = mt[w] & mask;
+    if (val > (unsigned)(n - 1)) continue;
+    dst[ord++] = (unsigned short)val;
+  }
+}
+
 __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const long long* off, View M, const double4* trig,
                                                                 Cosmo cosmo, const unsigned* mt, long long mt_len,
                                                                 double mass_unit, double* out, int* status,
-                                                                const double* big_psum) {
+                                                                const double* big_psum, const unsigned short* boot_table) {
   const int k = blockIdx.x;
   if (k >= K) return;
   const long long s0 = off[k];
@@ -834,11 +887,24 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   // bootstrap: 100 resamples of n-1 indices from the masked MT19937 stream.  Every thread owns a contiguous span of
   // the raw stream: one counting pass, one block scan for the ordinal of its first accepted word, then a second
   // pass that accumulates v^2 per resample and touches shared memory only when the resample changes.
-  unsigned mask = (unsigned)(n - 1);
-  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
   const long long want = (long long)kBootNum * (n - 1);
   typedef cub::BlockScan<long long, kVirialThreads> Scan;
   __shared__ typename Scan::TempStorage stmp;
+  if (cached && boot_table) {
+    // the resample indices of this cluster size come from the table: a warp per resample, fixed summation order
+    const unsigned short* idx = boot_table + boot_table_offset(n);
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int r = warp; r < kBootNum; r += kVirialThreads / 32) {
+      const unsigned short* row = idx + (long long)r * (n - 1);
+      double acc = 0.0;
+      for (int j = lane; j < n - 1; j += 32) acc += sv2[row[j]];
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) boot[r] = acc;
+    }
+    if (tid == 0) s_taken = want;
+  } else {
+  unsigned mask = (unsigned)(n - 1);
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
   long long L = (long long)((double)want * ((double)mask + 1.0) / (double)n * 1.05) + 2048;
   if (L > mt_len) L = mt_len;
   long long lo_w, hi_w, base, total;
@@ -880,6 +946,7 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
       }
     }
     if (acc != 0.0 && r < kBootNum) atomicAdd(&boot[r], acc);
+  }
   }
   __syncthreads();
   if (tid == 0) {
@@ -1032,7 +1099,29 @@ void CleanState::virial_core(fofb_handle* h, const fofb_params& p, int K, const 
       FOFB_LAUNCH_CHECK(h);
     }
   }
-  FOFB_PROFILED(h, "k_virial_mass", k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, trig, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status, big_psum));
+  // bootstrap index table: add the slices of the cluster sizes not seen before (usually none after the first call)
+  {
+    if (boot_built.empty()) boot_built.assign(kVirialCache + 1, 0);
+    int* present = d_present.alloc(kVirialCache + 2);
+    FOFB_CUDA(cudaMemsetAsync(present, 0, sizeof(int) * (kVirialCache + 2), st));
+    k_sizes_present<<<grid_for(K, 256), 256, 0, st>>>(K, off, kVirialCache, present);
+    FOFB_LAUNCH_CHECK(h);
+    std::vector<int> hp(kVirialCache + 2);
+    FOFB_CUDA(cudaMemcpyAsync(hp.data(), present, sizeof(int) * (kVirialCache + 2), cudaMemcpyDeviceToHost, st));
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> todo;
+    for (int n = 2; n <= kVirialCache; ++n)
+      if (hp[n] && !boot_built[n]) todo.push_back(n);
+    if (!todo.empty()) {
+      if (!d_boot_table.p) d_boot_table.alloc((size_t)boot_table_offset(kVirialCache + 1) + 64);
+      int* dtodo = d_present.p;  // reuse: the presence flags have been read
+      FOFB_CUDA(cudaMemcpyAsync(dtodo, todo.data(), sizeof(int) * todo.size(), cudaMemcpyHostToDevice, st));
+      FOFB_PROFILED(h, "k_boot_table", k_boot_table<<<(unsigned)todo.size(), kBootTabThreads, 0, st>>>(dtodo, d_mt.p, (long long)mt_len, d_boot_table.p, status));
+      FOFB_CUDA(cudaStreamSynchronize(st));  // todo[] lives on the host stack of this call
+      for (int n : todo) boot_built[n] = 1;
+    }
+  }
+  FOFB_PROFILED(h, "k_virial_mass", k_virial_mass<<<K, kVirialThreads, 0, st>>>(K, off, M, trig, cosmo, d_mt.p, (long long)mt_len, mass_unit, out, status, big_psum, d_boot_table.p));
   int bad = 0;
   FOFB_CUDA(cudaMemcpyAsync(&bad, status, sizeof(int), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));

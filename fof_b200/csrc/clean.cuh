@@ -1,5 +1,6 @@
 // Stage 5/6 scratch kept in the handle (see clean.cu).
 #pragma once
+#include <vector>
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -14,6 +15,9 @@ struct CleanState {
   DBuf<long long> d_big_off;
   DBuf<double> d_big_dev, d_big_psum;
   DBuf<double4> d_trig;
+  DBuf<unsigned short> d_boot_table;  // bootstrap indices per cluster size (clean.cu: k_boot_table)
+  DBuf<int> d_present;
+  std::vector<char> boot_built;
   size_t mt_len = 0;
   size_t clip_smem_set = 0;
   // device-resident cores: results stay in d_out_off (K+1) / d_out_index; returns the kept total
