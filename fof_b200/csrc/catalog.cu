@@ -106,6 +106,25 @@ __global__ void k_cell_starts(int n, const unsigned* key, int ncell, int* cell_s
   for (int c = prev + 1; c <= cur; ++c) cell_start[c] = k;
 }
 
+// ---- z-rank bins per cell: start offsets of every bin, from the cell-ordered z-ranks ------------------------------------
+__global__ void k_ztab(int n, const unsigned* key, const int* cell_start, const int* zrank, int zshift, unsigned short* tab,
+                       int* too_long) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int c = (int)key[k];
+  const int s = cell_start[c], e = cell_start[c + 1];
+  if (e - s >= 65535) {
+    if (k == s) *too_long = 1;
+    return;
+  }
+  const int b = zrank[k] >> zshift;
+  const int pb = k == s ? -1 : (zrank[k - 1] >> zshift);
+  unsigned short* t = tab + (size_t)c * kZBins;
+  for (int bb = pb + 1; bb <= b; ++bb) t[bb] = (unsigned short)(k - s);
+  if (k + 1 == e)
+    for (int bb = b + 1; bb < kZBins; ++bb) t[bb] = (unsigned short)(e - s);
+}
+
 struct MinMaxOp {
   __host__ __device__ double4 operator()(const double4& a, const double4& b) const {
     return make_double4(a.x < b.x ? a.x : b.x, a.y > b.y ? a.y : b.y, a.z < b.z ? a.z : b.z, a.w > b.w ? a.w : b.w);
@@ -226,6 +245,21 @@ void CellList::build(fofb_handle* h, const Catalog& cat, double r_max_deg, bool 
   int* cs = cell_start.alloc((size_t)ncell + 1);
   k_cell_starts<<<grid_for(n + 1, B), B, 0, st>>>(ni, key_out, ncell, cs);
   FOFB_LAUNCH_CHECK(h);
+  has_ztab = false;
+  if (packed) {
+    zshift = 0;
+    while (((ni - 1) >> zshift) >= kZBins) ++zshift;
+    unsigned short* zt = ztab.alloc((size_t)ncell * kZBins + 64);
+    int* flag = ztab_flag.alloc(1);
+    FOFB_CUDA(cudaMemsetAsync(zt, 0, sizeof(unsigned short) * (size_t)ncell * kZBins, st));
+    FOFB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    k_ztab<<<grid_for(n, B), B, 0, st>>>(ni, key_out, cs, zrank.p, zshift, zt, flag);
+    FOFB_LAUNCH_CHECK(h);
+    int too_long = 0;
+    FOFB_CUDA(cudaMemcpyAsync(&too_long, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FOFB_CUDA(cudaStreamSynchronize(st));
+    has_ztab = too_long == 0;
+  }
   built = true;
   radius = r_max_deg;
 }
@@ -239,6 +273,8 @@ CellListView CellList::view() const {
   v.s_ra = s_ra;
   v.s_dec = s_dec;
   v.pk = has_packed ? pk.p : nullptr;
+  v.ztab = has_packed && has_ztab ? ztab.p : nullptr;
+  v.zshift = zshift;
   v.ncx = ncx;
   v.ncy = ncy;
   v.cell_start = cell_start.p;

@@ -9,7 +9,8 @@
 
 namespace fofb {
 
-constexpr int kBBoxBlock = 256;  // block size of the two-level range min/max structure
+constexpr int kBBoxBlock = 256;
+constexpr int kZBins = 64;       // z-rank bins per cell of a packed cell list (128 bytes of u16 offsets per cell)  // block size of the two-level range min/max structure
 
 // One cell-list entry for the tiled bubble counts (16 bytes): offsets from the entry's own cell corner in degrees and
 // cos(dec) in fp32, plus the z-rank.  Differences between entries of neighbouring cells are then exact to ~1e-8 deg in
@@ -25,6 +26,11 @@ struct CellListView {
   double s_ra, s_dec;      // cell size in degrees
   int ncx, ncy;
   const PackedPoint* pk;   // cell-ordered, or null when the list was built without them
+  // z-rank bins per cell (with pk): ztab[cell * kZBins + b] = offset inside the cell of its first entry whose
+  // z-rank >> zshift is >= b.  A velocity window is about one bin wide, so the start of a cell's in-window run is one
+  // table look-up and a step or two instead of a binary search.  Null when a cell holds 65535 entries or more.
+  const unsigned short* ztab;
+  int zshift;
   const int* cell_start;   // [ncx*ncy + 1]
   const double* ra;        // cell-ordered SoA; z-rank ascending inside a cell
   const double* dec;

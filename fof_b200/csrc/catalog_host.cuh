@@ -14,6 +14,10 @@ struct CellList {
   int ncx = 1, ncy = 1;
   DBuf<double> ra, dec, cosdec;
   DBuf<PackedPoint> pk;   // only when built with packed = true (the tiled count kernels)
+  DBuf<unsigned short> ztab;
+  DBuf<int> ztab_flag;
+  bool has_ztab = false;
+  int zshift = 0;
   DBuf<int> zrank, row, cell_start, val_a, val_b;
   DBuf<unsigned> key_a, key_b;
   void build(fofb_handle* h, const Catalog& cat, double r_max_deg, bool packed = false);

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_count(CellListView cl, int ns
   const int xe = x0 + kCtW < cl.ncx ? x0 + kCtW : cl.ncx;
   const int q0 = __ldg(cl.cell_start + (size_t)y * cl.ncx + x0), q1 = __ldg(cl.cell_start + (size_t)y * cl.ncx + xe);
   if (q1 <= q0) return;
-  tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem), &s_bar, &s_fits);
+  tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem),
+             reinterpret_cast<unsigned short*>(ct_smem + (size_t)kCtMaxPts * sizeof(PackedPoint)), &s_bar, &s_fits);
   const double cell_deg = fmax(cl.s_ra, cl.s_dec);
   for (int qi = q0 + (int)threadIdx.x; qi < q1; qi += kCtThreads) {
     const PackedPoint self = t.pk[qi + t.delta[1]];

@@ -709,7 +709,8 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int
   // starts exactly there, so [qstart[b], qstart[b + 1]) is this strip's slice of the cell-sorted queries
   const int q0 = qstart[blockIdx.x], q1 = qstart[blockIdx.x + 1];
   if (q1 <= q0) return;
-  tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem), &s_bar, &s_fits);
+  tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem),
+             reinterpret_cast<unsigned short*>(ct_smem + (size_t)kCtMaxPts * sizeof(PackedPoint)), &s_bar, &s_fits);
   const int xb = t.xa + t.ncs - 2;
   const double cell_deg = fmax(cl.s_ra, cl.s_dec);
   for (int ti = q0 + (int)threadIdx.x; ti < q1; ti += kCtThreads) {

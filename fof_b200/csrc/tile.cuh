@@ -49,11 +49,15 @@ __device__ __forceinline__ int lower_bound_zr(const ZR* __restrict__ a, int lo, 
 // A strip is kCtW consecutive cells of one cell row.  Its neighbourhood -- the same cells plus one on either side, in
 // the rows above, at and below -- is three contiguous slices of the cell-ordered packed records (PackedPoint, 16 bytes).
 constexpr int kCtW = 4, kCtThreads = 256, kCtMaxPts = 3072;
-constexpr size_t kCtSmemBytes = (size_t)kCtMaxPts * sizeof(PackedPoint);
+constexpr size_t kCtZtabBytes = (size_t)3 * (kCtW + 2) * kZBins * sizeof(unsigned short);
+constexpr size_t kCtSmemBytes = (size_t)kCtMaxPts * sizeof(PackedPoint) + kCtZtabBytes;
 constexpr float kHalfDeg2RadF = 0.00872664625997164788f;  // pi / 360
 
 struct Tile {
   const PackedPoint* pk;   // the staged slices (shared memory), or the cell list's own array when they did not fit
+  const unsigned short* ztab;  // z-rank bin offsets of the neighbourhood's cells: [row][cell - xa][kZBins], or null
+  int zstride;             // cells per row in ztab (kCtW + 2 when staged; unused when ztab is the global table)
+  bool ztab_staged;
   int (*cs)[kCtW + 3];     // global cell boundaries of the three rows, from cell xa on
   int* delta;              // index of an entry in pk = its global index + delta[row]
   int xa, ncs;
@@ -63,7 +67,7 @@ struct Tile {
 // mbarrier).  When the slices exceed kCtMaxPts entries (percolating blobs) nothing is copied: t.pk is the cell list's
 // array and delta = 0.  Must be called by every thread of the CTA; bar and fits_sh are shared.
 __device__ __forceinline__ void tile_stage(const CellListView& cl, int y, int x0, Tile& t, PackedPoint* smem,
-                                           unsigned long long* bar, int* fits_sh) {
+                                           unsigned short* smem_ztab, unsigned long long* bar, int* fits_sh) {
   const int tid = threadIdx.x;
   t.xa = x0 > 0 ? x0 - 1 : 0;
   const int xb = x0 + kCtW < cl.ncx - 1 ? x0 + kCtW : cl.ncx - 1;  // staged cells xa..xb
@@ -86,20 +90,37 @@ __device__ __forceinline__ void tile_stage(const CellListView& cl, int y, int x0
     }
     const int fits = sbase <= kCtMaxPts ? 1 : 0;
     if (fits) {
-      mbar_expect_tx(bar, (unsigned)sbase * (unsigned)sizeof(PackedPoint));
+      // the bin tables of the staged cells ride along: (ncs - 1) cells x 128 bytes per valid row
+      const int ncell_row = t.ncs - 1;
+      int zrows = 0;
+      if (cl.ztab)
+        for (int r = 0; r < 3; ++r) zrows += (y + r - 1 >= 0 && y + r - 1 < cl.ncy) ? 1 : 0;
+      mbar_expect_tx(bar, (unsigned)sbase * (unsigned)sizeof(PackedPoint) + (unsigned)(zrows * ncell_row * kZBins * 2));
       for (int r = 0; r < 3; ++r)
         if (la[r]) bulk_g2s(smem + t.delta[r] + ga[r], cl.pk + ga[r], (unsigned)la[r] * (unsigned)sizeof(PackedPoint), bar);
+      if (cl.ztab)
+        for (int r = 0; r < 3; ++r) {
+          const int yy = y + r - 1;
+          if (yy < 0 || yy >= cl.ncy) continue;
+          bulk_g2s(smem_ztab + (size_t)r * (kCtW + 2) * kZBins, cl.ztab + ((size_t)yy * cl.ncx + t.xa) * kZBins,
+                   (unsigned)(ncell_row * kZBins * 2), bar);
+        }
     } else {
       t.delta[0] = t.delta[1] = t.delta[2] = 0;
     }
     *fits_sh = fits;
   }
   __syncthreads();
+  t.zstride = kCtW + 2;
   if (*fits_sh) {
     mbar_wait(bar, 0);
     t.pk = smem;
+    t.ztab = cl.ztab ? smem_ztab : nullptr;
+    t.ztab_staged = true;
   } else {
     t.pk = cl.pk;
+    t.ztab = cl.ztab;
+    t.ztab_staged = false;
   }
 }
 
@@ -123,21 +144,26 @@ __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t,
     int s = t.cs[r][cx0 - t.xa] + d;
     for (int cx = cx0; cx <= cx1; ++cx) {
       const int e = t.cs[r][cx - t.xa + 1] + d;
-      // in-window run of this cell (entries are z-rank sorted inside a cell)
-      int lo = s, hi = e;
-      while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        if (t.pk[m].zr < q.wlo) lo = m + 1; else hi = m;
-      }
-      const int first = lo;
-      hi = e;
-      while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        if (t.pk[m].zr < q.whi) lo = m + 1; else hi = m;
+      // in-window run of this cell (entries are z-rank sorted inside a cell): from the bin table, the first entry of
+      // wlo's bin and a step or two; without a table, a binary search.  The run ends at the first z-rank >= whi.
+      int first;
+      if (t.ztab) {
+        const unsigned short* tb = t.ztab_staged ? t.ztab + ((size_t)r * t.zstride + (cx - t.xa)) * kZBins
+                                                 : t.ztab + ((size_t)(y - 1 + r) * cl.ncx + cx) * kZBins;
+        first = s + tb[q.wlo >> cl.zshift];
+        while (first < e && t.pk[first].zr < q.wlo) ++first;
+      } else {
+        int lo = s, hi = e;
+        while (lo < hi) {
+          const int m = (lo + hi) >> 1;
+          if (t.pk[m].zr < q.wlo) lo = m + 1; else hi = m;
+        }
+        first = lo;
       }
       const float ox = (float)(cx - q.cx) * sx - q.fx;
-      for (int j = first; j < lo; ++j) {
+      for (int j = first; j < e; ++j) {
         const PackedPoint p = t.pk[j];
+        if (p.zr >= q.whi) break;
         bool hit;
         if (!boxed) {
           const float hx = kHalfDeg2RadF * (p.fx + ox), hy = kHalfDeg2RadF * (p.fy + oy);
