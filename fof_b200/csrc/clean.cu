@@ -255,9 +255,38 @@ __global__ void k_clip_bins(int K, int nbins, const long long* off, const double
   kept[g] = len;
 }
 
-// The same clipping with the cluster's velocities, bin permutation and scratch in shared memory: one warp per
-// cluster, lane b-1 owns radial bin b.  The serial chains of dependent loads then cost ~30 cycles instead of an L2
-// round trip each.  Dynamic shared memory: n_max * 21 bytes (launched only when that fits).
+// numpy's mean of v[p[0 .. len)] by one warp, bit for bit (np.mean = pairwise add.reduce / len): below 8 elements the
+// plain loop, up to 128 the eight strided accumulators -- one lane each -- combined as numpy combines them, then the
+// tail; longer slices (rare: bins are cut at kBigBin) run numpy's recursion on every lane.  All lanes get the result.
+__device__ __forceinline__ double warp_np_mean(const double* v, const int* p, int len, int lane) {
+  double res;
+  if (len < 8) {
+    res = 0.0;
+    for (int i = 0; i < len; ++i) res = __dadd_rn(res, v[p[i]]);
+  } else if (len <= 128) {
+    const int body = len - (len % 8);
+    double r = 0.0;
+    if (lane < 8) {
+      r = v[p[lane]];
+      for (int i = 8 + lane; i < body; i += 8) r = __dadd_rn(r, v[p[i]]);
+    }
+    const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1), r2 = __shfl_sync(0xffffffffu, r, 2),
+                 r3 = __shfl_sync(0xffffffffu, r, 3), r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5),
+                 r6 = __shfl_sync(0xffffffffu, r, 6), r7 = __shfl_sync(0xffffffffu, r, 7);
+    res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (int i = body; i < len; ++i) res = __dadd_rn(res, v[p[i]]);
+  } else {
+    auto getv = [&](long long i) -> double { return v[p[i]]; };
+    res = np_pairwise_sum(getv, 0, len);
+  }
+  return __ddiv_rn(res, (double)len);
+}
+
+// The same clipping with the cluster's velocities, bin permutation and scratch in shared memory: one warp per cluster
+// walks the radial bins one after the other and works on each together -- the mean (numpy's summation order, see
+// warp_np_mean), the deviations, a stable rank-by-counting sort (the permutation np.argsort's stable order gives; an
+// insertion sort by one thread is quadratic in the bin and leaves 31 lanes idle), the dispersion of the rest.
+// Dynamic shared memory: n_max * 33 bytes (launched only when that fits).
 __global__ void __launch_bounds__(32) k_clip_bins_smem(int K, int nbins, const long long* off, const double* vel, const double* rad,
                                                        int* perm, const int* bin_start, int* kept, int n_smem) {
   extern __shared__ double smem_d[];
@@ -267,10 +296,12 @@ __global__ void __launch_bounds__(32) k_clip_bins_smem(int K, int nbins, const l
   const int n = (int)(off[k + 1] - s0);
   if (n > n_smem) return;
   const int lane = threadIdx.x;
-  double* sv = smem_d;                                       // velocity by position in the cluster
-  double* sd = sv + n;                                       // deviation scratch, by slot
-  int* sp = reinterpret_cast<int*>(sd + n);                  // permutation (slot -> position)
-  unsigned char* sz = reinterpret_cast<unsigned char*>(sp + n);  // rad == 0 (the cluster centre itself)
+  double* sv = smem_d;                                        // velocity by position in the cluster
+  double* sd = sv + n;                                        // deviation, by slot
+  double* sd2 = sd + n;                                       // sort / squares scratch, by slot
+  int* sp = reinterpret_cast<int*>(sd2 + n);                  // permutation (slot -> position)
+  int* sp2 = sp + n;
+  unsigned char* sz = reinterpret_cast<unsigned char*>(sp2 + n);  // rad == 0 (the cluster centre itself)
   for (int i = lane; i < n; i += 32) {
     sv[i] = vel[s0 + i];
     sz[i] = rad[s0 + i] == 0.0 ? 1 : 0;
@@ -278,50 +309,58 @@ __global__ void __launch_bounds__(32) k_clip_bins_smem(int K, int nbins, const l
   }
   __syncwarp();
   const int* bs = bin_start + (long long)k * (nbins + 2);
-  for (int b = lane + 1; b <= nbins; b += 32) {
+  for (int b = 1; b <= nbins; ++b) {
     const int lo = bs[b], hi = (b == nbins) ? bs[nbins + 1] : bs[b + 1];
     if (hi - lo > kBigBin) continue;
     int* p = sp + lo;
+    int* p2 = sp2 + lo;
     double* d = sd + lo;
+    double* d2 = sd2 + lo;
     int len = hi - lo;
     bool changed = true;
     while (changed && len > 0) {
       changed = false;
       if (len > 2) {
-        auto getv = [&](long long i) -> double { return sv[p[i]]; };
-        const double mean = __ddiv_rn(np_pairwise_sum(getv, 0, len), (double)len);
-        for (int i = 0; i < len; ++i) d[i] = fabs(__dsub_rn(sv[p[i]], mean));
-        for (int i = 1; i < len; ++i) {  // stable insertion sort by deviation
+        const double mean = warp_np_mean(sv, p, len, lane);
+        for (int i = lane; i < len; i += 32) d[i] = fabs(__dsub_rn(sv[p[i]], mean));
+        __syncwarp();
+        for (int i = lane; i < len; i += 32) {  // stable ascending order by deviation
           const double di = d[i];
-          const int pi = p[i];
-          int j = i - 1;
-          while (j >= 0 && d[j] > di) {
-            d[j + 1] = d[j];
-            p[j + 1] = p[j];
-            --j;
+          int rank = 0;
+          for (int j = 0; j < len; ++j) {
+            const double dj = d[j];
+            rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
           }
-          d[j + 1] = di;
-          p[j + 1] = pi;
+          p2[rank] = p[i];
         }
-        if (!sz[p[len - 1]]) {
+        __syncwarp();
+        for (int i = lane; i < len; i += 32) p[i] = p2[i];
+        __syncwarp();
+        const int worst = p[len - 1];
+        if (!sz[worst]) {  // the largest deviation is not the cluster centre itself
           const int m = len - 1;
           if (m > 1) {
-            const double bin_mean = __ddiv_rn(np_pairwise_sum(getv, 0, m), (double)m);
-            double acc = 0.0;
-            for (int i = 0; i < m; ++i) {
+            const double bin_mean = warp_np_mean(sv, p, m, lane);
+            for (int i = lane; i < m; i += 32) {
               const double x = __dsub_rn(sv[p[i]], bin_mean);
-              acc = __dadd_rn(acc, __dmul_rn(x, x));
+              d2[i] = __dmul_rn(x, x);
             }
+            __syncwarp();
+            double acc = 0.0;  // builtin sum(): sequential
+            if (lane == 0)
+              for (int i = 0; i < m; ++i) acc = __dadd_rn(acc, d2[i]);
+            acc = __shfl_sync(0xffffffffu, acc, 0);
             const double disp = __ddiv_rn(acc, (double)(m - 1));
-            if (fabs(__dsub_rn(sv[p[len - 1]], bin_mean)) > __dmul_rn(3.0, sqrt(disp))) {
+            if (fabs(__dsub_rn(sv[worst], bin_mean)) > __dmul_rn(3.0, sqrt(disp))) {
               --len;
               changed = true;
             }
           }
         }
+        __syncwarp();
       }
     }
-    kept[(long long)k * nbins + b - 1] = len;
+    if (lane == 0) kept[(long long)k * nbins + b - 1] = len;
   }
   __syncwarp();
   for (int i = lane; i < n; i += 32) perm[s0 + i] = sp[i];
@@ -548,8 +587,8 @@ long long CleanState::three_sigma_core(fofb_handle* h, const fofb_params& p, int
   FOFB_CUDA(cudaMemcpyAsync(&nmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, st));
   FOFB_CUDA(cudaStreamSynchronize(st));
   const int smem_cap = 200 * 1024;
-  const int n_smem = (smem_cap - 64) / 21;  // clusters up to this many members are clipped in shared memory
-  const size_t smem = (size_t)std::min(nmax, n_smem) * 21 + 64;
+  const int n_smem = (smem_cap - 64) / 33;  // clusters up to this many members are clipped in shared memory
+  const size_t smem = (size_t)std::min(nmax, n_smem) * 33 + 64;
   if (smem > 48 * 1024 && smem > clip_smem_set) {
     FOFB_CUDA(cudaFuncSetAttribute(k_clip_bins_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
     clip_smem_set = smem_cap;

@@ -163,7 +163,7 @@ __global__ void k_cc_pack(int m, const int* idx, const double* c_ra, const doubl
 // centres whose window can contain the galaxy are visited.
 // The scan taken cell by cell and candidate by candidate: the least work when a blocker turns up early, as it does
 // for almost every centre of the first rounds (two million threads hide each other's latency).
-__global__ void k_ready_lazy(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
+__global__ void __launch_bounds__(128, 8) k_ready_lazy(int na, const int* active, CentreCells cc, const double* c_ra, const double* c_dec,
                         const double* c_cos, const double* c_z, const double* c_R1, const double* c_T1,
                         const unsigned char* alive, const unsigned char* decided, const long long* t_off, const int* t_rows,
                         const double* ra_row, const double* dec_row,
@@ -1524,17 +1524,34 @@ void FofState::round_evaluate(fofb_handle* h) {
           attr_set[h->device & 63] = true;
         }
         // persistent CTAs over the three queues: <= 256 candidates (4 CTAs per SM), <= 1024 (one per SM), the rest
-        // (global-memory path).  The queues are usually short or empty; an empty queue costs one launch.
+        // (global-memory path).  The queues are independent, and a round waits for its slowest centre: the second and
+        // third queue run on side streams beside the first.  An empty queue costs one launch.
         const int g0 = std::min(nr, h->sm_count * 4), g1 = std::min(nr, h->sm_count), g2 = std::min(nr, h->sm_count * 2);
+        if (!hop2_side[0]) {
+          for (int q = 0; q < 2; ++q) {
+            FOFB_CUDA(cudaStreamCreateWithFlags(&hop2_side[q], cudaStreamNonBlocking));
+            FOFB_CUDA(cudaEventCreateWithFlags(&hop2_done[q], cudaEventDisableTiming));
+          }
+          FOFB_CUDA(cudaEventCreateWithFlags(&hop2_go, cudaEventDisableTiming));
+        }
+        FOFB_CUDA(cudaEventRecord(hop2_go, st));
+        FOFB_CUDA(cudaStreamWaitEvent(hop2_side[0], hop2_go, 0));
+        FOFB_CUDA(cudaStreamWaitEvent(hop2_side[1], hop2_go, 0));
+        k_hop2_heavy<kHop2LargeRows><<<g1, kHop2Threads, hop2_smem_bytes(kHop2LargeRows), hop2_side[0]>>>(
+            1, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
+            pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above());
+        FOFB_LAUNCH_CHECK(h);
+        FOFB_CUDA(cudaEventRecord(hop2_done[0], hop2_side[0]));
+        k_hop2_heavy<0><<<g2, kHop2Threads, 0, hop2_side[1]>>>(
+            2, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
+            pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above());
+        FOFB_LAUNCH_CHECK(h);
+        FOFB_CUDA(cudaEventRecord(hop2_done[1], hop2_side[1]));
         FOFB_PROFILED(h, "k_hop2", k_hop2_heavy<kHop2SmallRows><<<g0, kHop2Threads, hop2_smem_bytes(kHop2SmallRows), st>>>(
             0, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
             pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above()));
-        FOFB_PROFILED(h, "k_hop2", k_hop2_heavy<kHop2LargeRows><<<g1, kHop2Threads, hop2_smem_bytes(kHop2LargeRows), st>>>(
-            1, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
-            pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above()));
-        FOFB_PROFILED(h, "k_hop2", k_hop2_heavy<0><<<g2, kHop2Threads, 0, st>>>(
-            2, nr, qc, ql, rb, nF_p, nnm, vo, ho, need, htab.p, G, v2ra.p, v2dec.p, v2cos.p, LLp, bb2, p, v2, mr, nml, fbatch, nms, nM_p,
-            pass_p, kill_target.p, alive.p, decided.p, k1, hop2_sort_above()));
+        FOFB_CUDA(cudaStreamWaitEvent(st, hop2_done[0], 0));
+        FOFB_CUDA(cudaStreamWaitEvent(st, hop2_done[1], 0));
       }
       // commit the clusters that passed the richness gate
       long long* len = need;  // reuse

@@ -89,6 +89,11 @@ struct FofState {
     if (overlap_scratch && overlap_scratch_free) overlap_scratch_free(overlap_scratch);
     if (rng_done) cudaEventDestroy(rng_done);
     if (rng_stream) cudaStreamDestroy(rng_stream);
+    for (int q = 0; q < 2; ++q) {
+      if (hop2_done[q]) cudaEventDestroy(hop2_done[q]);
+      if (hop2_side[q]) cudaStreamDestroy(hop2_side[q]);
+    }
+    if (hop2_go) cudaEventDestroy(hop2_go);
   }
   bool distributed = false, act_in_a = true;
   int na = 0;
@@ -101,6 +106,8 @@ struct FofState {
   DBuf<unsigned> mt_key, mt_words;
   void mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec);
   cudaStream_t rng_stream = nullptr;
+  cudaStream_t hop2_side[2] = {nullptr, nullptr};   // the larger hop-2 queues run beside the first (fof_stage.cu)
+  cudaEvent_t hop2_done[2] = {nullptr, nullptr}, hop2_go = nullptr;
   cudaEvent_t rng_done = nullptr;
   bool mt_prefetched = false;
   int mt_pos0 = 0, params_n_random_hint = 300;

@@ -144,14 +144,36 @@ __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t,
     int s = t.cs[r][cx0 - t.xa] + d;
     for (int cx = cx0; cx <= cx1; ++cx) {
       const int e = t.cs[r][cx - t.xa + 1] + d;
-      // in-window run of this cell (entries are z-rank sorted inside a cell): from the bin table, the first entry of
-      // wlo's bin and a step or two; without a table, a binary search.  The run ends at the first z-rank >= whi.
-      int first;
+      // in-window run [first, last) of this cell (entries are z-rank sorted inside a cell).  With the bin table both ends
+      // are a look-up and a short walk (a walk that gets long -- a blob whose members share one bin -- turns into a
+      // binary search); without it, two binary searches.
+      int first, last;
       if (t.ztab) {
         const unsigned short* tb = t.ztab_staged ? t.ztab + ((size_t)r * t.zstride + (cx - t.xa)) * kZBins
                                                  : t.ztab + ((size_t)(y - 1 + r) * cl.ncx + cx) * kZBins;
         first = s + tb[q.wlo >> cl.zshift];
-        while (first < e && t.pk[first].zr < q.wlo) ++first;
+        const int hb = ((q.whi - 1) >> cl.zshift) + 1;
+        last = hb < kZBins ? s + tb[hb] : e;
+        for (int steps = 0; first < last && t.pk[first].zr < q.wlo; ++first)
+          if (++steps > 12) {
+            int lo = first, hi = last;
+            while (lo < hi) {
+              const int m = (lo + hi) >> 1;
+              if (t.pk[m].zr < q.wlo) lo = m + 1; else hi = m;
+            }
+            first = lo;
+            break;
+          }
+        for (int steps = 0; last > first && t.pk[last - 1].zr >= q.whi; --last)
+          if (++steps > 12) {
+            int lo = first, hi = last;
+            while (lo < hi) {
+              const int m = (lo + hi) >> 1;
+              if (t.pk[m].zr < q.whi) lo = m + 1; else hi = m;
+            }
+            last = lo;
+            break;
+          }
       } else {
         int lo = s, hi = e;
         while (lo < hi) {
@@ -159,11 +181,16 @@ __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t,
           if (t.pk[m].zr < q.wlo) lo = m + 1; else hi = m;
         }
         first = lo;
+        hi = e;
+        while (lo < hi) {
+          const int m = (lo + hi) >> 1;
+          if (t.pk[m].zr < q.whi) lo = m + 1; else hi = m;
+        }
+        last = lo;
       }
       const float ox = (float)(cx - q.cx) * sx - q.fx;
-      for (int j = first; j < e; ++j) {
+      for (int j = first; j < last; ++j) {
         const PackedPoint p = t.pk[j];
-        if (p.zr >= q.whi) break;
         bool hit;
         if (!boxed) {
           const float hx = kHalfDeg2RadF * (p.fx + ox), hy = kHalfDeg2RadF * (p.fy + oy);
