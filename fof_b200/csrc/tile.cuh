@@ -124,6 +124,56 @@ __device__ __forceinline__ void tile_stage(const CellListView& cl, int y, int x0
   }
 }
 
+// In-window run [first, last) of one cell of the neighbourhood (row r, cell cx, entries [s, e) in t.pk; entries are
+// z-rank sorted inside a cell).  With the bin table both ends are a look-up and a short walk (a walk that gets long -- a
+// blob whose members share one bin -- turns into a binary search); without it, two binary searches.
+__device__ __forceinline__ void tile_run(const CellListView& cl, const Tile& t, int y, int r, int cx, int s, int e, int wlo, int whi,
+                                         int* first_out, int* last_out) {
+  int first, last;
+  if (t.ztab) {
+    const unsigned short* tb = t.ztab_staged ? t.ztab + ((size_t)r * t.zstride + (cx - t.xa)) * kZBins
+                                             : t.ztab + ((size_t)(y - 1 + r) * cl.ncx + cx) * kZBins;
+    first = s + tb[wlo >> cl.zshift];
+    const int hb = ((whi - 1) >> cl.zshift) + 1;
+    last = hb < kZBins ? s + tb[hb] : e;
+    for (int steps = 0; first < last && t.pk[first].zr < wlo; ++first)
+      if (++steps > 12) {
+        int lo = first, hi = last;
+        while (lo < hi) {
+          const int m = (lo + hi) >> 1;
+          if (t.pk[m].zr < wlo) lo = m + 1; else hi = m;
+        }
+        first = lo;
+        break;
+      }
+    for (int steps = 0; last > first && t.pk[last - 1].zr >= whi; --last)
+      if (++steps > 12) {
+        int lo = first, hi = last;
+        while (lo < hi) {
+          const int m = (lo + hi) >> 1;
+          if (t.pk[m].zr < whi) lo = m + 1; else hi = m;
+        }
+        last = lo;
+        break;
+      }
+  } else {
+    int lo = s, hi = e;
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if (t.pk[m].zr < wlo) lo = m + 1; else hi = m;
+    }
+    first = lo;
+    hi = e;
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if (t.pk[m].zr < whi) lo = m + 1; else hi = m;
+    }
+    last = lo;
+  }
+  *first_out = first;
+  *last_out = last;
+}
+
 // One bubble query against the neighbourhood: the number of entries of the window [wlo, whi) within the bubble.
 //   (cx, cy), q : the query point's cell and its packed offsets (q.fx / q.fy relative to that cell's corner);
 //   bt          : the same bubble in fp64 -- decides the pairs the fp32 test leaves open (|a - T| <= band * T);
@@ -144,50 +194,8 @@ __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t,
     int s = t.cs[r][cx0 - t.xa] + d;
     for (int cx = cx0; cx <= cx1; ++cx) {
       const int e = t.cs[r][cx - t.xa + 1] + d;
-      // in-window run [first, last) of this cell (entries are z-rank sorted inside a cell).  With the bin table both ends
-      // are a look-up and a short walk (a walk that gets long -- a blob whose members share one bin -- turns into a
-      // binary search); without it, two binary searches.
       int first, last;
-      if (t.ztab) {
-        const unsigned short* tb = t.ztab_staged ? t.ztab + ((size_t)r * t.zstride + (cx - t.xa)) * kZBins
-                                                 : t.ztab + ((size_t)(y - 1 + r) * cl.ncx + cx) * kZBins;
-        first = s + tb[q.wlo >> cl.zshift];
-        const int hb = ((q.whi - 1) >> cl.zshift) + 1;
-        last = hb < kZBins ? s + tb[hb] : e;
-        for (int steps = 0; first < last && t.pk[first].zr < q.wlo; ++first)
-          if (++steps > 12) {
-            int lo = first, hi = last;
-            while (lo < hi) {
-              const int m = (lo + hi) >> 1;
-              if (t.pk[m].zr < q.wlo) lo = m + 1; else hi = m;
-            }
-            first = lo;
-            break;
-          }
-        for (int steps = 0; last > first && t.pk[last - 1].zr >= q.whi; --last)
-          if (++steps > 12) {
-            int lo = first, hi = last;
-            while (lo < hi) {
-              const int m = (lo + hi) >> 1;
-              if (t.pk[m].zr < q.whi) lo = m + 1; else hi = m;
-            }
-            last = lo;
-            break;
-          }
-      } else {
-        int lo = s, hi = e;
-        while (lo < hi) {
-          const int m = (lo + hi) >> 1;
-          if (t.pk[m].zr < q.wlo) lo = m + 1; else hi = m;
-        }
-        first = lo;
-        hi = e;
-        while (lo < hi) {
-          const int m = (lo + hi) >> 1;
-          if (t.pk[m].zr < q.whi) lo = m + 1; else hi = m;
-        }
-        last = lo;
-      }
+      tile_run(cl, t, y, r, cx, s, e, q.wlo, q.whi, &first, &last);
       const float ox = (float)(cx - q.cx) * sx - q.fx;
       for (int j = first; j < last; ++j) {
         const PackedPoint p = t.pk[j];
