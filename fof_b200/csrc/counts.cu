@@ -147,9 +147,38 @@ __global__ void __launch_bounds__(kCtThreads, 3) k_count(CellListView cl, int ns
     if (tid == 0) B.item_start[kCtThreads] = N;
     __syncthreads();
     // ---- phase B: the batch's (galaxy, candidate) pairs, an equal share per thread ----
+    const bool light = N < 24 * kCtThreads;  // a field-only batch: a handful of pairs per galaxy, nothing to balance
+    if (light) {
+      int cnt = 0;
+      for (int rr = 0; rr < nrun; ++rr) {
+        const int slot = tid * kCtRunsPerQuery + rr;
+        const int code = B.run_cell[slot];
+        const int r = code / 3, dx = code % 3 - 1;
+        const float ox = (float)dx * sx - B.fx[tid], oy = (float)(r - 1) * sy - B.fy[tid];
+        const float fc = B.fcos[tid], T_lo = B.T_lo[tid], T_hi = B.T_hi[tid];
+        const int jb = B.run_first[slot], je = jb + B.run_len[slot];
+        for (int j = jb; j < je; ++j) {
+          const PackedPoint p = t.pk[j];
+          const float hx = kHalfDeg2RadF * (p.fx + ox), hy = kHalfDeg2RadF * (p.fy + oy);
+          const float sl = hx * (1.0f - hx * hx * (1.0f / 6.0f)), sd = hy * (1.0f - hy * hy * (1.0f / 6.0f));
+          const float a = sd * sd + (fc * p.fcos) * (sl * sl);
+          bool hit;
+          if (a < T_lo) hit = true;
+          else if (a > T_hi) hit = false;
+          else {
+            const int gj = j - t.delta[r];
+            BubbleTest bt;
+            bt.init(cl.ra[qi], cl.dec[qi], cl.cosdec[qi], rec[t.pk[qi + t.delta[1]].zr].r_deg);
+            hit = bt.inside(cl.ra[gj], cl.dec[gj], cl.cosdec[gj]);
+          }
+          cnt += hit ? 1 : 0;
+        }
+      }
+      if (cnt) B.count[tid] += cnt;
+    }
     const int C = (N + kCtThreads - 1) / kCtThreads;
     const int i0 = tid * C, i1 = i0 + C < N ? i0 + C : N;
-    if (i0 < i1) {
+    if (!light && i0 < i1) {
       int lo = 0, hi = kCtThreads;  // last galaxy whose first pair is <= i0 (galaxies without pairs share a start: the last wins)
       while (hi - lo > 1) {
         const int m = (lo + hi) >> 1;
