@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -172,6 +173,19 @@ inline void count_launch(fofb_handle* h, int k = 1) { h->launches += k; }
     ::fofb::count_launch(h);                                          \
     FOFB_CUDA(cudaGetLastError());                                    \
   } while (0)
+
+// One device scalar read back through the handle's pinned staging word (a pageable destination makes the driver
+// stage and block; the priority rounds read a dozen scalars each).
+template <class T>
+inline T d2h_scalar(fofb_handle* h, const T* dptr) {
+  static_assert(sizeof(T) <= 16, "scalar read-back");
+  int64_t* stage = h->pinned_i64.alloc(8);
+  FOFB_CUDA(cudaMemcpyAsync(stage, dptr, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  FOFB_CUDA(cudaStreamSynchronize(h->stream));
+  T v;
+  memcpy(&v, stage, sizeof(T));
+  return v;
+}
 
 #define FOFB_LAUNCH_CHECK(h)          \
   do {                                \

@@ -127,6 +127,25 @@ __device__ __forceinline__ void grid_axis_bounds(const GridAxis& g, double c, do
   }
 }
 
+// Shortcut for the common case of grid_axis_bounds: true when NEITHER side of the cell box can bind, decided on the
+// approximate quotients t = (x - b0) * inv_w (inv_w = ncell / (bN - b0)) whenever they are farther than 1e-9 from the
+// integers that separate the outcomes -- a few ulps of rounding cannot move them across.  False means "not decided
+// here": the caller runs the exact routine.
+__device__ __forceinline__ bool grid_axis_unbound_fast(const GridAxis& g, double inv_w, double c, double r, double reach) {
+  const double top = (double)(g.ncell - 1);
+  const double t1 = (c - r - g.b0) * inv_w, t2 = (c - reach - g.b0) * inv_w;   // lower side: t2 <= t1
+  const double t3 = (c + r - g.b0) * inv_w, t4 = (c + reach - g.b0) * inv_w;   // upper side: t4 >= t3
+  auto clear = [](double t) {  // not within the margin of an integer
+    const double f = t - floor(t), m = 1.0e-9 * (fabs(t) + 1.0);
+    return f > m && f < 1.0 - m;
+  };
+  const double m1 = 1.0e-9 * (fabs(t1) + 1.0), m3 = 1.0e-9 * (fabs(t3) + 1.0);
+  const bool lower_free = (t1 < 1.0 - m1) ||
+                          (t2 > 0.0 && floor(t1) == floor(t2) && floor(t1) <= top && clear(t1) && clear(t2));
+  const bool upper_free = (t3 > top + m3) || (t3 > m3 && floor(t3) == floor(t4) && clear(t3) && clear(t4));
+  return lower_free && upper_free;
+}
+
 struct Box {  // cell-box bounds of one query in raw coordinates
   double ra_lo, ra_hi, dec_lo, dec_hi;
   __device__ __forceinline__ bool contains(double ra, double dec) const {
@@ -149,6 +168,24 @@ __device__ __forceinline__ Box grid_box(const BBox& bb, int ncell, double c_ra, 
   const double reach_ra = 1.01 * r / cos(dd * kDeg2Rad) + 1e-12;
   grid_axis_bounds(gx, c_ra, r, reach_ra, &b.ra_lo, &b.ra_hi);
   grid_axis_bounds(gy, c_dec, r, r * (1.0 + 1e-9) + 1e-12, &b.dec_lo, &b.dec_hi);
+  return b;
+}
+
+// The same with the shortcut first: inv_wx / inv_wy = ncell / (bN - b0) of the two axes, precomputed by the caller.
+// *bound is false when the box is known not to bind (its four bounds are then infinite).
+__device__ __forceinline__ Box grid_box_fast(const BBox& bb, int ncell, double inv_wx, double inv_wy, double c_ra, double c_dec,
+                                             double r, bool* bound) {
+  GridAxis gx, gy;
+  gx.init(bb.ra_min, bb.ra_max, ncell);
+  gy.init(bb.dec_min, bb.dec_max, ncell);
+  const double dd = fmin(89.0, fabs(c_dec) + r);
+  const double reach_ra = 1.01 * r / cos(dd * kDeg2Rad) + 1e-12;
+  if (grid_axis_unbound_fast(gx, inv_wx, c_ra, r, reach_ra) && grid_axis_unbound_fast(gy, inv_wy, c_dec, r, r * (1.0 + 1e-9) + 1e-12)) {
+    *bound = false;
+    return Box{-INFINITY, INFINITY, -INFINITY, INFINITY};
+  }
+  const Box b = grid_box(bb, ncell, c_ra, c_dec, r);
+  *bound = b.ra_lo != -INFINITY || b.ra_hi != INFINITY || b.dec_lo != -INFINITY || b.dec_hi != INFINITY;
   return b;
 }
 

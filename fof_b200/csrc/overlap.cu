@@ -14,27 +14,17 @@ namespace fofb {
 
 static unsigned char* cub_tmp(fofb_handle* h, size_t bytes) { return h->cub_tmp.alloc(bytes + 256); }
 
-template <class T>
-static T d2h_scalar(fofb_handle* h, const T* dptr) {
-  T v;
-  FOFB_CUDA(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-  FOFB_CUDA(cudaStreamSynchronize(h->stream));
-  return v;
-}
+
+__global__ void k_scan_total_ov(const long long* len, long long* off, int n) { off[n] = off[n - 1] + len[n - 1]; }
 
 static long long scan_offsets(fofb_handle* h, const long long* len, long long* off, int n) {
   if (n == 0) return 0;
   size_t bytes = 0;
   FOFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len, off, n, h->stream));
   FOFB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp(h, bytes), bytes, len, off, n, h->stream));
-  count_launch(h, 2);
-  long long last_off, last_len;
-  FOFB_CUDA(cudaMemcpyAsync(&last_off, off + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-  FOFB_CUDA(cudaMemcpyAsync(&last_len, len + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-  FOFB_CUDA(cudaStreamSynchronize(h->stream));
-  const long long total = last_off + last_len;
-  FOFB_CUDA(cudaMemcpyAsync(off + n, &total, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-  return total;
+  k_scan_total_ov<<<1, 1, 0, h->stream>>>(len, off, n);  // off[n] = total, on the device
+  count_launch(h, 3);
+  return d2h_scalar(h, off + n);
 }
 
 struct OverlapScratch {
@@ -644,11 +634,12 @@ __global__ void k_own_count(int K, const int* centre, const long long* off, cons
 struct OdCluster {
   double4 bbox;
   double r;
+  double inv_wx, inv_wy;  // grid_cells / (bins[-1] - bins[0]) of the window's GriSPy grid, per axis
   int wlo, whi;
 };
 
 __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, const int* c_wlo, const int* c_whi,
-                          const double* c_th05, const double* rra, const double* rdec, OdCluster* oc) {
+                          const double* c_th05, const double* rra, const double* rdec, int grid_cells, OdCluster* oc) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (k >= K) return;
@@ -671,6 +662,8 @@ __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, c
     OdCluster o;
     o.bbox = make_double4(b.ra_min, b.ra_max, b.dec_min, b.dec_max);
     o.r = r;
+    o.inv_wx = (double)grid_cells / ((b.ra_max + 1.0e-6) - (b.ra_min - 1.0e-6));
+    o.inv_wy = (double)grid_cells / ((b.dec_max + 1.0e-6) - (b.dec_min - 1.0e-6));
     o.wlo = lo;
     o.whi = (all || hi <= lo) ? lo : hi;
     oc[k] = o;
@@ -735,8 +728,8 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int
     int cnt = 0;
     if (o.whi > o.wlo) {
       const double ra = rra[qid], dec = rdec[qid], r = o.r;
-      const Box bx = grid_box(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, ra, dec, r);
-      const bool boxed = bx.ra_lo != -INFINITY || bx.ra_hi != INFINITY || bx.dec_lo != -INFINITY || bx.dec_hi != INFINITY;
+      bool boxed;
+      const Box bx = grid_box_fast(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, o.inv_wx, o.inv_wy, ra, dec, r, &boxed);
       const double cs = cos(__dmul_rn(dec, kDeg2Rad));
       BubbleTest bt;
       bt.init(ra, dec, cs, r);
@@ -1115,8 +1108,8 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   double* D = merged.D.alloc(K);
   FOFB_PROFILED(h, "k_own_count", k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,
                                        c_ra.p, c_dec.p, c_cos.p, c_th05.p, p.grid_cells, N_own));
-  OdCluster* oc = reinterpret_cast<OdCluster*>(sc.bbox.alloc((size_t)K * 2));  // 48 bytes per cluster
-  k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, oc);
+  OdCluster* oc = reinterpret_cast<OdCluster*>(sc.bbox.alloc((size_t)K * 2 + 2));  // 64 bytes per cluster
+  k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, p.grid_cells, oc);
   FOFB_LAUNCH_CHECK(h);
   int* counts = sc.ev_a.alloc((size_t)total);
   FOFB_REQUIRE(total < (1ll << 31), "too many overdensity sample points");

@@ -16,27 +16,17 @@ void fof_overlap_and_bcg(fofb_handle* h, FofState& S);  // overlap.cu
 
 static unsigned char* cub_tmp(fofb_handle* h, size_t bytes) { return h->cub_tmp.alloc(bytes + 256); }
 
-template <class T>
-static T d2h_scalar(fofb_handle* h, const T* dptr) {
-  T v;
-  FOFB_CUDA(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-  FOFB_CUDA(cudaStreamSynchronize(h->stream));
-  return v;
-}
+
+__global__ void k_scan_total_pl(const long long* len, long long* off, int n) { off[n] = off[n - 1] + len[n - 1]; }
 
 static long long scan_offsets(fofb_handle* h, const long long* len, long long* off, int n) {
   if (n == 0) return 0;
   size_t bytes = 0;
   FOFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len, off, n, h->stream));
   FOFB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp(h, bytes), bytes, len, off, n, h->stream));
-  count_launch(h, 2);
-  long long last_off, last_len;
-  FOFB_CUDA(cudaMemcpyAsync(&last_off, off + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-  FOFB_CUDA(cudaMemcpyAsync(&last_len, len + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-  FOFB_CUDA(cudaStreamSynchronize(h->stream));
-  const long long total = last_off + last_len;
-  FOFB_CUDA(cudaMemcpyAsync(off + n, &total, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-  return total;
+  k_scan_total_pl<<<1, 1, 0, h->stream>>>(len, off, n);  // off[n] = total, on the device
+  count_launch(h, 3);
+  return d2h_scalar(h, off + n);
 }
 
 // pipeline.py:80-86: galaxies with zmin <= z <= zmax_gal keep their place in the FoF() input
