@@ -861,7 +861,8 @@ int fofb_dist_round_advance2(fofb_handle* h, const uint8_t* buf, int64_t n_buf, 
   Pipeline& P = dist_pipe(h);
   FOFB_REQUIRE(buf && n_buf >= 1 && any_active, "fofb_dist_round_advance2: bad argument");
   FOFB_CUDA(cudaSetDevice(h->device));
-  uint8_t* flag = reinterpret_cast<uint8_t*>(h->pinned_i64.alloc(1));
+  // its own pinned word: d2h_scalar (common.cuh) stages through word 0 of the same buffer while the rounds advance
+  uint8_t* flag = reinterpret_cast<uint8_t*>(h->pinned_i64.alloc(16) + 8);
   FOFB_CUDA(cudaMemcpyAsync(flag, buf + (n_buf - 1), 1, cudaMemcpyDeviceToHost, h->stream));
   P.fof.round_advance(h);  // synchronises the stream when there is anything to advance
   FOFB_CUDA(cudaStreamSynchronize(h->stream));

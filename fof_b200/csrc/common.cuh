@@ -179,7 +179,7 @@ inline void count_launch(fofb_handle* h, int k = 1) { h->launches += k; }
 template <class T>
 inline T d2h_scalar(fofb_handle* h, const T* dptr) {
   static_assert(sizeof(T) <= 16, "scalar read-back");
-  int64_t* stage = h->pinned_i64.alloc(8);
+  int64_t* stage = h->pinned_i64.alloc(16);  // words 0-1: this helper; word 8: fofb_dist_round_advance2's flag
   FOFB_CUDA(cudaMemcpyAsync(stage, dptr, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
   FOFB_CUDA(cudaStreamSynchronize(h->stream));
   T v;
