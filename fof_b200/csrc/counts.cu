@@ -26,11 +26,6 @@ __global__ void k_count_prep(CatalogView cat, Cosmo cosmo, double count_radius, 
   q.r_deg = theta;
   q.wlo = lo;
   q.whi = hi;
-  {
-    const double sh = sin_small(0.5 * theta * kDeg2Rad);
-    q.T = (float)(sh * sh);
-    q.inv_r = (float)(1.0 / theta);
-  }
   if (hi - lo >= min_window) {
     const BBox bb = range_bbox(cat, lo, hi);
     const Box b = grid_box(bb, grid_cells, cat.zra[r], cat.zdec[r], theta);
@@ -72,7 +67,7 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_count(CellListView cl, int ns
   if (q1 <= q0) return;
   tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem),
              reinterpret_cast<unsigned short*>(ct_smem + (size_t)kCtMaxPts * sizeof(PackedPoint)), &s_bar, &s_fits);
-  const float cell_deg = (float)fmax(cl.s_ra, cl.s_dec);
+  const double cell_deg = fmax(cl.s_ra, cl.s_dec);
   for (int qi = q0 + (int)threadIdx.x; qi < q1; qi += kCtThreads) {
     const PackedPoint self = t.pk[qi + t.delta[1]];
     const CountRec qr = rec[self.zr];
@@ -81,8 +76,9 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_count(CellListView cl, int ns
     q.whi = qr.whi & 0x7fffffff;
     int count = 0;
     if (q.whi > q.wlo) {
-      const double ra = cl.ra[qi];
-      q.ra = ra; q.dec = cl.dec[qi]; q.cosdec = cl.cosdec[qi]; q.r_deg = qr.r_deg;
+      const double ra = cl.ra[qi], dec = cl.dec[qi];
+      BubbleTest bt;
+      bt.init(ra, dec, cl.cosdec[qi], qr.r_deg);
       Box bx{-INFINITY, INFINITY, -INFINITY, INFINITY};
       const bool boxed = qr.whi < 0;
       if (boxed) {
@@ -92,9 +88,9 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_count(CellListView cl, int ns
       q.fx = self.fx; q.fy = self.fy; q.fcos = self.fcos;
       q.cx = cl.cx_of(ra);
       q.cy = y;
-      tile_thresholds32(qr.T, qr.inv_r, cell_deg, &q.T_lo, &q.T_hi);
+      tile_thresholds(qr.r_deg, cell_deg, &q.T_lo, &q.T_hi);
       const int cx0 = q.cx > 0 ? q.cx - 1 : 0, cx1 = q.cx < cl.ncx - 1 ? q.cx + 1 : cl.ncx - 1;
-      count = tile_count(cl, t, y, q, y > 0 ? 0 : 1, y < cl.ncy - 1 ? 2 : 1, cx0, cx1, boxed, bx);
+      count = tile_count(cl, t, y, q, y > 0 ? 0 : 1, y < cl.ncy - 1 ? 2 : 1, cx0, cx1, bt, boxed, bx);
     }
     N_row[cl.row[qi]] = count;
   }

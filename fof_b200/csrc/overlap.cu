@@ -636,8 +636,6 @@ struct OdCluster {
   double r;
   double inv_wx, inv_wy;  // grid_cells / (bins[-1] - bins[0]) of the window's GriSPy grid, per axis
   int wlo, whi;
-  float T, inv_r;         // sin^2(r/2) and 1/r for the fp32 decision thresholds (tile.cuh)
-  float pad[2];
 };
 
 __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, const int* c_wlo, const int* c_whi,
@@ -666,10 +664,6 @@ __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, c
     o.r = r;
     o.inv_wx = (double)grid_cells / ((b.ra_max + 1.0e-6) - (b.ra_min - 1.0e-6));
     o.inv_wy = (double)grid_cells / ((b.dec_max + 1.0e-6) - (b.dec_min - 1.0e-6));
-    const double sh = sin_small(0.5 * r * kDeg2Rad);
-    o.T = (float)(sh * sh);
-    o.inv_r = (float)(1.0 / r);
-    o.pad[0] = o.pad[1] = 0.f;
     o.wlo = lo;
     o.whi = (all || hi <= lo) ? lo : hi;
     oc[k] = o;
@@ -727,7 +721,7 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int
   tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem),
              reinterpret_cast<unsigned short*>(ct_smem + (size_t)kCtMaxPts * sizeof(PackedPoint)), &s_bar, &s_fits);
   const int xb = t.xa + t.ncs - 2;
-  const float cell_deg = (float)fmax(cl.s_ra, cl.s_dec);
+  const double cell_deg = fmax(cl.s_ra, cl.s_dec);
   for (int ti = q0 + (int)threadIdx.x; ti < q1; ti += kCtThreads) {
     const int qid = order[ti];
     const OdCluster o = oc[qid / npts];
@@ -737,6 +731,8 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int
       bool boxed;
       const Box bx = grid_box_fast(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, o.inv_wx, o.inv_wy, ra, dec, r, &boxed);
       const double cs = cos(__dmul_rn(dec, kDeg2Rad));
+      BubbleTest bt;
+      bt.init(ra, dec, cs, r);
       const double reach = ra_reach(r, dec);
       const int cx0 = cl.cx_of(ra - reach), cx1 = cl.cx_of(ra + reach);
       const int cy0 = cl.cy_of(dec - r * 1.000001), cy1 = cl.cy_of(dec + r * 1.000001);
@@ -749,12 +745,9 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int
         q.fcos = (float)cs;
         q.wlo = o.wlo;
         q.whi = o.whi;
-        q.ra = ra; q.dec = dec; q.cosdec = cs; q.r_deg = r;
-        tile_thresholds32(o.T, o.inv_r, cell_deg, &q.T_lo, &q.T_hi);
-        cnt = tile_count(cl, t, y, q, cy0 - (y - 1), cy1 - (y - 1), cx0, cx1, boxed, bx);
+        tile_thresholds(r, cell_deg, &q.T_lo, &q.T_hi);
+        cnt = tile_count(cl, t, y, q, cy0 - (y - 1), cy1 - (y - 1), cx0, cx1, bt, boxed, bx);
       } else {  // a bubble wider than one cell (points beyond the cell list's own declination range): walk the cell list
-        BubbleTest bt;
-        bt.init(ra, dec, cs, r);
         for (int yy = cy0; yy <= cy1; ++yy)
           for (int xx = cx0; xx <= cx1; ++xx) {
             const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
@@ -1115,7 +1108,7 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   double* D = merged.D.alloc(K);
   FOFB_PROFILED(h, "k_own_count", k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,
                                        c_ra.p, c_dec.p, c_cos.p, c_th05.p, p.grid_cells, N_own));
-  OdCluster* oc = reinterpret_cast<OdCluster*>(sc.bbox.alloc((size_t)K * 3 + 4));  // 80 bytes per cluster
+  OdCluster* oc = reinterpret_cast<OdCluster*>(sc.bbox.alloc((size_t)K * 2 + 2));  // 64 bytes per cluster
   k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, p.grid_cells, oc);
   FOFB_LAUNCH_CHECK(h);
   int* counts = sc.ev_a.alloc((size_t)total);

@@ -10,10 +10,9 @@ struct QueryRec {  // one bubble query: cell-box bounds, radius, z-rank window
   int wlo, whi;
 };
 
-struct CountRec {  // stage-0 query of one galaxy (24 bytes): radius, z-rank window (bit 31 of whi: the cell box binds),
-  double r_deg;    // and what the fp32 decision thresholds of tile.cuh are made of: T = sin^2(r/2), 1/r
+struct CountRec {  // stage-0 query of one galaxy (16 bytes): radius, z-rank window; bit 31 of whi: the cell box binds
+  double r_deg;
   int wlo, whi;
-  float T, inv_r;
 };
 
 struct Catalog;

@@ -176,24 +176,16 @@ __device__ __forceinline__ void tile_run(const CellListView& cl, const Tile& t, 
 
 // One bubble query against the neighbourhood: the number of entries of the window [wlo, whi) within the bubble.
 //   (cx, cy), q : the query point's cell and its packed offsets (q.fx / q.fy relative to that cell's corner);
-//   q.ra ..     : the same bubble in fp64 -- decides the pairs the fp32 test leaves open (|a - T| <= band * T);
+//   bt          : the same bubble in fp64 -- decides the pairs the fp32 test leaves open (|a - T| <= band * T);
 //   bx          : the GriSPy cell box of the query when `boxed` (rare): those queries run in fp64 throughout;
 //   rows r0..r1 of the neighbourhood (0 = row y - 1), cells cx0..cx1.
 struct TileQuery {
   float fx, fy, fcos, T_lo, T_hi;
   int cx, cy, wlo, whi;
-  double ra, dec, cosdec, r_deg;  // the same bubble in fp64: built into a BubbleTest only when a pair needs it
 };
 
-// the fp64 decision of one pair (rare: inside the fp32 band, or a query whose cell box binds); kept out of line
-static __device__ __noinline__ bool tile_exact(const TileQuery& q, double pra, double pdec, double pcos) {
-  BubbleTest bt;
-  bt.init(q.ra, q.dec, q.cosdec, q.r_deg);
-  return bt.inside(pra, pdec, pcos);
-}
-
 __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t, int y, const TileQuery& q, int r0, int r1, int cx0,
-                                          int cx1, bool boxed, const Box& bx) {
+                                          int cx1, const BubbleTest& bt, bool boxed, const Box& bx) {
   int count = 0;
   const float sx = (float)cl.s_ra, sy = (float)cl.s_dec;
   for (int r = r0; r <= r1; ++r) {
@@ -214,10 +206,10 @@ __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t,
           const float a = sd * sd + (q.fcos * p.fcos) * (sl * sl);
           if (a < q.T_lo) hit = true;
           else if (a > q.T_hi) hit = false;
-          else hit = tile_exact(q, cl.ra[j - d], cl.dec[j - d], cl.cosdec[j - d]);
+          else hit = bt.inside(cl.ra[j - d], cl.dec[j - d], cl.cosdec[j - d]);
         } else {
           const double pra = cl.ra[j - d], pdec = cl.dec[j - d];
-          hit = bx.contains(pra, pdec) && tile_exact(q, pra, pdec, cl.cosdec[j - d]);
+          hit = bx.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j - d]);
         }
         count += hit ? 1 : 0;
       }
@@ -235,13 +227,6 @@ __device__ __forceinline__ void tile_thresholds(double r_deg, double cell_deg, f
   const double band = fmax(1.0e-4, 1.0e-5 * cell_deg / r_deg);
   *T_lo = (float)(T * (1.0 - band));
   *T_hi = (float)(T * (1.0 + band));
-}
-
-// the same from T = sin^2(r/2) and 1/r precomputed in fp32 (per galaxy in k_count_prep, per cluster in k_od_prep)
-__device__ __forceinline__ void tile_thresholds32(float T, float inv_r, float cell_deg, float* T_lo, float* T_hi) {
-  const float band = fmaxf(1.0e-4f, 1.0e-5f * cell_deg * inv_r);
-  *T_lo = T * (1.0f - band);
-  *T_hi = T * (1.0f + band);
 }
 
 }  // namespace fofb
