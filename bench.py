@@ -239,12 +239,12 @@ def slab_inputs(arr_or_dev, world, rank, max_velocity):
         t = arr_or_dev
         n = t.shape[0]
         z = t[:, 2]
-        inner = [float(z[(n * k) // world].item()) for k in range(1, world)]  # the table is sorted by redshift
-        edges = np.concatenate([[-np.inf], inner, [np.inf]])
+        step = max(1, n // 2_000_000)                       # the table is sorted by redshift: a strided sample of z
+        edges = D.slab_edges_balanced(z[::step].cpu().numpy(), world, max_velocity)
         own, valid, local = D.plan_slab(edges, rank, max_velocity)
         rows = torch.nonzero((z >= local[0]) & (z <= local[1])).flatten()
         return t[rows].contiguous(), rows, own, valid
-    edges = D.slab_edges(arr_or_dev[:, 2], world)
+    edges = D.slab_edges_balanced(arr_or_dev[::max(1, len(arr_or_dev) // 2_000_000), 2], world, max_velocity)
     rows, own, valid = D.select_local_rows(arr_or_dev[:, 2], edges, rank, max_velocity)
     return np.ascontiguousarray(arr_or_dev[rows]), rows, own, valid
 
@@ -314,6 +314,8 @@ def run_slabs(args, rank, world, local_rank, h, p, dist):
     red = torch.tensor([float(st["candidate_centres"]), float(st["stage1_members"]), float(tim.get("local_rows", 0))],
                        dtype=torch.float64, device="cuda")
     dist.all_reduce(red)
+    by_rank = [None] * world
+    dist.all_gather_object(by_rank, {k: v for k, v in tim.items() if k.startswith("ms_")})
     wide = None
     if args.wide_galaxies > 0:
         del local_dev, host
@@ -338,6 +340,7 @@ def run_slabs(args, rank, world, local_rank, h, p, dist):
                            "parallelism": f"{world} redshift slabs with window-wide halos; NCCL all-gather of boundary centres, cluster "
                                           "lists and final catalogue, one all-reduce of the tracker state per priority round",
                            "l2": "per-rank inputs larger than the 126 MB L2; no explicit flush",
+                           "phase_ms_by_rank": {k: [r[k] for r in by_rank] for k in by_rank[0]},
                            "rows_held_by_all_ranks": int(red[2].item()), "halo_overhead": round(red[2].item() / n_total - 1.0, 4),
                            "clusters_final": int(len(res_e[0]) - 1), "members_final": members_final,
                            "value_output": "the final catalogue stays sharded (every rank holds the clusters it owns, in host arrays); "
@@ -390,6 +393,11 @@ def run_wide(args, rank, world, h, p, dist, comm):
     red = torch.tensor([float(st["candidate_centres"]), float(st["stage1_members"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(red)
+    by_rank = None
+    if world > 1:
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, {k: v for k, v in tim.items() if k.startswith("ms_")})
+        tim = dict(tim, phase_ms_by_rank={k: [r[k] for r in by_rank] for k in by_rank[0]})
     peak, _ = _peaks()
     gbs = _path_bytes(n, red[0].item(), red[1].item(), M) / dt / 1e9
     return {"workload": f"ONE {n}-galaxy wide-field mock (RA 100-150, Dec -20..20, 0.5<z<2, 20% in Plummer clusters; drawn on the "
@@ -397,7 +405,7 @@ def run_wide(args, rank, world, h, p, dist, comm):
             "value": n / dt, "unit": UNIT, "ms_per_step": 1e3 * dt, "steps": steps, "warmup": warmup, "resident": True,
             "clusters_final": K, "members_final": M, "candidate_centres": int(red[0].item()), "stage1_members": int(red[1].item()),
             "path_hbm_GBps": gbs, "path_hbm_frac_of_peak_per_gpu": gbs / (peak * world),
-            **{k: (int(v) if float(v).is_integer() else v) for k, v in tim.items()}}
+            **{k: (v if isinstance(v, dict) else (int(v) if float(v).is_integer() else v)) for k, v in tim.items()}}
 
 
 def main():

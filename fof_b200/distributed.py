@@ -37,6 +37,46 @@ def slab_edges(z, world):
     return np.concatenate([[-np.inf], inner, [np.inf]])
 
 
+def slab_edges_balanced(z, world, max_velocity, iterations=6, pair_weight=1.0):
+    """Redshift boundaries that equalise the WORK of the rows every rank holds (its own interval widened twice, see
+    ``plan_slab``) rather than the number of rows it owns.  Windows grow with (1 + z), so equal-count slabs leave the
+    interior ranks with the largest halos; and a row's cost has a part proportional to the number of galaxies in its
+    velocity window, i.e. to the catalogue's density in redshift there, dN/dz * (1 + z) (the link tests of stage 0).
+    A row at redshift z weighs 1 + pair_weight * rho(z) (1 + z) / <rho (1 + z)>.  ``z`` may be a sorted sample of the
+    table's redshifts (every k-th row is enough)."""
+    z = np.sort(np.asarray(z, dtype=np.float64))
+    if world <= 1 or len(z) < 4 * world:
+        return slab_edges(z, world) if len(z) else np.array([-np.inf] + [np.inf] * world)
+    beta = float(max_velocity) / C_KMS
+    k = max(8, len(z) // 2000)
+    idx = np.arange(len(z))
+    dz = z[np.minimum(idx + k, len(z) - 1)] - z[np.maximum(idx - k, 0)]
+    rho = (np.minimum(idx + k, len(z) - 1) - np.maximum(idx - k, 0)) / np.maximum(dz, 1e-12)
+    pair = rho * (1.0 + z)
+    w = 1.0 + pair_weight * pair / pair.mean()
+    W = np.concatenate([[0.0], np.cumsum(w)])
+
+    def held(lo, hi):
+        a, b = _widen(*_widen(lo, hi, beta), beta)
+        return W[np.searchsorted(z, b, side="right")] - W[np.searchsorted(z, a, side="left")]
+
+    edges = slab_edges(z, world)
+    for _ in range(iterations):
+        target = sum(held(edges[r], edges[r + 1]) for r in range(world)) / world
+        new = [-np.inf]
+        for r in range(world - 1):
+            lo_z, hi_z = (z[0] if r == 0 else new[r]), z[-1]
+            for _ in range(50):  # held(new[r], x) grows with x
+                mid = 0.5 * (lo_z + hi_z)
+                if held(new[r], mid) < target:
+                    lo_z = mid
+                else:
+                    hi_z = mid
+            new.append(0.5 * (lo_z + hi_z))
+        edges = np.array(new + [np.inf])
+    return edges
+
+
 def _widen(lo, hi, beta):
     """Redshift interval that contains the velocity window of every centre in [lo, hi]."""
     m = 1.0 + 1e-6

@@ -143,3 +143,20 @@ def test_thread_comm_collectives_world3():
         assert [x.tolist() for x in t] == [[0], [100, 101], [200, 201, 202]]
         assert s.tolist() == [6.0, -3.0] and mn.tolist() == [1.0, -2.0] and mx.tolist() == [3.0, 0.0]
         assert alive.tolist() == [0, 0, 0, 1] and decided.tolist() == [0, 1, 1, 1]
+
+
+def test_balanced_slab_edges_cover_the_table_and_even_out_the_held_rows():
+    """slab_edges_balanced: increasing edges, every row owned by exactly one rank, and the heaviest rank holds clearly
+    fewer (weighted) rows than under equal-count slabs."""
+    from fof_b200 import distributed as D
+    from fof_b200.mock import make_catalog
+    z = make_catalog(200000, seed=3, as_frame=False)[:, 2]
+    for world in (2, 4, 8):
+        e = D.slab_edges_balanced(z[::4], world, 2000.0)
+        assert len(e) == world + 1 and np.all(np.diff(e[1:-1]) > 0) and e[0] == -np.inf and e[-1] == np.inf
+        owned = sum(int(((z >= e[r]) & (z < e[r + 1])).sum()) for r in range(world))
+        assert owned == len(z)
+        held = lambda edges: [int(((z >= D.plan_slab(edges, r, 2000.0)[2][0]) & (z <= D.plan_slab(edges, r, 2000.0)[2][1])).sum())
+                              for r in range(world)]
+        interior_equal = held(D.slab_edges(z, world))
+        assert max(held(e)[1:-1] or [0]) <= max(interior_equal[1:-1] or [1 << 60])
