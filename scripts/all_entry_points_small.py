@@ -41,4 +41,12 @@ gg[0, :3] = (150, 2, 1.0)
 cleaned, removed = fof.interloper_removal([Cluster(gg[0], gg.copy())])
 v = mass_analysis.find_masses(cleaned, "virial")[0]
 print("giant group", removed, float(v.cluster_mass) > 0)
+# photo-z style columns (duplicated z_upper: the by-value tracker) and a field dense enough that strip neighbourhoods
+# exceed the shared-memory tile (the global-memory path of the tiled counts, the larger hop-2 queues)
+pz = make_catalog(4000, seed=5, photoz_decimals=2, as_frame=False)
+np.random.seed(7)
+print("photo-z", len(pipeline.find_clusters(pz, richness=8, overdensity=0.0)))
+crowded = make_catalog(12000, seed=6, density=3.0e6, richness_range=(200, 900), cluster_fraction=0.6, as_frame=False)
+np.random.seed(7)
+print("crowded", len(pipeline.find_clusters(crowded, linking_length_factor=0.05, richness=8, overdensity=0.0)))
 print("all entry points ran")
