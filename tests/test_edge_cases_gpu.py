@@ -174,3 +174,13 @@ def test_dataframe_column_major_input_takes_the_split_upload(lib):
     for name in ("offsets", "member_rows", "centre_row", "N", "D", "N_row"):
         assert np.array_equal(getattr(a, name), getattr(b, name)), name
     np.testing.assert_allclose(a.props, b.props, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [8000, 12000])
+def test_crowded_field_takes_the_overflow_paths(lib, n):
+    """A field so crowded (3e6 galaxies/deg^2, clusters of 200-900 members) that strip neighbourhoods exceed the
+    shared-memory tile of the tiled counts (they are then read from global memory), N(0.5) reaches ~1000, and centres have
+    hundreds to thousands of hop-2 candidates (the larger hop-2 queues).  Whole path against the oracle."""
+    arr = make_catalog(n, seed=6, density=3.0e6, richness_range=(200, 900), cluster_fraction=0.6, as_frame=False)
+    cat = _compare(arr, b=0.05, rich=8, D=0.0, seed=7)
+    assert len(cat) > 50 and cat.N_row.max() > 500
