@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_count(CellListView cl, int ns
       q.cy = y;
       tile_thresholds(qr.r_deg, cell_deg, &q.T_lo, &q.T_hi);
       const int cx0 = q.cx > 0 ? q.cx - 1 : 0, cx1 = q.cx < cl.ncx - 1 ? q.cx + 1 : cl.ncx - 1;
-      count = tile_count(cl, t, y, q, y > 0 ? 0 : 1, y < cl.ncy - 1 ? 2 : 1, cx0, cx1, bt, boxed, bx);
+      count = tile_count(cl, t, y, q, y > 0 ? 0 : 1, y < cl.ncy - 1 ? 2 : 1, cx0, cx1,
+                         [&](double pra, double pdec, double pcos) { return bt.inside(pra, pdec, pcos); }, boxed, bx);
     }
     N_row[cl.row[qi]] = count;
   }

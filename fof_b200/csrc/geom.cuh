@@ -128,18 +128,19 @@ __device__ __forceinline__ void grid_axis_bounds(const GridAxis& g, double c, do
 }
 
 // Shortcut for the common case of grid_axis_bounds: true when NEITHER side of the cell box can bind, decided on the
-// approximate quotients t = (x - b0) * inv_w (inv_w = ncell / (bN - b0)) whenever they are farther than 1e-9 from the
+// approximate quotients t = (x - b0) * inv_w (inv_w = ncell / (bN - b0)) whenever they are farther than `rel` from the
 // integers that separate the outcomes -- a few ulps of rounding cannot move them across.  False means "not decided
 // here": the caller runs the exact routine.
-__device__ __forceinline__ bool grid_axis_unbound_fast(const GridAxis& g, double inv_w, double c, double r, double reach) {
+__device__ __forceinline__ bool grid_axis_unbound_fast(const GridAxis& g, double inv_w, double c, double r, double reach,
+                                                       double rel = 1.0e-9) {
   const double top = (double)(g.ncell - 1);
   const double t1 = (c - r - g.b0) * inv_w, t2 = (c - reach - g.b0) * inv_w;   // lower side: t2 <= t1
   const double t3 = (c + r - g.b0) * inv_w, t4 = (c + reach - g.b0) * inv_w;   // upper side: t4 >= t3
-  auto clear = [](double t) {  // not within the margin of an integer
-    const double f = t - floor(t), m = 1.0e-9 * (fabs(t) + 1.0);
+  auto clear = [rel](double t) {  // not within the margin of an integer
+    const double f = t - floor(t), m = rel * (fabs(t) + 1.0);
     return f > m && f < 1.0 - m;
   };
-  const double m1 = 1.0e-9 * (fabs(t1) + 1.0), m3 = 1.0e-9 * (fabs(t3) + 1.0);
+  const double m1 = rel * (fabs(t1) + 1.0), m3 = rel * (fabs(t3) + 1.0);
   const bool lower_free = (t1 < 1.0 - m1) ||
                           (t2 > 0.0 && floor(t1) == floor(t2) && floor(t1) <= top && clear(t1) && clear(t2));
   const bool upper_free = (t3 > top + m3) || (t3 > m3 && floor(t3) == floor(t4) && clear(t3) && clear(t4));

@@ -34,6 +34,7 @@ struct OverlapScratch {
   DBuf<long long> eoff, elen, loff, soff;
   DBuf<unsigned long long> ekey, ekey_sorted, lkey, lkey_sorted;
   DBuf<double4> bbox;
+  DBuf<PackedPoint> od_pay_a, od_pay_b;
   DBuf<unsigned char> keep;
   DBuf<int> sel, selcount, attr_iota;
   DBuf<double> attr;
@@ -636,10 +637,13 @@ struct OdCluster {
   double r;
   double inv_wx, inv_wy;  // grid_cells / (bins[-1] - bins[0]) of the window's GriSPy grid, per axis
   int wlo, whi;
+  float T_lo, T_hi;       // fp32 decision thresholds of the tiled count (tile.cuh), the same for the cluster's 300 points
+  float pad[2];
 };
 
 __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, const int* c_wlo, const int* c_whi,
-                          const double* c_th05, const double* rra, const double* rdec, int grid_cells, OdCluster* oc) {
+                          const double* c_th05, const double* rra, const double* rdec, int grid_cells, double cell_deg,
+                          OdCluster* oc, unsigned long long* sums) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (k >= K) return;
@@ -664,6 +668,9 @@ __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, c
     o.r = r;
     o.inv_wx = (double)grid_cells / ((b.ra_max + 1.0e-6) - (b.ra_min - 1.0e-6));
     o.inv_wy = (double)grid_cells / ((b.dec_max + 1.0e-6) - (b.dec_min - 1.0e-6));
+    tile_thresholds(r, cell_deg, &o.T_lo, &o.T_hi);
+    o.pad[0] = o.pad[1] = 0.f;
+    sums[2 * k] = sums[2 * k + 1] = 0ull;
     o.wlo = lo;
     o.whi = (all || hi <= lo) ? lo : hi;
     oc[k] = o;
@@ -671,12 +678,20 @@ __global__ void k_od_prep(int K, int npts, const int* centre, CatalogView cat, c
 }
 
 // cell of every query point, so that the queries can be processed in cell order (the 300 points of one cluster are
-// scattered over the whole footprint)
-__global__ void k_od_keys(long long total, CellListView cl, const double* rra, const double* rdec, unsigned* key, int* val) {
+// scattered over the whole footprint), and what the count needs of the point as a 16-byte record that travels through
+// the sort with the key: offsets from the cell corner and cos(dec) in fp32, and the point's index (zr field).
+__global__ void k_od_keys(long long total, CellListView cl, const double* rra, const double* rdec, unsigned* key, PackedPoint* val) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= total) return;
-  key[q] = (unsigned)(cl.cy_of(rdec[q]) * cl.ncx + cl.cx_of(rra[q]));
-  val[q] = (int)q;
+  const double ra = rra[q], dec = rdec[q];
+  const int cx = cl.cx_of(ra), cy = cl.cy_of(dec);
+  key[q] = (unsigned)(cy * cl.ncx + cx);
+  PackedPoint p;
+  p.fx = (float)(ra - (cl.ra0 + (double)cx * cl.s_ra));
+  p.fy = (float)(dec - (cl.dec0 + (double)cy * cl.s_dec));
+  p.fcos = (float)cos(__dmul_rn(dec, kDeg2Rad));
+  p.zr = (int)q;
+  val[q] = p;
 }
 
 // first query (in cell order) of every strip: qstart[strip] = lower bound of the strip's first cell key, qstart[nstrips] = total
@@ -700,11 +715,15 @@ __global__ void k_od_strip_starts(int nstrips, int nsx, int ncx, long long total
 // Galaxies of the centre's velocity window within theta_0.5 of each random point (helper.py:207-216).  One CTA per
 // strip of cells, as in k_count (counts.cu): the strip's neighbourhood is staged in shared memory once with a bulk
 // asynchronous copy and serves every query point that fell into the strip -- the points of many different clusters,
-// each with its own window, whose binary searches would otherwise walk the same cells in global memory again and again.
+// each with its own window.  A point arrives as the 16-byte record the sort carried along (sequential reads); its
+// full-precision coordinates are fetched only by the few points that need them (a pair inside the fp32 band, a GriSPy
+// box that may bind).  The counts are not stored: D needs their sum and sum of squares per cluster (helper.py:216-221),
+// exact integers whatever the order, so each point adds its two terms to its cluster's accumulators.
 __global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int nsx, int npts, const int* __restrict__ qstart,
-                                                            const int* __restrict__ order, const OdCluster* __restrict__ oc,
-                                                            const double* __restrict__ rra, const double* __restrict__ rdec,
-                                                            int grid_cells, int* __restrict__ counts) {
+                                                            const unsigned* __restrict__ qkey, const PackedPoint* __restrict__ pay,
+                                                            const OdCluster* __restrict__ oc, const double* __restrict__ rra,
+                                                            const double* __restrict__ rdec, int grid_cells,
+                                                            unsigned long long* __restrict__ sums) {
   extern __shared__ __align__(128) unsigned char ct_smem[];
   __shared__ int s_cs[3][kCtW + 3];
   __shared__ int s_delta[3];
@@ -721,66 +740,85 @@ __global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int
   tile_stage(cl, y, x0, t, reinterpret_cast<PackedPoint*>(ct_smem),
              reinterpret_cast<unsigned short*>(ct_smem + (size_t)kCtMaxPts * sizeof(PackedPoint)), &s_bar, &s_fits);
   const int xb = t.xa + t.ncs - 2;
-  const double cell_deg = fmax(cl.s_ra, cl.s_dec);
+  const float sxf = (float)cl.s_ra, syf = (float)cl.s_dec;
   for (int ti = q0 + (int)threadIdx.x; ti < q1; ti += kCtThreads) {
-    const int qid = order[ti];
-    const OdCluster o = oc[qid / npts];
+    const PackedPoint P = pay[ti];
+    const int qid = P.zr, k = qid / npts;
+    const OdCluster o = oc[k];
+    if (o.whi <= o.wlo) continue;
+    const int cx = (int)qkey[ti] - y * cl.ncx;
+    const double r = o.r;
+    // the point from its record: exact to ~1e-8 deg, enough for everything that carries a margin
+    const double ra_a = cl.ra0 + (double)cx * cl.s_ra + (double)P.fx, dec_a = cl.dec0 + (double)y * cl.s_dec + (double)P.fy;
+    const double reach = ra_reach(r, dec_a);
+    const float reach_f = (float)reach, rdec_f = (float)(r * 1.00001);
     int cnt = 0;
-    if (o.whi > o.wlo) {
-      const double ra = rra[qid], dec = rdec[qid], r = o.r;
-      bool boxed;
-      const Box bx = grid_box_fast(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, o.inv_wx, o.inv_wy, ra, dec, r, &boxed);
-      const double cs = cos(__dmul_rn(dec, kDeg2Rad));
-      BubbleTest bt;
-      bt.init(ra, dec, cs, r);
-      const double reach = ra_reach(r, dec);
-      const int cx0 = cl.cx_of(ra - reach), cx1 = cl.cx_of(ra + reach);
-      const int cy0 = cl.cy_of(dec - r * 1.000001), cy1 = cl.cy_of(dec + r * 1.000001);
-      if (cx0 >= t.xa && cx1 <= xb && cy0 >= y - 1 && cy1 <= y + 1) {
-        TileQuery q;
-        q.cx = cl.cx_of(ra);
-        q.cy = cl.cy_of(dec);
-        q.fx = (float)(ra - (cl.ra0 + (double)q.cx * cl.s_ra));
-        q.fy = (float)(dec - (cl.dec0 + (double)q.cy * cl.s_dec));
-        q.fcos = (float)cs;
-        q.wlo = o.wlo;
-        q.whi = o.whi;
-        tile_thresholds(r, cell_deg, &q.T_lo, &q.T_hi);
-        cnt = tile_count(cl, t, y, q, cy0 - (y - 1), cy1 - (y - 1), cx0, cx1, bt, boxed, bx);
-      } else {  // a bubble wider than one cell (points beyond the cell list's own declination range): walk the cell list
-        for (int yy = cy0; yy <= cy1; ++yy)
-          for (int xx = cx0; xx <= cx1; ++xx) {
-            const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
-            const int a = lower_bound_zr(cl.zrank, s, e, o.wlo);
-            const int b = lower_bound_zr(cl.zrank, a, e, o.whi);
-            for (int j = a; j < b; ++j) {
-              const double pra = cl.ra[j], pdec = cl.dec[j];
-              if (bx.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
-            }
-          }
-      }
+    // neighbour cells the bubble can reach (1 % margin in reach, 1e-5 in dec: the record's rounding is 1e-6 of that)
+    const bool wide = reach >= cl.s_ra || r * 1.00001 >= cl.s_dec || P.fx < -sxf || P.fx > 2.f * sxf || P.fy < -syf || P.fy > 2.f * syf;
+    // GriSPy's cell box: cannot bind for almost every point -- decided on the approximate point with margins a
+    // thousand times its rounding; otherwise the exact routine on the exact point
+    GridAxis gx, gy;
+    gx.init(o.bbox.x, o.bbox.y, grid_cells);
+    gy.init(o.bbox.z, o.bbox.w, grid_cells);
+    const double dd = fmin(89.0, fabs(dec_a) + r);
+    const double reach_box = 1.01 * r / cos(dd * kDeg2Rad) + 1e-12;
+    bool boxed = false;
+    Box bx{-INFINITY, INFINITY, -INFINITY, INFINITY};
+    if (!(grid_axis_unbound_fast(gx, o.inv_wx, ra_a, r, reach_box, 1.0e-4) &&
+          grid_axis_unbound_fast(gy, o.inv_wy, dec_a, r, r * (1.0 + 1e-9) + 1e-12, 1.0e-4))) {
+      bx = grid_box(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, rra[qid], rdec[qid], r);
+      boxed = bx.ra_lo != -INFINITY || bx.ra_hi != INFINITY || bx.dec_lo != -INFINITY || bx.dec_hi != INFINITY;
     }
-    counts[qid] = cnt;
+    auto exact = [&](double pra, double pdec, double pcos) -> bool {
+      const double ra = rra[qid], dec = rdec[qid];
+      BubbleTest bt;
+      bt.init(ra, dec, cos(__dmul_rn(dec, kDeg2Rad)), r);
+      return bt.inside(pra, pdec, pcos);
+    };
+    const int cx0 = (P.fx - reach_f < 0.f && cx > 0) ? cx - 1 : cx, cx1 = (P.fx + reach_f >= sxf && cx < cl.ncx - 1) ? cx + 1 : cx;
+    const int cy0 = (P.fy - rdec_f < 0.f && y > 0) ? y - 1 : y, cy1 = (P.fy + rdec_f >= syf && y < cl.ncy - 1) ? y + 1 : y;
+    if (!wide && cx0 >= t.xa && cx1 <= xb) {
+      TileQuery q;
+      q.cx = cx;
+      q.cy = y;
+      q.fx = P.fx; q.fy = P.fy; q.fcos = P.fcos;
+      q.wlo = o.wlo;
+      q.whi = o.whi;
+      q.T_lo = o.T_lo; q.T_hi = o.T_hi;
+      cnt = tile_count(cl, t, y, q, cy0 - (y - 1), cy1 - (y - 1), cx0, cx1, exact, boxed, bx);
+    } else {  // a bubble wider than one cell, or a point far outside the cell list's footprint: walk the cell list
+      const double ra = rra[qid], dec = rdec[qid];
+      const Box bxe = grid_box(BBox{o.bbox.x, o.bbox.y, o.bbox.z, o.bbox.w}, grid_cells, ra, dec, r);
+      BubbleTest bt;
+      bt.init(ra, dec, cos(__dmul_rn(dec, kDeg2Rad)), r);
+      const double rch = ra_reach(r, dec);
+      const int ex0 = cl.cx_of(ra - rch), ex1 = cl.cx_of(ra + rch);
+      const int ey0 = cl.cy_of(dec - r * 1.000001), ey1 = cl.cy_of(dec + r * 1.000001);
+      for (int yy = ey0; yy <= ey1; ++yy)
+        for (int xx = ex0; xx <= ex1; ++xx) {
+          const int s = cl.cell_start[yy * cl.ncx + xx], e = cl.cell_start[yy * cl.ncx + xx + 1];
+          const int a = lower_bound_zr(cl.zrank, s, e, o.wlo);
+          const int b = lower_bound_zr(cl.zrank, a, e, o.whi);
+          for (int j = a; j < b; ++j) {
+            const double pra = cl.ra[j], pdec = cl.dec[j];
+            if (bxe.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j])) ++cnt;
+          }
+        }
+    }
+    if (cnt) {
+      atomicAdd(sums + 2 * k, (unsigned long long)cnt);
+      atomicAdd(sums + 2 * k + 1, (unsigned long long)cnt * (unsigned long long)cnt);
+    }
   }
 }
 
 // D = (N - mean) / rms over the 300 counts (helper.py:216-221), and the final selection (fof.py:385-390)
-__global__ void k_od_finish(int K, int npts, const int* counts, const int* N_own, const long long* off, double overdensity,
-                            int min_count, int richness, double* D_out, int* keep) {
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+__global__ void k_od_finish(int K, int npts, const unsigned long long* sums, const int* N_own, const long long* off,
+                            double overdensity, int min_count, int richness, double* D_out, int* keep) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  long long s1 = 0, s2 = 0;
-  for (int t = lane; t < npts; t += 32) {
-    const long long v = counts[(long long)k * npts + t];
-    s1 += v;
-    s2 += v * v;
-  }
-  for (int o = 16; o; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (lane == 0) {
+  const long long s1 = (long long)sums[2 * k], s2 = (long long)sums[2 * k + 1];
+  {
     const double mean = __ddiv_rn((double)s1, (double)npts);
     const double rms = sqrt(__ddiv_rn((double)s2, (double)npts));
     const double D = __ddiv_rn(__dsub_rn((double)N_own[k], mean), rms);
@@ -1108,16 +1146,17 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
   double* D = merged.D.alloc(K);
   FOFB_PROFILED(h, "k_own_count", k_own_count<<<wblocks, 128, 0, st>>>(K, merged.centre.p, merged.off.p, merged.rows.p, cat.ra_row.p, cat.dec_row.p, cos_row.p,
                                        c_ra.p, c_dec.p, c_cos.p, c_th05.p, p.grid_cells, N_own));
-  OdCluster* oc = reinterpret_cast<OdCluster*>(sc.bbox.alloc((size_t)K * 2 + 2));  // 64 bytes per cluster
-  k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, p.grid_cells, oc);
-  FOFB_LAUNCH_CHECK(h);
-  int* counts = sc.ev_a.alloc((size_t)total);
-  FOFB_REQUIRE(total < (1ll << 31), "too many overdensity sample points");
   const CellListView scl = smallp->view();
+  OdCluster* oc = reinterpret_cast<OdCluster*>(sc.bbox.alloc((size_t)K * 3 + 4));  // 80 bytes per cluster
+  unsigned long long* sums = sc.lkey.alloc((size_t)K * 2);
+  k_od_prep<<<wblocks, 128, 0, st>>>(K, npts, merged.centre.p, cat.view(), c_wlo.p, c_whi.p, c_th05.p, rra, rdec, p.grid_cells,
+                                     fmax(scl.s_ra, scl.s_dec), oc, sums);
+  FOFB_LAUNCH_CHECK(h);
+  FOFB_REQUIRE(total < (1ll << 31), "too many overdensity sample points");
   unsigned* qk = reinterpret_cast<unsigned*>(sc.ev_c.alloc((size_t)total));
   unsigned* qk2 = reinterpret_cast<unsigned*>(sc.ev_loser.alloc((size_t)total));
-  int* qv = sc.kidx.alloc((size_t)total);
-  int* qv2 = sc.kidx_sorted.alloc((size_t)total);
+  PackedPoint* qv = sc.od_pay_a.alloc((size_t)total);
+  PackedPoint* qv2 = sc.od_pay_b.alloc((size_t)total);
   k_od_keys<<<grid_for(total, 256), 256, 0, st>>>(total, scl, rra, rdec, qk, qv);
   FOFB_LAUNCH_CHECK(h);
   {
@@ -1139,11 +1178,11 @@ void FofState::finish(fofb_handle* h, const double* rand_ra, const double* rand_
     int* qstart = sc.wlo.alloc((size_t)nstrips + 1);
     k_od_strip_starts<<<grid_for(nstrips + 1, 256), 256, 0, st>>>(nstrips, nsx, scl.ncx, total, qk2, qstart);
     FOFB_LAUNCH_CHECK(h);
-    FOFB_PROFILED(h, "k_od_count", k_od_count<<<nstrips, kCtThreads, kCtSmemBytes, st>>>(scl, nsx, npts, qstart, qv2, oc, rra, rdec,
-                                                                                          p.grid_cells, counts));
+    FOFB_PROFILED(h, "k_od_count", k_od_count<<<nstrips, kCtThreads, kCtSmemBytes, st>>>(scl, nsx, npts, qstart, qk2, qv2, oc, rra, rdec,
+                                                                                          p.grid_cells, sums));
   }
   int* keep = sc.state.alloc(K);
-  k_od_finish<<<wblocks, 128, 0, st>>>(K, npts, counts, N_own, merged.off.p, p.overdensity, p.min_count, p.richness, D, keep);
+  k_od_finish<<<grid_for(K, 128), 128, 0, st>>>(K, npts, sums, N_own, merged.off.p, p.overdensity, p.min_count, p.richness, D, keep);
   FOFB_LAUNCH_CHECK(h);
   sublist(h, merged, keep, final_, sc);
   if (final_.K > 0) {

@@ -176,7 +176,8 @@ __device__ __forceinline__ void tile_run(const CellListView& cl, const Tile& t, 
 
 // One bubble query against the neighbourhood: the number of entries of the window [wlo, whi) within the bubble.
 //   (cx, cy), q : the query point's cell and its packed offsets (q.fx / q.fy relative to that cell's corner);
-//   bt          : the same bubble in fp64 -- decides the pairs the fp32 test leaves open (|a - T| <= band * T);
+//   exact(ra, dec, cos) : the same bubble in fp64 -- decides the pairs the fp32 test leaves open (|a - T| <= band * T);
+//                 a functor, so that a caller can fetch what the fp64 test needs only when a pair asks for it;
 //   bx          : the GriSPy cell box of the query when `boxed` (rare): those queries run in fp64 throughout;
 //   rows r0..r1 of the neighbourhood (0 = row y - 1), cells cx0..cx1.
 struct TileQuery {
@@ -184,8 +185,9 @@ struct TileQuery {
   int cx, cy, wlo, whi;
 };
 
+template <class Exact>
 __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t, int y, const TileQuery& q, int r0, int r1, int cx0,
-                                          int cx1, const BubbleTest& bt, bool boxed, const Box& bx) {
+                                          int cx1, Exact exact, bool boxed, const Box& bx) {
   int count = 0;
   const float sx = (float)cl.s_ra, sy = (float)cl.s_dec;
   for (int r = r0; r <= r1; ++r) {
@@ -206,10 +208,10 @@ __device__ __forceinline__ int tile_count(const CellListView& cl, const Tile& t,
           const float a = sd * sd + (q.fcos * p.fcos) * (sl * sl);
           if (a < q.T_lo) hit = true;
           else if (a > q.T_hi) hit = false;
-          else hit = bt.inside(cl.ra[j - d], cl.dec[j - d], cl.cosdec[j - d]);
+          else hit = exact(cl.ra[j - d], cl.dec[j - d], cl.cosdec[j - d]);
         } else {
           const double pra = cl.ra[j - d], pdec = cl.dec[j - d];
-          hit = bx.contains(pra, pdec) && bt.inside(pra, pdec, cl.cosdec[j - d]);
+          hit = bx.contains(pra, pdec) && exact(pra, pdec, cl.cosdec[j - d]);
         }
         count += hit ? 1 : 0;
       }
