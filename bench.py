@@ -41,9 +41,9 @@ ZCUT = (0.5, 2.52, 2.5)  # pipeline.py:80-86 with params.py:19-20
 # Algorithmic bytes per unit for each instrumented kernel (DESIGN.md section "Kernels"); unit counts are
 # filled in from the run's statistics.  Only HBM-shaped kernels have a meaningful figure.
 ALGO_BYTES = {
-    "k_count": ("galaxy", 28 + 48),          # ra,dec,z-rank 24 R + N 4 W + query record 48 R
-    "k_count_prep": ("galaxy", 8 + 16 + 56),   # z, (ra,dec) R + record and theta W
-    "k_cell_gather": ("galaxy", 4 + 4 + 16 + 32),
+    "k_count": ("galaxy", 16 + 16 + 24 + 4 + 4),  # packed tile entry once, query record, fp64 ra/dec/cos, row R + N W
+    "k_count_prep": ("galaxy", 8 + 16 + 16 + 8),  # z, (ra,dec) R + record and theta W
+    "k_cell_gather": ("galaxy", 4 + 4 + 16 + 32 + 16),
     "k_bbox_blocks": ("galaxy", 16 + 64),
     "k_extract": ("galaxy", 24 + 28),
     "k_build_rows": ("galaxy", 64 + 64 + 8),
@@ -57,7 +57,7 @@ ALGO_BYTES = {
     "k_virial_fill": ("stage1_member", 28 + 8),
     "k_hop1": ("stage1_member", 8 + 24 + 8),
     "k_hop2": ("stage1_member", 8 + 8 + 64 + 4),
-    "k_od_count": ("overdensity_point", 16 + 4),
+    "k_od_count": ("overdensity_point", 4 + 16 + 16),  # sorted key + 16-byte record R, two 8-byte accumulator updates
     "k_member_vr": ("final_member", 24 + 16),
     "k_clip_bins": ("final_member", 8 + 4 + 4),
     "k_gather_members": ("final_member", 4 + 128),
