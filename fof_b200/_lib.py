@@ -103,6 +103,8 @@ def load():
         "fofb_mt19937_words": (C.c_int, [vp, vp, vp, i64, vp, i32]),
         "fofb_match_catalog": (C.c_int, [vp, P(Params), P(Matrix), P(Matrix), dbl, dbl, vp, vp, i32, vp]),
         "fofb_dist_prefetch_mt": (C.c_int, [vp, vp, i32, i64]),
+        "fofb_dist_prefetch_mt_part": (C.c_int, [vp, vp, i32, i64, i32, i32, P(C.c_uint64), P(i64), P(i64)]),
+        "fofb_dist_mt_wait": (C.c_int, [vp]),
         "fofb_dist_local_clusters_dev": (C.c_int, [vp, vp, vp, vp]),
         "fofb_dist_overlap_rows": (C.c_int, [vp, i64, vp, vp, i64, vp, vp]),
         "fofb_fof_sizes": (C.c_int, [vp, i32, P(i64), P(i64)]),

@@ -747,6 +747,35 @@ int fofb_dist_prefetch_mt(fofb_handle* h, const uint32_t* mt_key, int32_t mt_pos
   FOFB_CATCH(h)
 }
 
+/* Slab runs: generate only share `part` of `parts` of the stream (whole chunks), to be all-gathered by the caller.
+ * Returns the device address of the word buffer and where the shares sit in it: words[blocks_offset + r * share_words ..)
+ * is share r.  fofb_dist_mt_wait makes the handle's stream wait for the generator's side stream. */
+int fofb_dist_prefetch_mt_part(fofb_handle* h, const uint32_t* mt_key, int32_t mt_pos, int64_t k_spec, int32_t part, int32_t parts,
+                               uint64_t* words_ptr, int64_t* blocks_offset, int64_t* share_words) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_REQUIRE(words_ptr && blocks_offset && share_words, "fofb_dist_prefetch_mt_part: null output");
+  FOFB_CUDA(cudaSetDevice(h->device));
+  P.fof.params_n_random_hint = P.params.n_random;
+  P.fof.mt_prefetch(h, mt_key, mt_pos, k_spec, part, parts);
+  *words_ptr = reinterpret_cast<uint64_t>(P.fof.mt_words.p);
+  *blocks_offset = 624;
+  *share_words = P.fof.mt_parts > 1 ? P.fof.mt_blocks / P.fof.mt_parts * 624 : 0;  // 0: generated in full here
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
+int fofb_dist_mt_wait(fofb_handle* h) {
+  if (!h) return FOFB_ERR_INVALID;
+  FOFB_TRY(h)
+  Pipeline& P = dist_pipe(h);
+  FOFB_CUDA(cudaSetDevice(h->device));
+  if (P.fof.rng_done && P.fof.mt_prefetched) FOFB_CUDA(cudaStreamWaitEvent(h->stream, P.fof.rng_done, 0));
+  return FOFB_OK;
+  FOFB_CATCH(h)
+}
+
 int fofb_dist_local_inputs(fofb_handle* h, double* centre_rows, int32_t* centre_src_row, int32_t* fof_src_row, double* bbox4) {
   if (!h) return FOFB_ERR_INVALID;
   FOFB_TRY(h)

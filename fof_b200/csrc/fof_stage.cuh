@@ -104,7 +104,8 @@ struct FofState {
   // draw the points on the device from numpy's legacy MT19937 state (624-word key + position), advanced in place
   void finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host);
   DBuf<unsigned> mt_key, mt_words;
-  void mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec);
+  void mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec, int part = 0, int parts = 1);
+  int mt_part = 0, mt_parts = 1;  // this process generated chunk share `part` of `parts` (slab runs all-gather the shares)
   cudaStream_t rng_stream = nullptr;
   cudaStream_t hop2_side[2] = {nullptr, nullptr};   // the larger hop-2 queues run beside the first (fof_stage.cu)
   cudaEvent_t hop2_done[2] = {nullptr, nullptr}, hop2_go = nullptr;

@@ -889,16 +889,19 @@ constexpr size_t kMtSmemBytes = sizeof(unsigned) * (kMtSeqBlocks * 624 + 624);
 // shared memory).  kMtJump[k] holds g for 2^k chunks (scripts/make_mt_jump.py, checked against numpy); the binary
 // digits of c are applied one after the other.  The jumped block may differ from the true one in the low 31 bits of
 // word 0, which never reach an output or a later block.
+// A launch may cover only the chunks [chunk0, chunk0 + gridDim.x) of nchunks (slab runs: every rank generates its share of
+// the stream and the shares are all-gathered); the head words are written by the first CTA of every launch.
 __global__ void __launch_bounds__(kMtThreads) k_mt19937_chunks(const unsigned* key_in, unsigned* key_out, int pos, int first,
-                                                               unsigned* head, long long nblocks, unsigned* out) {
+                                                               unsigned* head, long long nblocks, unsigned* out, long long chunk0,
+                                                               long long nchunks) {
   extern __shared__ unsigned mt_smem[];
   unsigned* seq = mt_smem;
   unsigned* poly = mt_smem + kMtSeqBlocks * 624;
   const int tid = threadIdx.x;
-  const long long c = blockIdx.x, nchunks = gridDim.x;
+  const long long c = blockIdx.x + chunk0;
   if (tid < 624) seq[tid] = key_in[tid];
   __syncthreads();
-  if (c == 0 && first)
+  if (blockIdx.x == 0 && first)
     for (int k = pos + tid; k < 624; k += kMtThreads) head[k - pos] = mt_temper(seq[k]);
   for (int k = 0; (c >> k) != 0; ++k) {
     if (!((c >> k) & 1)) continue;
@@ -935,12 +938,13 @@ __global__ void __launch_bounds__(kMtThreads) k_mt19937_chunks(const unsigned* k
 
 // key_in = mt_key[0 .. 624) (or the previous final state), key_out = mt_key[1248 .. 1872)
 static void launch_mt19937(fofb_handle* h, cudaStream_t st, const unsigned* key_in, unsigned* key_out, int pos, int first,
-                           unsigned* head, long long nblocks, unsigned* out) {
+                           unsigned* head, long long nblocks, unsigned* out, int part = 0, int parts = 1) {
   // per device, so set on every launch (a handle may live on any device of the process)
   FOFB_CUDA(cudaFuncSetAttribute(k_mt19937_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMtSmemBytes));
   long long nchunks = (nblocks + kMtChunkBlocks - 1) / kMtChunkBlocks;
   nchunks = std::min<long long>(std::max<long long>(nchunks, 1), 1ll << kMtJumpTables);
-  k_mt19937_chunks<<<(unsigned)nchunks, kMtThreads, kMtSmemBytes, st>>>(key_in, key_out, pos, first, head, nblocks, out);
+  const long long per = nchunks / parts;  // parts > 1: nblocks is a multiple of parts * kMtChunkBlocks (mt_prefetch)
+  k_mt19937_chunks<<<(unsigned)per, kMtThreads, kMtSmemBytes, st>>>(key_in, key_out, pos, first, head, nblocks, out, part * per, nchunks);
   count_launch(h);
   FOFB_CUDA(cudaGetLastError());
 }
@@ -999,8 +1003,9 @@ void mt19937_words(fofb_handle* h, unsigned* key_host, int* pos_host, long long 
 }
 
 // Start generating the stream on a side stream while stages 0-3 run: enough words for k_spec clusters.
-void FofState::mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec) {
+void FofState::mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, long long k_spec, int part, int parts) {
   FOFB_REQUIRE(key_host && pos >= 0 && pos <= 624, "bad MT19937 state");
+  FOFB_REQUIRE(parts >= 1 && part >= 0 && part < parts, "bad MT19937 share");
   if (!rng_stream) {
     FOFB_CUDA(cudaStreamCreateWithFlags(&rng_stream, cudaStreamNonBlocking));
     FOFB_CUDA(cudaEventCreateWithFlags(&rng_done, cudaEventDisableTiming));
@@ -1009,11 +1014,18 @@ void FofState::mt_prefetch(fofb_handle* h, const unsigned* key_host, int pos, lo
   mt_head = 624 - pos;
   const long long W = std::max<long long>(k_spec, 1) * params_n_random_hint * 4;
   mt_blocks = std::max<long long>((W - mt_head + 623) / 624, 1);
+  if (parts > 1) {  // equal shares of whole chunks; too long a stream for the jump tables: everybody generates everything
+    const long long unit = (long long)parts * kMtChunkBlocks;
+    const long long padded = (mt_blocks + unit - 1) / unit * unit;
+    if (padded / kMtChunkBlocks <= (1ll << kMtJumpTables)) mt_blocks = padded; else { part = 0; parts = 1; }
+  }
+  mt_part = part;
+  mt_parts = parts;
   unsigned* key = mt_key.alloc(624 * 4);  // [0] input state, [1] untempered output, [2] state after the stream, [3] scratch
   unsigned* words = mt_words.alloc((size_t)(624 + mt_blocks * 624));
   std::memcpy(mt_key_host, key_host, sizeof(unsigned) * 624);
   FOFB_CUDA(cudaMemcpyAsync(key, mt_key_host, sizeof(unsigned) * 624, cudaMemcpyHostToDevice, rng_stream));
-  launch_mt19937(h, rng_stream, key, key + 1248, pos, 1, words, mt_blocks, words + 624);
+  launch_mt19937(h, rng_stream, key, key + 1248, pos, 1, words, mt_blocks, words + 624, part, parts);
   FOFB_CUDA(cudaEventRecord(rng_done, rng_stream));
   mt_prefetched = true;
 }
@@ -1048,6 +1060,12 @@ void FofState::finish_mt(fofb_handle* h, unsigned* key_host, int* pos_host) {
             (t_b.tv_sec - t_a.tv_sec) * 1e3 + (t_b.tv_nsec - t_a.tv_nsec) * 1e-6, mt_blocks);
   }
   const long long need_blocks = W > mt_head ? (W - mt_head + 623) / 624 : 0;
+  if (need_blocks > mt_blocks && mt_parts > 1) {
+    // a shared stream that fell short: the state after its last block lives on another process; generate the stream
+    // here in full (rare: the speculation is the previous run's cluster count plus a quarter)
+    mt_prefetch(h, key_host, *pos_host, K_stream, 0, 1);
+    FOFB_CUDA(cudaStreamWaitEvent(st, rng_done, 0));
+  }
   if (need_blocks > mt_blocks) {  // the speculation fell short: continue from the last generated state
     const long long extra = need_blocks - mt_blocks;
     DBuf<unsigned> bigger;

@@ -133,6 +133,10 @@ class SoloComm:
     def allreduce_max_bytes(self, buf):
         pass
 
+    def allgather_shares(self, full, share):
+        full.copy_(share)
+        return None
+
     def barrier(self):
         pass
 
@@ -195,6 +199,12 @@ class ThreadComm:
         parts = self._exchange(buf)
         buf.copy_(torch.stack(parts).max(dim=0).values)
 
+    def allgather_shares(self, full, share):
+        """full := the ranks' equal-sized shares one after the other; returns a handle to wait on (or None)."""
+        import torch
+        full.copy_(torch.cat(self._exchange(share)))
+        return None
+
     def barrier(self):
         self.s.barrier.wait()
 
@@ -252,6 +262,9 @@ class TorchComm:
     def allreduce_max_bytes(self, buf):
         self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX)
 
+    def allgather_shares(self, full, share):
+        return self.dist.all_gather_into_tensor(full, share, async_op=True)
+
     def barrier(self):
         self.dist.barrier()
 
@@ -274,6 +287,19 @@ def select_local_rows(z, edges, rank, max_velocity):
     own, valid, local = plan_slab(edges, rank, max_velocity)
     rows = np.nonzero((z >= local[0]) & (z <= local[1]))[0]
     return rows, own, valid
+
+
+class _DevicePointer:
+    """A block of device memory owned by the library, described to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def _device_view(ptr, n_words, dev):
+    """int32 torch tensor aliasing n_words 32-bit words at device address ptr (no copy)."""
+    import torch
+    return torch.as_tensor(_DevicePointer(ptr, n_words), device=dev)
 
 
 def find_clusters_slabs(local_rows, global_row, own, valid, comm, handle, params=None, zcut=None, timings=None,
@@ -354,8 +380,21 @@ def _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, z
     else:
         mt_key, mt_pos = mt_state
     mt_key = np.ascontiguousarray(mt_key, dtype=np.uint32)
-    k_spec = int(getattr(h, "_slab_last_merged", 0) * 1.25) + 256 if getattr(h, "_slab_last_merged", 0) else int(m.rows) * world // 150 + 1024
-    h.check(L.fofb_dist_prefetch_mt(h.h, mt_key.ctypes.data, int(mt_pos), k_spec))
+    # Once the number of clusters is known from an earlier call (the same on every rank), the stream is generated in
+    # shares: every rank produces 1 / world of it and the shares are all-gathered after the rounds.  The first call
+    # has only a per-rank guess and generates the whole stream everywhere.
+    last = getattr(h, "_slab_last_merged", 0)
+    mt_words_t = mt_share = None
+    if last and world > 1:
+        wp, boff, share = C.c_uint64(), C.c_int64(), C.c_int64()
+        h.check(L.fofb_dist_prefetch_mt_part(h.h, mt_key.ctypes.data, int(mt_pos), int(last * 1.25) + 256, rank, world,
+                                             C.byref(wp), C.byref(boff), C.byref(share)))
+        if share.value:
+            mt_words_t = _device_view(wp.value, boff.value + share.value * world, dev)[boff.value:]
+            mt_share = share.value
+    else:
+        k_spec = int(last * 1.25) + 256 if last else int(m.rows) * world // 150 + 1024
+        h.check(L.fofb_dist_prefetch_mt(h.h, mt_key.ctypes.data, int(mt_pos), k_spec))
     cen = torch.empty((max(m_loc, 1), 8), dtype=f64, device=dev)[:m_loc]
     csrc = torch.empty(max(m_loc, 1), dtype=torch.int32, device=dev)[:m_loc]
     h.check(L.fofb_dist_local_inputs(h.h, cen.data_ptr(), csrc.data_ptr(), None, None))
@@ -422,6 +461,11 @@ def _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, z
     kc, kt = C.c_int64(), C.c_int64()
     h.check(L.fofb_dist_finalize(h.h, C.byref(kc), C.byref(kt)))
     K_loc, tot_loc = kc.value, kt.value
+    mt_work = None
+    if mt_words_t is not None:  # the shares of the MT19937 stream travel while stage 2 is being sorted out
+        h.check(L.fofb_dist_mt_wait(h.h))
+        mine = mt_words_t[rank * mt_share:(rank + 1) * mt_share].clone()
+        mt_work = comm.allgather_shares(mt_words_t, mine)
     lap("rounds")
 
     # ---- stage 2: every rank lists the contests of ITS clusters (it needs the neighbours' boundary clusters for that:
@@ -511,6 +555,8 @@ def _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, z
         K_merged = 0
     h.check(L.fofb_dist_set_merged(h.h, keep_local.data_ptr(), gidx_local.data_ptr(), K_merged, gbbox.ctypes.data))
     h._slab_last_merged = K_merged
+    if mt_work is not None:
+        mt_work.wait()
     lap("overlap")
 
     # ---- stage 4 (every rank consumes the same MT19937 stream and uses its own clusters' blocks), stages 5-6 ----

@@ -228,6 +228,13 @@ int fofb_pipeline_stats(fofb_handle* h, int64_t* stats7);
 int fofb_dist_begin(fofb_handle* h, const fofb_params* p, const fofb_matrix* galaxies, const double* zcut3,
                     const double* z_valid2, const double* z_own2, int64_t* n_fof_rows, int64_t* n_local_centres);
 int fofb_dist_prefetch_mt(fofb_handle* h, const uint32_t* mt_key, int32_t mt_pos, int64_t k_spec);
+/* the same for share `part` of `parts` of the stream (whole chunks of it): every process generates its share, the caller
+ * all-gathers the shares in place -- words_ptr[blocks_offset + r * share_words ..) is share r (share_words = 0: the stream
+ * was too long to share and has been generated in full) -- after fofb_dist_mt_wait has put the generator's side stream
+ * in front of the handle's stream */
+int fofb_dist_prefetch_mt_part(fofb_handle* h, const uint32_t* mt_key, int32_t mt_pos, int64_t k_spec, int32_t part, int32_t parts,
+                               uint64_t* words_ptr, int64_t* blocks_offset, int64_t* share_words);
+int fofb_dist_mt_wait(fofb_handle* h);
 int fofb_dist_local_inputs(fofb_handle* h, double* centre_rows, int32_t* centre_src_row, int32_t* fof_src_row, double* bbox4);
 int fofb_dist_prepare(fofb_handle* h, const double* centres, int64_t n_centres, const uint8_t* owned, double* local_bbox4);
 int fofb_dist_round_evaluate(fofb_handle* h);

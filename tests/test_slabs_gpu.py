@@ -20,7 +20,11 @@ def _run_ranks(arr, world, state):
     def work(r):
         try:
             h = _lib.Handle(0)
+            first = D.find_clusters_distributed(arr, comm=comms[r], handle=h, mt_state=state)
+            # the second call on a handle knows the cluster count and generates the MT19937 stream in shares that the
+            # ranks all-gather: the result must not change
             out[r] = D.find_clusters_distributed(arr, comm=comms[r], handle=h, mt_state=state)
+            assert np.array_equal(first.member_rows, out[r].member_rows) and np.array_equal(first.D, out[r].D)
             h.close()
         except Exception as e:  # pragma: no cover
             err.append(e)
@@ -69,7 +73,9 @@ from fof_b200.mock import make_catalog
 arr = make_catalog(int(sys.argv[2]), seed=17, as_frame=False)
 np.random.seed(99)
 st = np.random.get_state()
-cat = D.find_clusters_distributed(arr, comm=D.TorchComm(), handle=_lib.Handle(rank), mt_state=(st[1].copy(), st[2]))
+handle = _lib.Handle(rank)
+cat = D.find_clusters_distributed(arr, comm=D.TorchComm(), handle=handle, mt_state=(st[1].copy(), st[2]))
+cat = D.find_clusters_distributed(arr, comm=D.TorchComm(), handle=handle, mt_state=(st[1].copy(), st[2]))  # MT stream in shares
 np.savez(sys.argv[3] + f".rank{rank}.npz", off=cat.offsets, rows=cat.member_rows, centre=cat.centre_row, N=cat.N, D=cat.D,
          props=cat.props, key=cat.mt_state[0], pos=cat.mt_state[1])
 dist.barrier()
