@@ -385,7 +385,8 @@ def _slabs_on_stream(local_rows, global_row, own, valid, comm, h, dev, params, z
     # has only a per-rank guess and generates the whole stream everywhere.
     last = getattr(h, "_slab_last_merged", 0)
     mt_words_t = mt_share = None
-    if last and world > 1:
+    # (worth the extra collective only for long streams: 1e8 words ~ 8e4 clusters; below that everybody generates all)
+    if last and world > 1 and last * 4 * p.n_random >= getattr(h, "_mt_share_min_words", 100_000_000):
         wp, boff, share = C.c_uint64(), C.c_int64(), C.c_int64()
         h.check(L.fofb_dist_prefetch_mt_part(h.h, mt_key.ctypes.data, int(mt_pos), int(last * 1.25) + 256, rank, world,
                                              C.byref(wp), C.byref(boff), C.byref(share)))

@@ -20,6 +20,7 @@ def _run_ranks(arr, world, state):
     def work(r):
         try:
             h = _lib.Handle(0)
+            h._mt_share_min_words = 0   # share the stream however short it is
             first = D.find_clusters_distributed(arr, comm=comms[r], handle=h, mt_state=state)
             # the second call on a handle knows the cluster count and generates the MT19937 stream in shares that the
             # ranks all-gather: the result must not change
@@ -74,6 +75,7 @@ arr = make_catalog(int(sys.argv[2]), seed=17, as_frame=False)
 np.random.seed(99)
 st = np.random.get_state()
 handle = _lib.Handle(rank)
+handle._mt_share_min_words = 0   # share the MT19937 stream on the second call however short it is
 cat = D.find_clusters_distributed(arr, comm=D.TorchComm(), handle=handle, mt_state=(st[1].copy(), st[2]))
 cat = D.find_clusters_distributed(arr, comm=D.TorchComm(), handle=handle, mt_state=(st[1].copy(), st[2]))  # MT stream in shares
 np.savez(sys.argv[3] + f".rank{rank}.npz", off=cat.offsets, rows=cat.member_rows, centre=cat.centre_row, N=cat.N, D=cat.D,
