@@ -28,8 +28,12 @@ __global__ void k_count_prep(CatalogView cat, Cosmo cosmo, double count_radius, 
   q.whi = hi;
   if (hi - lo >= min_window) {
     const BBox bb = range_bbox(cat, lo, hi);
-    const Box b = grid_box(bb, grid_cells, cat.zra[r], cat.zdec[r], theta);
-    if (b.ra_lo != -INFINITY || b.ra_hi != INFINITY || b.dec_lo != -INFINITY || b.dec_hi != INFINITY) {
+    // almost never binds: the shortcut decides that on two divisions; the exact routine (a dozen) runs for the rest
+    bool bound;
+    const Box b = grid_box_fast(bb, grid_cells, (double)grid_cells / ((bb.ra_max + 1.0e-6) - (bb.ra_min - 1.0e-6)),
+                                (double)grid_cells / ((bb.dec_max + 1.0e-6) - (bb.dec_min - 1.0e-6)), cat.zra[r], cat.zdec[r],
+                                theta, &bound);
+    if (bound) {
       box[r] = make_double4(b.ra_lo, b.ra_hi, b.dec_lo, b.dec_hi);
       q.whi |= (int)0x80000000;
     }
