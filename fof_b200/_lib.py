@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfofb200.so")
+LIB_PATH = os.environ.get("FOFB_LIB") or os.path.join(HERE, "libfofb200.so")  # FOFB_LIB: a developer build (scripts/build_tile_variants.py)
 
 
 class FofbError(RuntimeError):

@@ -10,7 +10,10 @@
 namespace fofb {
 
 constexpr int kBBoxBlock = 256;
-constexpr int kZBins = 64;       // z-rank bins per cell of a packed cell list (128 bytes of u16 offsets per cell)  // block size of the two-level range min/max structure
+#ifndef FOFB_ZBINS
+#define FOFB_ZBINS 64
+#endif
+constexpr int kZBins = FOFB_ZBINS;       // z-rank bins per cell of a packed cell list (128 bytes of u16 offsets per cell)  // block size of the two-level range min/max structure
 
 // One cell-list entry for the tiled bubble counts (16 bytes): offsets from the entry's own cell corner in degrees and
 // cos(dec) in fp32, plus the z-rank.  Differences between entries of neighbouring cells are then exact to ~1e-8 deg in

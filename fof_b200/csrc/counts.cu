@@ -54,7 +54,7 @@ __global__ void k_count_prep(CatalogView cat, Cosmo cosmo, double count_radius, 
 // (A variant that first located every galaxy's runs and then dealt the (galaxy, candidate) pairs of a 256-galaxy batch
 // evenly over the CTA was measured at 6.5 ms against 3.8 ms for this one at 10 M galaxies: the extra shared-memory
 // state cost a resident CTA per SM and two barriers per batch, more than the idle lanes it recovered.)
-__global__ void __launch_bounds__(kCtThreads, 4) k_count(CellListView cl, int nsx, const CountRec* __restrict__ rec,
+__global__ void __launch_bounds__(kCtThreads, kCtResident) k_count(CellListView cl, int nsx, const CountRec* __restrict__ rec,
                                                         const double4* __restrict__ box, int* __restrict__ N_row) {
   extern __shared__ __align__(128) unsigned char ct_smem[];
   __shared__ int s_cs[3][kCtW + 3];

@@ -719,7 +719,7 @@ __global__ void k_od_strip_starts(int nstrips, int nsx, int ncx, long long total
 // full-precision coordinates are fetched only by the few points that need them (a pair inside the fp32 band, a GriSPy
 // box that may bind).  The counts are not stored: D needs their sum and sum of squares per cluster (helper.py:216-221),
 // exact integers whatever the order, so each point adds its two terms to its cluster's accumulators.
-__global__ void __launch_bounds__(kCtThreads, 4) k_od_count(CellListView cl, int nsx, int npts, const int* __restrict__ qstart,
+__global__ void __launch_bounds__(kCtThreads, kCtResident) k_od_count(CellListView cl, int nsx, int npts, const int* __restrict__ qstart,
                                                             const unsigned* __restrict__ qkey, const PackedPoint* __restrict__ pay,
                                                             const OdCluster* __restrict__ oc, const double* __restrict__ rra,
                                                             const double* __restrict__ rdec, int grid_cells,

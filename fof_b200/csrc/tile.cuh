@@ -48,7 +48,23 @@ __device__ __forceinline__ int lower_bound_zr(const ZR* __restrict__ a, int lo, 
 // ---- one strip of cells and its neighbourhood ---------------------------------------------------------------------
 // A strip is kCtW consecutive cells of one cell row.  Its neighbourhood -- the same cells plus one on either side, in
 // the rows above, at and below -- is three contiguous slices of the cell-ordered packed records (PackedPoint, 16 bytes).
-constexpr int kCtW = 4, kCtThreads = 256, kCtMaxPts = 3072;
+// Tile geometry (overridable for sweeps: scripts/build_tile_variants.py).  Measured at 10 M galaxies (53 per cell, 212
+// per strip, 960 staged points on average, 1.3 % of the strips above 1 536): 128 threads and 28 KB per CTA keep seven
+// CTAs resident per SM -- k_count 2.99 ms against 3.80 ms with 256 threads, 3 072 points and four CTAs; 1 024 points
+// send a third of the strips down the global-memory path (3.41 ms), eight CTAs at 64 registers spill (3.50 ms).
+#ifndef FOFB_CT_W
+#define FOFB_CT_W 4
+#endif
+#ifndef FOFB_CT_THREADS
+#define FOFB_CT_THREADS 128
+#endif
+#ifndef FOFB_CT_MAXPTS
+#define FOFB_CT_MAXPTS 1536
+#endif
+#ifndef FOFB_CT_RESIDENT
+#define FOFB_CT_RESIDENT 7
+#endif
+constexpr int kCtW = FOFB_CT_W, kCtThreads = FOFB_CT_THREADS, kCtMaxPts = FOFB_CT_MAXPTS, kCtResident = FOFB_CT_RESIDENT;
 constexpr size_t kCtZtabBytes = (size_t)3 * (kCtW + 2) * kZBins * sizeof(unsigned short);
 constexpr size_t kCtSmemBytes = (size_t)kCtMaxPts * sizeof(PackedPoint) + kCtZtabBytes;
 constexpr float kHalfDeg2RadF = 0.00872664625997164788f;  // pi / 360
