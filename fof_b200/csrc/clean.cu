@@ -84,6 +84,35 @@ __device__ double np_pairwise_sum(F get, long long lo, long long n) {
   return np_pairwise_tree([&](long long l, long long c) -> double { return np_pairwise_leaf(get, l, c); }, lo, n);
 }
 
+// The same sum by one warp, bit for bit: numpy's eight strided accumulators of a block are one lane each, combined as
+// numpy combines them; the recursion above 128 elements is walked by every lane alike (its shape depends on n only).
+// All 32 lanes must call it with the same arguments; every lane gets the result.
+template <class F>
+__device__ __forceinline__ double warp_np_leaf(F get, long long lo, long long n, int lane) {  // n <= 128
+  if (n < 8) {
+    double res = 0.0;
+    for (long long i = 0; i < n; ++i) res = __dadd_rn(res, get(lo + i));
+    return res;
+  }
+  const long long body = n - (n % 8);
+  double r = 0.0;
+  if (lane < 8) {
+    r = get(lo + lane);
+    for (long long i = 8 + lane; i < body; i += 8) r = __dadd_rn(r, get(lo + i));
+  }
+  const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1), r2 = __shfl_sync(0xffffffffu, r, 2),
+               r3 = __shfl_sync(0xffffffffu, r, 3), r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5),
+               r6 = __shfl_sync(0xffffffffu, r, 6), r7 = __shfl_sync(0xffffffffu, r, 7);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+  for (long long i = body; i < n; ++i) res = __dadd_rn(res, get(lo + i));
+  return res;
+}
+
+template <class F>
+__device__ double warp_np_pairwise_sum(F get, long long n, int lane) {
+  return np_pairwise_tree([&](long long l, long long c) -> double { return warp_np_leaf(get, l, c, lane); }, 0, n);
+}
+
 // The same sum by a whole CTA, bit for bit: thread 0 lists the leaves of the recursion, the threads evaluate them
 // (each leaf is serial, as in numpy), thread 0 adds them up along the same tree.  Falls back to the serial walk when
 // the leaf table is too small.  All threads of the block must call it; the result is returned to every thread.
@@ -842,13 +871,35 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   for (int i = tid; i < kBootNum; i += kVirialThreads) boot[i] = 0.0;
   __syncthreads();
   auto getz = [&](long long i) -> double { return cached ? s_z[i] : M.at(s0 + i, 2); };
-  if (tid == 0) {
-    s_zbar = __ddiv_rn(np_pairwise_sum(getz, 0, n), (double)n);  // np.mean
+  // The numpy-ordered sums: a chain of dependent adds each, which used to leave 127 threads at a barrier behind thread
+  // 0.  Now warp 0 runs the pairwise sums with numpy's eight accumulators on eight lanes, every thread computes the
+  // v^2 terms (one division each) in between, and the sequential builtin sum() of velocity_error runs on warp 1
+  // beside the second pairwise sum.  Same operations in the same order: the results are bit-identical.
+  const int lane0 = tid & 31, warp0 = tid >> 5;
+  if (warp0 == 0) {
+    const double zsum = warp_np_pairwise_sum(getz, n, lane0);
+    if (lane0 == 0) s_zbar = __ddiv_rn(zsum, (double)n);  // np.mean
+  }
+  __syncthreads();
+  if (cached)
+    for (int i = tid; i < n; i += kVirialThreads) {
+      const double v = redshift_to_velocity(s_z[i], s_zbar);
+      sv2[i] = __dmul_rn(v, v);
+    }
+  __syncthreads();
+  if (warp0 == 0) {
     auto getv2 = [&](long long i) -> double {
+      if (cached) return sv2[i];
       const double v = redshift_to_velocity(getz(i), s_zbar);
       return __dmul_rn(v, v);
     };
-    s_vdisp = __ddiv_rn(np_pairwise_sum(getv2, 0, n), (double)(n - 1));  // np.sum(v**2)/(n-1)
+    const double vsum = warp_np_pairwise_sum(getv2, n, lane0);
+    if (lane0 == 0) {
+      s_vdisp = __ddiv_rn(vsum, (double)(n - 1));  // np.sum(v**2)/(n-1)
+      s_taken = 0;
+      s_fail = 0;
+    }
+  } else if (tid == 32) {
     // velocity_error: z_average_err = sqrt(sum(zerr**2)) / n   (builtin sum: sequential)
     double acc = 0.0;
     for (int i = 0; i < n; ++i) {
@@ -862,8 +913,6 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
       acc = __dadd_rn(acc, __dmul_rn(e, e));
     }
     s_zavg_err = __ddiv_rn(sqrt(acc), (double)n);
-    s_taken = 0;
-    s_fail = 0;
   }
   __syncthreads();
   const double zbar = s_zbar;
@@ -878,7 +927,6 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
     const double err = fabs(v) * sqrt(a * a + b * b);
     part += 1.0 / (err * err);
     mag += pow(10.0, -0.4 * M.at(s0 + i, 5));
-    if (cached) sv2[i] = v * v;
   }
   typedef cub::BlockReduce<double, kVirialThreads> Reduce;
   __shared__ typename Reduce::TempStorage rtmp;
@@ -988,17 +1036,23 @@ __global__ void __launch_bounds__(kVirialThreads) k_virial_mass(int K, const lon
   }
   }
   __syncthreads();
+  // statistic: sum(x^2) / (len(x) - 1) with len(x) = n - 1; np.std over the 100 values.  The divisions and the
+  // deviations are a thread each; the two sums stay sequential on thread 0, in the order they always had.
+  __shared__ double s_bmean;
+  for (int r = tid; r < kBootNum; r += kVirialThreads) boot[r] = boot[r] / (double)(n - 2);
+  __syncthreads();
+  if (tid == 0) {
+    double mean = 0.0;
+    for (int r = 0; r < kBootNum; ++r) mean += boot[r];
+    s_bmean = mean / kBootNum;
+  }
+  __syncthreads();
+  for (int r = tid; r < kBootNum; r += kVirialThreads) boot[r] = boot[r] - s_bmean;
+  __syncthreads();
   if (tid == 0) {
     if (s_taken < want) s_fail = 1;
-    // statistic: sum(x^2) / (len(x) - 1) with len(x) = n - 1; np.std over the 100 values
-    double mean = 0.0;
-    for (int r = 0; r < kBootNum; ++r) {
-      boot[r] = boot[r] / (double)(n - 2);
-      mean += boot[r];
-    }
-    mean /= kBootNum;
     double var = 0.0;
-    for (int r = 0; r < kBootNum; ++r) var += (boot[r] - mean) * (boot[r] - mean);
+    for (int r = 0; r < kBootNum; ++r) var = fma(boot[r], boot[r], var);
     const double bootstrap_disp = sqrt(var / kBootNum);
     const double harmonic = (1.0 / n) * (1.0 / inv_err_sum);
     const double combined = sqrt(harmonic * harmonic + bootstrap_disp * bootstrap_disp);
