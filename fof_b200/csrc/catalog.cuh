@@ -88,34 +88,6 @@ __device__ __forceinline__ void velocity_window(const double* zs, int n, double 
   *hi = a;
 }
 
-// The same window when the caller knows brackets for both ends: lo in [lo_a, lo_b], hi in [hi_a, hi_b] (the windows of
-// the first and the last of a run of z-ordered centres: both ends move forward with the centre's redshift).  The
-// brackets are checked against the predicate itself, so a bracket that does not hold (it always should) only costs the
-// full search; the result is the full search's in every case.
-__device__ __forceinline__ void velocity_window_bracketed(const double* zs, int n, double zc, double vmax, int lo_a, int lo_b,
-                                                          int hi_a, int hi_b, int* lo, int* hi) {
-  int a = lo_a, b = lo_b;
-  if (!(a <= b && (a == 0 || redshift_to_velocity(zs[a - 1], zc) < -vmax) && (b == n || !(redshift_to_velocity(zs[b], zc) < -vmax)))) {
-    a = 0;
-    b = n;
-  }
-  while (a < b) {  // first j with v >= -vmax
-    const int m = (a + b) >> 1;
-    if (redshift_to_velocity(zs[m], zc) < -vmax) a = m + 1; else b = m;
-  }
-  *lo = a;
-  int c = hi_a, d = hi_b;
-  if (!(c <= d && c >= a && (c == 0 || redshift_to_velocity(zs[c - 1], zc) <= vmax) && (d == n || !(redshift_to_velocity(zs[d], zc) <= vmax)))) {
-    c = a;
-    d = n;
-  }
-  while (c < d) {  // first j with v > vmax
-    const int m = (c + d) >> 1;
-    if (redshift_to_velocity(zs[m], zc) <= vmax) c = m + 1; else d = m;
-  }
-  *hi = c;
-}
-
 __device__ __forceinline__ double4 bbox_merge(double4 a, double4 b) {
   return make_double4(fmin(a.x, b.x), fmax(a.y, b.y), fmin(a.z, b.z), fmax(a.w, b.w));
 }

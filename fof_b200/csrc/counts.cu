@@ -17,24 +17,11 @@ namespace fofb {
 __global__ void k_count_prep(CatalogView cat, Cosmo cosmo, double count_radius, double vmax, int min_window,
                              int grid_cells, CountRec* rec, double4* box, double* theta_out) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  // Threads are z-ranks, so the windows of the CTA's first and last galaxy bracket everybody else's: two threads run
-  // the full binary searches (23 steps at 10 M galaxies), the others search the few hundred ranks in between.
-  __shared__ int s_w[4];
-  if (threadIdx.x < 2) {
-    const int r_first = blockIdx.x * blockDim.x;
-    const int r_last = (r_first + (int)blockDim.x < (int)cat.n ? r_first + (int)blockDim.x : (int)cat.n) - 1;
-    const int rr = threadIdx.x == 0 ? r_first : r_last;
-    int lo, hi;
-    velocity_window(cat.zs, (int)cat.n, cat.zs[rr], vmax, &lo, &hi);
-    s_w[threadIdx.x] = lo;
-    s_w[2 + threadIdx.x] = hi;
-  }
-  __syncthreads();
   if (r >= cat.n) return;
   const double z = cat.zs[r];
   const double theta = cosmo_linear_to_angular_dist(cosmo, count_radius, z);
   int lo, hi;
-  velocity_window_bracketed(cat.zs, (int)cat.n, z, vmax, s_w[0], s_w[1], s_w[2], s_w[3], &lo, &hi);
+  velocity_window(cat.zs, (int)cat.n, z, vmax, &lo, &hi);
   CountRec q;
   q.r_deg = theta;
   q.wlo = lo;
