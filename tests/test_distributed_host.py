@@ -77,6 +77,14 @@ assert a.tolist() == [1, 0, 1] and d.tolist() == [0, 1, 1]
 buf = torch.tensor([0, 2 * r, 1 - r, r], dtype=torch.uint8)
 c.allreduce_max_bytes(buf)
 assert buf.tolist() == [0, 2, 1, 1]
+# ragged tensors (exact sizes, no padding in the result) and the equal shares of the MT19937 stream
+t = c.allgatherv_t(torch.arange(3 * r + 1, dtype=torch.int64) + 100 * r)
+assert [x.tolist() for x in t] == [[0], [100, 101, 102, 103]]
+full = torch.zeros(8, dtype=torch.int32)
+work = c.allgather_shares(full, torch.arange(4, dtype=torch.int32) + 10 * r)
+if work is not None:
+    work.wait()
+assert full.tolist() == [0, 1, 2, 3, 10, 11, 12, 13]
 c.barrier()
 dist.destroy_process_group()
 print("ok", r)
@@ -126,6 +134,9 @@ def test_thread_comm_collectives_world3():
             state[4] = 1 if r == 1 else 0                                                  # only rank 1 still has work
             c.allreduce_max_bytes(state)
             assert state.tolist() == [1, 2, 2, 2, 1], state.tolist()
+            full = torch.zeros(6, dtype=torch.int32)                                       # MT19937 stream in equal shares
+            assert c.allgather_shares(full, torch.tensor([10 * r, 10 * r + 1], dtype=torch.int32)) is None
+            assert full.tolist() == [0, 1, 10, 11, 20, 21], full.tolist()
             c.barrier()
             results[r] = (g, t, s, mn, mx, alive.clone(), decided.clone())
         except Exception as e:  # noqa: BLE001
