@@ -144,19 +144,31 @@ struct Timed {  // CUDA-event bracket around one compute call
 
 using namespace fofb;
 
+// An entry point that fails returns while copies it enqueued may still be reading the caller's host buffers (pinned
+// memory: cudaMemcpyAsync is truly asynchronous) -- drain the handle's streams before handing the error back, so that
+// the caller may free or reuse its arrays as soon as any call has returned, failed or not.
+static void drain_after_error(fofb_handle* h) {
+  if (!h) return;
+  cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+}
+
 #define FOFB_TRY(h) try {
 #define FOFB_CATCH(h)                                              \
   }                                                                \
   catch (const fofb::Error& e) {                                   \
     if (h) (h)->last_error = e.what();                             \
+    drain_after_error(h);                                          \
     return e.code;                                                 \
   }                                                                \
   catch (const std::bad_alloc&) {                                  \
     if (h) (h)->last_error = "host allocation failed";             \
+    drain_after_error(h);                                          \
     return FOFB_ERR_INTERNAL;                                      \
   }                                                                \
   catch (const std::exception& e) {                                \
     if (h) (h)->last_error = std::string("internal: ") + e.what(); \
+    drain_after_error(h);                                          \
     return FOFB_ERR_INTERNAL;                                      \
   }
 
